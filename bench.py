@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- collider-updates/sec of the collision step (BASELINE.json metric).
+
+A "step" is one CollisionSystem::update (bvh_update + grid broadphase + narrowphase) over one frame of a
+synthetic collider field.  Workload: BASELINE.json configs[3] -- 16M mixed sphere/box colliders, clustered
+(Gaussian-blob) density, per-frame transform jitter -- which fits one B200.
+
+  value : whole-job collider-updates/s with the frame's transforms already resident in HBM
+  e2e   : same metric through the C ABI with HOST (pinned) transform arrays: H2D of the frame's
+          position+rotation arrays and D2H of the contact pairs inside the timed region
+  roofline : the dominant kernel's algorithmic bytes / its CUDA-event time vs the measured HBM peak
+  cpu_baseline / --impl reference : the CPU restatement of the reference algorithm (oracle/, 8 work
+          units on 8 threads as grid_collision.rs:104-105) on this box's host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "collider-updates/sec"
+UNIT = "collider-updates/s"
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_scene(cfg: int, n: int):
+    from gunship_rs_b200 import scenes
+    return scenes.by_config(cfg, n)
+
+
+def workload_name(cfg: int, n: int) -> str:
+    names = {1: "bench scene spheres", 2: "uniform spheres", 3: "mixed sphere+OBB uniform, per-frame jitter",
+             4: "mixed sphere+OBB, clustered Gaussian blobs, per-frame jitter", 5: "uniform spheres"}
+    return f"configs[{cfg - 1}]: {n} colliders, {names[cfg]}"
+
+
+def stage_bytes(n, f_box, n_cells, passes, n_pairs, n_so, n_oo, neigh_reads):
+    """Algorithmic HBM bytes per stage: every array a stage must read or write once."""
+    b = {}
+    # bvh_update: kind 1 + offset 12 + size 12 + pos 12 + entity 4 (+ quat 16 + scale 12 for boxes); writes rec 32 (+ obb 64)
+    b["bvh_update"] = n * (41 + 32) + n * f_box * (28 + 64)
+    # cell_keys: read rec 32, write key 4
+    b["cell_keys"] = n * 36
+    # sort: pass 0 reads key 4 writes 8; later passes read 8 write 8
+    b["sort"] = n * (12 + 16 * max(passes - 1, 0))
+    # cell table + permute: read key 4 + idx 4 + rec 32 (gather), write rec 32 + table 4 per cell
+    b["cell_table"] = n * 72 + n_cells * 4
+    # pairs: read sorted rec 32 + key 4 once (neighbour re-reads are served by L1/L2), table lookups, write pairs/candidates
+    b["pairs"] = n * 36 + n_pairs * 8 + (n_so + n_oo) * 8
+    # narrow: read candidates 8, sphere rec 32 + obb 64 / 2 x obb 64 per candidate, write hits
+    b["narrow"] = n_so * (8 + 96) + n_oo * (8 + 128)
+    return b
+
+
+def run_reference(args, scene, frames):
+    """--impl reference: the reference's CPU algorithm (oracle restatement; the Rust crate cannot be built here)."""
+    import oracle_lib as O
+    cores = min(8, os.cpu_count() or 1)
+    sysm = O.OracleSystem(8, cores)
+    times = []
+    for i in range(args.warmup + args.steps):
+        pos, quat = frames[i % len(frames)]
+        t0 = time.perf_counter()
+        sysm.bvh_update(scene.entity, scene.kind, scene.offset, scene.size, pos, quat, scene.scale)
+        sysm.grid_update()
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    sysm.close()
+    total = sum(times)
+    return scene.n * len(times) / total, 1e3 * total / len(times), cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=4)
+    ap.add_argument("--n", type=int, default=0, help="override the collider count (parity/dev runs only)")
+    ap.add_argument("--frames", type=int, default=3, help="distinct jittered frames cycled through")
+    ap.add_argument("--cpu-sample-n", type=int, default=0, help="collider count of the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    default_n = {1: 1000, 2: 1 << 20, 3: 1 << 22, 4: 1 << 24, 5: 1 << 26}[args.config]
+    n = args.n or default_n
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        # bounded sample: the reference path at 16M takes ~6 s/step on 8 threads; time it on a 2M-collider
+        # field from the same generator (same density, same mix) so K+W steps end within minutes
+        n_ref = args.cpu_sample_n or min(n, 1 << 21)
+        scene = make_scene(args.config, n_ref)
+        frames = [scene.frame(f) for f in range(min(args.frames, 2))]
+        value, ms, cores = run_reference(args, scene, frames)
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name(args.config, n),
+                           "sample": f"{n_ref} colliders of the same generator per step"},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": f"{args.steps} steps over {n_ref} colliders (same generator, density and mix)"},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the collision path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from gunship_rs_b200 import slabs
+        return slabs.bench_multi_gpu(args, n, rank, world, local_rank, METRIC, UNIT, workload_name, measured_peak_gbs,
+                                     ClockSampler)
+
+    from gunship_rs_b200 import context as G
+    scene = make_scene(args.config, n)
+    n = scene.n
+    nframes = max(1, args.frames)
+    # pinned host frames (what the engine's TransformManager would hold) and device-resident copies
+    h_pos = [torch.empty((n, 3), dtype=torch.float32, pin_memory=True) for _ in range(nframes)]
+    h_quat = [torch.empty((n, 4), dtype=torch.float32, pin_memory=True) for _ in range(nframes)]
+    for f in range(nframes):
+        pos, quat = scene.frame(f)
+        h_pos[f].numpy()[:] = pos
+        h_quat[f].numpy()[:] = quat
+    h_scale = torch.from_numpy(scene.scale).pin_memory()
+    d_pos = [t.cuda() for t in h_pos]
+    d_quat = [t.cuda() for t in h_quat]
+    d_scale = h_scale.cuda()
+
+    ctx = G.CollisionContext(n, device=local_rank, timing=True)
+    ctx.upload_colliders(scene.entity, scene.kind, scene.offset, scene.size)
+    f_box = float((scene.kind == 1).mean())
+
+    def step_resident(i):
+        f = i % nframes
+        ctx.bind_device_transforms(d_pos[f].data_ptr(), d_quat[f].data_ptr(), d_scale.data_ptr())
+        return ctx.step()
+
+    # ---- value: inputs resident in HBM ----
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    torch.cuda.synchronize()
+    dev_ms, stage_ms, outs = [], np.zeros(6), []
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        out = step_resident(args.warmup + i)
+        dev_ms.append(out.step_ms)
+        stage_ms += np.array(list(out.stage_ms))
+        outs.append((out.n_pairs, out.n_sphere_obb, out.n_obb_obb, out.n_cells, out.sort_passes))
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    stage_ms /= args.steps
+    ms_per_step = 1e3 * wall / args.steps
+    value = n * args.steps / wall
+
+    # ---- e2e: host transforms in, contact pairs out, through the C ABI ----
+    max_pairs = int(max(o[0] for o in outs))
+    h_pairs = torch.empty((max(max_pairs, 1) * 2 + 1024,), dtype=torch.int32, pin_memory=True)
+    import ctypes as C
+    lib = ctx._lib
+    npairs = C.c_uint64(0)
+
+    def step_e2e(i):
+        f = i % nframes
+        ctx.update_transforms_ptr(h_pos[f].data_ptr(), h_quat[f].data_ptr(), 0)
+        out = ctx.step()
+        rc = lib.gsc_download_pairs(ctx._h, h_pairs.data_ptr(), h_pairs.numel() // 2, 0, C.byref(npairs))
+        assert rc == 0, lib.gsc_last_error(ctx._h)
+        return out
+
+    ctx.update_transforms_ptr(h_pos[0].data_ptr(), h_quat[0].data_ptr(), h_scale.data_ptr())
+    for i in range(args.warmup):
+        step_e2e(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    d2h = 0
+    for i in range(args.steps):
+        out = step_e2e(args.warmup + i)
+        d2h += out.n_pairs * 8
+    torch.cuda.synchronize()
+    wall_e2e = time.perf_counter() - t0
+    e2e_value = n * args.steps / wall_e2e
+
+    # ---- roofline of the dominant kernel ----
+    peak, peak_kind = measured_peak_gbs()
+    mean = np.mean(np.array(outs, dtype=np.float64), axis=0)
+    from gunship_rs_b200._native import STAGE_NAMES
+    sb = stage_bytes(n, f_box, mean[3], int(mean[4]), mean[0], mean[1], mean[2], 0)
+    dom = int(np.argmax(stage_ms))
+    dom_name = STAGE_NAMES[dom]
+    launches_in_stage = {"sort": int(mean[4])}.get(dom_name, 1)
+    achieved = sb[dom_name] / (stage_ms[dom] * 1e-3) / 1e9
+    stages = {STAGE_NAMES[i]: {"ms": round(float(stage_ms[i]), 4), "alg_bytes": int(sb[STAGE_NAMES[i]]),
+                               "gbs": round(sb[STAGE_NAMES[i]] / max(stage_ms[i], 1e-9) / 1e6, 1)} for i in range(6)}
+    total_bytes = sum(sb.values())
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, n), "frames_cycled": nframes,
+                   "l2": "inputs larger than L2 (no flush needed)" if n * 100 > 126e6 else "inputs fit in L2",
+                   "box_fraction": round(f_box, 3), "contact_pairs_per_step": int(mean[0])},
+        "p50_step_ms": float(np.median(dev_ms)), "device_ms_per_step": float(np.mean(dev_ms)),
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": 1e3 * wall_e2e / args.steps,
+                "h2d_bytes_per_step": n * 28, "d2h_bytes_per_step": int(d2h / args.steps)},
+        "gpu_launches": 12 * args.steps,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                     "launches_per_step": launches_in_stage,
+                     "step_alg_bytes": int(total_bytes), "step_frac": total_bytes / (np.mean(dev_ms) * 1e-3) / 1e9 / peak},
+        "stages": stages,
+    }
+    ctx.close()
+    del d_pos, d_quat
+
+    if not args.no_cpu_baseline:
+        import oracle_lib as O
+        cores = min(8, os.cpu_count() or 1)
+        n_cpu = args.cpu_sample_n or min(n, 1 << 22)
+        cs = scene if n_cpu == n else make_scene(args.config, n_cpu)
+        sysm = O.OracleSystem(8, cores)
+        ts = []
+        for i in range(3):
+            pos, quat = (h_pos[i % nframes].numpy(), h_quat[i % nframes].numpy()) if n_cpu == n else cs.frame(i)
+            t0 = time.perf_counter()
+            sysm.bvh_update(cs.entity, cs.kind, cs.offset, cs.size, pos, quat, cs.scale)
+            sysm.grid_update()
+            ts.append(time.perf_counter() - t0)
+        sysm.close()
+        best = float(np.median(ts[1:]))
+        line["cpu_baseline"] = {"value": n_cpu / best, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"3 steps (first discarded) over {n_cpu} colliders of the same generator",
+                                "ms_per_step": 1e3 * best}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

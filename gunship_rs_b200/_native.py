@@ -1,0 +1,103 @@
+"""Loader + ctypes prototypes of libgunship_collision.so (include/gunship_collision.h).
+
+There is no CPU fallback: if the CUDA library is missing this module raises at import of the
+symbols, and gsc_create fails loudly when no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgunship_collision.so")
+
+GSC_OK, GSC_ERR_INVALID, GSC_ERR_CUDA, GSC_ERR_NCCL, GSC_ERR_CAPACITY, GSC_ERR_RANGE, GSC_ERR_KIND = range(7)
+GSC_SPHERE, GSC_BOX, GSC_MESH = 0, 1, 2
+GSC_FLAG_TIMING, GSC_FLAG_GRAPH = 1, 2
+GSC_NUM_STAGES = 6
+STAGE_NAMES = ("bvh_update", "cell_keys", "sort", "cell_table", "pairs", "narrow")
+(GSC_DBG_AABB, GSC_DBG_SORTED_KEYS, GSC_DBG_SORTED_IDX, GSC_DBG_CELL_START, GSC_DBG_OBB) = range(5)
+
+ERROR_NAMES = {GSC_ERR_INVALID: "GSC_ERR_INVALID", GSC_ERR_CUDA: "GSC_ERR_CUDA", GSC_ERR_NCCL: "GSC_ERR_NCCL",
+               GSC_ERR_CAPACITY: "GSC_ERR_CAPACITY", GSC_ERR_RANGE: "GSC_ERR_RANGE", GSC_ERR_KIND: "GSC_ERR_KIND"}
+
+
+class GscError(RuntimeError):
+    """A non-zero status from the C ABI (the reference panics in the same situations)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"{ERROR_NAMES.get(code, code)}: {message}")
+        self.code = code
+
+
+class GscConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_colliders", C.c_uint32), ("max_pairs", C.c_uint64),
+                ("max_candidates", C.c_uint64), ("max_cells", C.c_uint64), ("flags", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+class GscStepOut(C.Structure):
+    _fields_ = [("n_pairs", C.c_uint64), ("n_sphere_obb", C.c_uint64), ("n_obb_obb", C.c_uint64),
+                ("n_cells", C.c_uint64), ("cell_size", C.c_float), ("n_wide", C.c_uint32),
+                ("grid_origin", C.c_int32 * 3), ("grid_dims", C.c_int32 * 3), ("sort_passes", C.c_uint32),
+                ("status_flags", C.c_uint32), ("stage_ms", C.c_float * GSC_NUM_STAGES), ("step_ms", C.c_float),
+                ("d_pairs", C.c_void_p)]
+
+
+class GscBounds(C.Structure):
+    _fields_ = [("longest_axis", C.c_float), ("world_min", C.c_float * 3), ("world_max", C.c_float * 3),
+                ("status_flags", C.c_uint32)]
+
+
+# every symbol include/gunship_collision.h declares
+EXPORTS = (
+    "gsc_create", "gsc_destroy", "gsc_last_error", "gsc_abi_version", "gsc_upload_colliders",
+    "gsc_update_transforms", "gsc_bind_device_transforms", "gsc_step", "gsc_download_pairs", "gsc_debug_download",
+    "gsc_test_sphere_sphere", "gsc_test_sphere_obb", "gsc_test_obb_obb", "gsc_test_aabb_aabb", "gsc_fnv1a_gridcell",
+    "gsc_sort_pairs_u32", "gsc_phase_bounds", "gsc_set_global_bounds", "gsc_local_x_range", "gsc_halo_select",
+    "gsc_halo_append", "gsc_phase_finish",
+)
+
+_lib = None
+
+
+def load():
+    """dlopen the CUDA library; raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, u32p, u8p, f32p, u64p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
+    L.gsc_abi_version.restype = C.c_int
+    L.gsc_last_error.restype = C.c_char_p
+    L.gsc_last_error.argtypes = [vp]
+    L.gsc_create.argtypes = [C.POINTER(GscConfig), C.POINTER(vp)]
+    L.gsc_destroy.argtypes = [vp]
+    L.gsc_destroy.restype = None
+    L.gsc_upload_colliders.argtypes = [vp, C.c_uint32, u32p, u8p, f32p, f32p, u32p]
+    L.gsc_update_transforms.argtypes = [vp, C.c_uint32, f32p, f32p, f32p]
+    L.gsc_bind_device_transforms.argtypes = [vp, C.c_uint32, vp, vp, vp]
+    L.gsc_step.argtypes = [vp, C.POINTER(GscStepOut)]
+    L.gsc_download_pairs.argtypes = [vp, u32p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
+    L.gsc_debug_download.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.gsc_test_sphere_sphere.argtypes = [C.c_int, C.c_size_t, f32p, f32p, u8p]
+    L.gsc_test_sphere_obb.argtypes = [C.c_int, C.c_size_t, f32p, f32p, u8p]
+    L.gsc_test_obb_obb.argtypes = [C.c_int, C.c_size_t, f32p, f32p, u8p]
+    L.gsc_test_aabb_aabb.argtypes = [C.c_int, C.c_size_t, f32p, f32p, u8p]
+    L.gsc_fnv1a_gridcell.argtypes = [C.c_int, C.c_size_t, vp, u64p]
+    L.gsc_sort_pairs_u32.argtypes = [C.c_int, C.c_size_t, u32p, u32p, C.c_int]
+    L.gsc_phase_bounds.argtypes = [vp, C.POINTER(GscBounds)]
+    L.gsc_set_global_bounds.argtypes = [vp, C.POINTER(GscBounds)]
+    L.gsc_local_x_range.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.gsc_halo_select.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_uint32), C.POINTER(vp), C.POINTER(vp)]
+    L.gsc_halo_append.argtypes = [vp, C.c_uint32, vp, vp]
+    L.gsc_phase_finish.argtypes = [vp, C.POINTER(GscStepOut)]
+    for name in EXPORTS:
+        fn = getattr(L, name)  # raises AttributeError if the .so does not export it
+        if name not in ("gsc_destroy", "gsc_last_error"):
+            fn.restype = C.c_int
+    _lib = L
+    return L

@@ -1,0 +1,174 @@
+"""Thin object wrapper over the C ABI (one gsc_ctx per GPU).  Host arrays are numpy; nothing here
+computes -- every call forwards to libgunship_collision.so and raises GscError on a non-zero status."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from ._native import GscError
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def _c(a, dtype):
+    return None if a is None else np.ascontiguousarray(a, dtype=dtype)
+
+
+class CollisionContext:
+    """gsc_ctx: device buffers + the per-frame step for up to `max_colliders` colliders on one GPU."""
+
+    def __init__(self, max_colliders: int, device: int = 0, max_pairs: int = 0, max_candidates: int = 0,
+                 max_cells: int = 0, timing: bool = False):
+        self._lib = N.load()
+        cfg = N.GscConfig(device, max_colliders, max_pairs, max_candidates, max_cells,
+                          N.GSC_FLAG_TIMING if timing else 0, 0)
+        h = C.c_void_p()
+        rc = self._lib.gsc_create(C.byref(cfg), C.byref(h))
+        if rc != N.GSC_OK:
+            raise GscError(rc, self._lib.gsc_last_error(None).decode())
+        self._h = h
+        self.device = device
+        self.n = 0
+        self.last = None
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gsc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != N.GSC_OK:
+            raise GscError(rc, self._lib.gsc_last_error(self._h).decode())
+
+    # ColliderManager::assign over the dense array (mod.rs:221-223)
+    def upload_colliders(self, entity, kind, offset, size, global_index=None):
+        e, k = _c(entity, np.uint32), _c(kind, np.uint8)
+        o, s, g = _c(offset, np.float32), _c(size, np.float32), _c(global_index, np.uint32)
+        self.n = int(e.shape[0])
+        self._check(self._lib.gsc_upload_colliders(self._h, self.n, _ptr(e), _ptr(k), _ptr(o), _ptr(s), _ptr(g)))
+
+    def update_transforms(self, pos, quat=None, scale=None):
+        p, q, s = _c(pos, np.float32), _c(quat, np.float32), _c(scale, np.float32)
+        self._keep = [p, q, s]  # stay alive until the step has consumed them
+        self._check(self._lib.gsc_update_transforms(self._h, self.n, _ptr(p), _ptr(q), _ptr(s)))
+
+    def update_transforms_ptr(self, pos_ptr: int, quat_ptr: int = 0, scale_ptr: int = 0):
+        """Host pointers (e.g. pinned torch tensors' data_ptr()); arrays must outlive the next step()."""
+        self._check(self._lib.gsc_update_transforms(self._h, self.n, pos_ptr or None, quat_ptr or None, scale_ptr or None))
+
+    def bind_device_transforms(self, d_pos: int, d_quat: int = 0, d_scale: int = 0):
+        self._check(self._lib.gsc_bind_device_transforms(self._h, self.n, d_pos, d_quat or None, d_scale or None))
+
+    # CollisionSystem::update (mod.rs:590-611)
+    def step(self) -> N.GscStepOut:
+        out = N.GscStepOut()
+        rc = self._lib.gsc_step(self._h, C.byref(out))
+        self.last = out
+        self._check(rc)
+        return out
+
+    def pairs(self, sorted: bool = True) -> np.ndarray:
+        """(n,2) uint32: (entity of later volume, entity of earlier volume) -- grid_collision.rs:119,497."""
+        n = C.c_uint64(0)
+        self._check(self._lib.gsc_download_pairs(self._h, None, 0, 0, C.byref(n)))
+        out = np.zeros((int(n.value), 2), dtype=np.uint32)
+        if n.value:
+            self._check(self._lib.gsc_download_pairs(self._h, _ptr(out), n.value, 1 if sorted else 0, C.byref(n)))
+        return out
+
+    def pairs_packed(self, sorted: bool = True) -> np.ndarray:
+        p = self.pairs(sorted).astype(np.uint64)
+        return (p[:, 0] << np.uint64(32)) | p[:, 1]
+
+    def debug(self, what: int) -> np.ndarray:
+        n = self.n
+        if what == N.GSC_DBG_AABB:
+            out = np.zeros((n, 6), dtype=np.float32)
+        elif what == N.GSC_DBG_OBB:
+            out = np.zeros((n, 16), dtype=np.float32)
+        elif what == N.GSC_DBG_CELL_START:
+            out = np.zeros(int(self.last.n_cells) + 1, dtype=np.uint32)
+        else:
+            out = np.zeros(n, dtype=np.uint32)
+        self._check(self._lib.gsc_debug_download(self._h, what, _ptr(out), out.nbytes))
+        return out
+
+    # multi-GPU phases
+    def phase_bounds(self) -> N.GscBounds:
+        b = N.GscBounds()
+        self._check(self._lib.gsc_phase_bounds(self._h, C.byref(b)))
+        return b
+
+    def set_global_bounds(self, b: N.GscBounds):
+        self._check(self._lib.gsc_set_global_bounds(self._h, C.byref(b)))
+
+    def phase_finish(self) -> N.GscStepOut:
+        out = N.GscStepOut()
+        rc = self._lib.gsc_phase_finish(self._h, C.byref(out))
+        self.last = out
+        self._check(rc)
+        return out
+
+
+# ---- micro-bench batches (benches/collision.rs, benches/grid_collision.rs) ----
+
+def _batch(fn_name, a, b, a_dtype, out_dtype, device=0):
+    L = N.load()
+    a = np.ascontiguousarray(a, dtype=a_dtype)
+    n = a.shape[0]
+    out = np.zeros(n, dtype=out_dtype)
+    if b is not None:
+        b = np.ascontiguousarray(b, dtype=a_dtype)
+        rc = getattr(L, fn_name)(device, n, _ptr(a), _ptr(b), _ptr(out))
+    else:
+        rc = getattr(L, fn_name)(device, n, _ptr(a), _ptr(out))
+    if rc != N.GSC_OK:
+        raise GscError(rc, L.gsc_last_error(None).decode())
+    return out
+
+
+def test_sphere_sphere(a4, b4, device=0):
+    return _batch("gsc_test_sphere_sphere", a4, b4, np.float32, np.uint8, device)
+
+
+def test_sphere_obb(s4, obb16, device=0):
+    return _batch("gsc_test_sphere_obb", s4, obb16, np.float32, np.uint8, device)
+
+
+def test_obb_obb(a16, b16, device=0):
+    return _batch("gsc_test_obb_obb", a16, b16, np.float32, np.uint8, device)
+
+
+def test_aabb_aabb(a6, b6, device=0):
+    return _batch("gsc_test_aabb_aabb", a6, b6, np.float32, np.uint8, device)
+
+
+def fnv1a_gridcell(cells3, device=0):
+    return _batch("gsc_fnv1a_gridcell", cells3, None, np.int16, np.uint64, device)
+
+
+def sort_pairs_u32(keys, vals, key_bits=32, device=0):
+    L = N.load()
+    k = np.array(keys, dtype=np.uint32, copy=True)
+    v = np.array(vals, dtype=np.uint32, copy=True)
+    rc = L.gsc_sort_pairs_u32(device, k.shape[0], _ptr(k), _ptr(v), key_bits)
+    if rc != N.GSC_OK:
+        raise GscError(rc, L.gsc_last_error(None).decode())
+    return k, v

@@ -1,0 +1,691 @@
+// gsc_api.cu -- the C ABI of include/gunship_collision.h: context, buffers, stage orchestration.
+//
+// A step is a fixed sequence of kernel launches on one stream with NO host round trip in the middle:
+// data-dependent quantities (cell size, grid extent, number of radix passes, candidate counts) stay in
+// a device-side control block (FrameBlock) that later kernels read, and the host reads it back once
+// at the end together with the pair count.
+#include "../../include/gunship_collision.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "gsc_kernels.cuh"
+
+using namespace gsc;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr int kGridStrideBlocks = 148 * 8;  // 148 SMs x resident CTAs for the grid-stride kernels
+
+struct Buf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct gsc_ctx {
+    gsc_config cfg{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    std::string err;
+
+    uint32_t cap = 0;       // max colliders (local + ghost)
+    uint32_t n_local = 0;   // uploaded colliders
+    uint32_t n_ghost = 0;   // ghosts appended this step
+    bool have_colliders = false, have_transforms = false, have_gidx = false;
+
+    // static collider data + transforms (SoA, as uploaded)
+    uint32_t *d_entity = nullptr, *d_gidx = nullptr;
+    uint8_t *d_kind = nullptr;
+    float *d_offset = nullptr, *d_size = nullptr;
+    float *d_pos = nullptr, *d_quat = nullptr, *d_scale = nullptr;          // owned
+    const float *b_pos = nullptr, *b_quat = nullptr, *b_scale = nullptr;    // in use (owned or bound)
+
+    // per-step buffers
+    float4 *d_rec = nullptr, *d_rec_sorted = nullptr, *d_obb = nullptr;
+    uint32_t *d_keys[2] = { nullptr, nullptr }, *d_vals[2] = { nullptr, nullptr };
+    uint32_t *d_cell_start = nullptr, *d_wide = nullptr;
+    uint2 *d_pairs = nullptr, *d_cand_so = nullptr, *d_cand_oo = nullptr;
+    uint2 *d_pairs_sorted = nullptr;
+    FrameBlock *d_fb = nullptr;
+    FrameBlock *h_fb = nullptr;  // pinned
+    uint32_t *d_lookback = nullptr;
+    uint32_t lookback_tiles = 0;
+    // halo staging
+    float4 *d_halo_rec = nullptr, *d_halo_obb = nullptr;
+    uint32_t *d_halo_count = nullptr;
+    uint32_t halo_cap = 0;
+
+    uint64_t max_pairs = 0, max_cands = 0, max_cells = 0;
+    uint64_t last_pairs = 0;
+    bool bounds_done = false, global_bounds_set = false;
+
+    cudaEvent_t ev[GSC_NUM_STAGES + 1] = {};
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+};
+
+namespace {
+
+int fail(gsc_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CU(c, expr)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e_ = (expr);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail((c), GSC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T>
+cudaError_t dmalloc(T **p, size_t count)
+{
+    return cudaMalloc((void **)p, std::max<size_t>(count, 1) * sizeof(T));
+}
+
+__global__ void k_fill_default_transforms(uint32_t n, float *quat4, float *scale3)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    quat4[4 * (size_t)i] = 0.f; quat4[4 * (size_t)i + 1] = 0.f; quat4[4 * (size_t)i + 2] = 0.f; quat4[4 * (size_t)i + 3] = 1.f;
+    scale3[3 * (size_t)i] = 1.f; scale3[3 * (size_t)i + 1] = 1.f; scale3[3 * (size_t)i + 2] = 1.f;
+}
+
+// AABB::from_collider as the records encode it, expanded to (min xyz, max xyz) for parity read-back
+__global__ void k_decode_aabb(uint32_t n, const float4 *rec, float *out6)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Volume v = volume_decode(rec[2 * (size_t)i], rec[2 * (size_t)i + 1]);
+    for (int a = 0; a < 3; ++a) { out6[6 * (size_t)i + a] = v.mn[a]; out6[6 * (size_t)i + 3 + a] = v.mx[a]; }
+}
+
+inline uint32_t tiles_for(uint32_t n) { return (n + kSortTile - 1) / kSortTile; }
+
+// Runs the radix passes on `n` (key, value) pairs.  Passes beyond ctl->num_passes exit on the device.
+void launch_sort(cudaStream_t s, uint32_t n, uint32_t *keys[2], uint32_t *vals[2], bool first_vals_identity,
+                 int max_passes, const SortControl *ctl, const uint32_t *hist, uint32_t *lookback,
+                 uint32_t *tile_counter)
+{
+    const uint32_t tiles = tiles_for(n);
+    if (tiles == 0) return;
+    for (int pass = 0; pass < max_passes; ++pass) {
+        const int in = pass & 1, out = in ^ 1;
+        const uint32_t *vin = (pass == 0 && first_vals_identity) ? nullptr : vals[in];
+        k_onesweep_pass<<<tiles, kSortThreads, 0, s>>>(keys[in], vin, keys[out], vals[out], n, pass, ctl, hist, lookback,
+                                                      tile_counter, tiles);
+    }
+}
+
+int check_ctx(gsc_ctx *c)
+{
+    if (!c) return GSC_ERR_INVALID;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return fail(c, GSC_ERR_CUDA, "cudaSetDevice(%d): %s", c->device, cudaGetErrorString(e));
+    return GSC_OK;
+}
+
+int status_to_error(gsc_ctx *c, const FrameBlock &fb)
+{
+    const uint32_t st = fb.status;
+    if (st & kStMesh) return fail(c, GSC_ERR_KIND, "Collider::Mesh is not supported (unimplemented!() in the reference, mod.rs:331)");
+    if (st & kStNonFinite) return fail(c, GSC_ERR_RANGE, "a collider produced a NaN/Inf bounding box");
+    if (st & kStCellSize) return fail(c, GSC_ERR_RANGE, "cell size (longest AABB axis) is not positive: %g", (double)fb.grid.cell_size);
+    if (st & kStRange) return fail(c, GSC_ERR_RANGE, "a grid coordinate leaves the i16 range of GridCoord (grid_collision.rs:535)");
+    if (st & kStCells) return fail(c, GSC_ERR_CAPACITY, "dense cell table too small: raise gsc_config.max_cells (have %llu)", (unsigned long long)c->max_cells);
+    return GSC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gsc_abi_version(void) { return GSC_ABI_VERSION; }
+
+const char *gsc_last_error(const gsc_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int gsc_create(const gsc_config *cfg, gsc_ctx **out)
+{
+    if (!cfg || !out) return fail(nullptr, GSC_ERR_INVALID, "gsc_create: null argument");
+    *out = nullptr;
+    if (cfg->max_colliders >= (1u << 28)) return fail(nullptr, GSC_ERR_INVALID, "max_colliders must be < 2^28");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, GSC_ERR_CUDA, "no CUDA device: %s -- this library has no CPU fallback", cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, GSC_ERR_INVALID, "device %d out of range", cfg->device);
+    gsc_ctx *c = new gsc_ctx();
+    c->cfg = *cfg;
+    c->device = cfg->device;
+    c->cap = std::max<uint32_t>(cfg->max_colliders, 1);
+    c->max_pairs = cfg->max_pairs ? cfg->max_pairs : 8ull * c->cap + 65536;
+    c->max_cands = cfg->max_candidates ? cfg->max_candidates : 8ull * c->cap + 65536;
+    c->max_cells = cfg->max_cells ? cfg->max_cells : 16ull * c->cap + (1ull << 20);
+    c->max_cells = std::min<uint64_t>(c->max_cells, (1ull << 31) - 2);
+    const size_t M = c->cap;
+    c->lookback_tiles = tiles_for(c->cap);
+#define CR(expr)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e2_ = (expr);                                                                    \
+        if (e2_ != cudaSuccess) {                                                                    \
+            fail(nullptr, GSC_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e2_));            \
+            gsc_destroy(c);                                                                          \
+            return GSC_ERR_CUDA;                                                                     \
+        }                                                                                            \
+    } while (0)
+    CR(cudaSetDevice(c->device));
+    CR(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CR(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CR(dmalloc(&c->d_entity, M));
+    CR(dmalloc(&c->d_gidx, M));
+    CR(dmalloc(&c->d_kind, M));
+    CR(dmalloc(&c->d_offset, 3 * M));
+    CR(dmalloc(&c->d_size, 3 * M));
+    CR(dmalloc(&c->d_pos, 3 * M));
+    CR(dmalloc(&c->d_quat, 4 * M));
+    CR(dmalloc(&c->d_scale, 3 * M));
+    CR(dmalloc(&c->d_rec, 2 * M));
+    CR(dmalloc(&c->d_rec_sorted, 2 * M));
+    CR(dmalloc(&c->d_obb, 4 * M));
+    for (int i = 0; i < 2; ++i) {
+        CR(dmalloc(&c->d_keys[i], M));
+        CR(dmalloc(&c->d_vals[i], M));
+    }
+    CR(dmalloc(&c->d_cell_start, c->max_cells + 2));
+    CR(dmalloc(&c->d_wide, M));
+    CR(dmalloc(&c->d_pairs, c->max_pairs));
+    CR(dmalloc(&c->d_cand_so, c->max_cands));
+    CR(dmalloc(&c->d_cand_oo, c->max_cands));
+    CR(dmalloc(&c->d_fb, 1));
+    CR(dmalloc(&c->d_lookback, (size_t)kMaxPasses * c->lookback_tiles * kRadix));
+    CR(dmalloc(&c->d_halo_count, 1));
+    CR(cudaHostAlloc((void **)&c->h_fb, sizeof(FrameBlock), cudaHostAllocDefault));
+    for (auto &ev : c->ev) CR(cudaEventCreate(&ev));
+    CR(cudaEventCreate(&c->ev_begin));
+    CR(cudaEventCreate(&c->ev_end));
+    // identity quaternion / unit scale so a sphere-only caller may pass NULL for them
+    k_fill_default_transforms<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>((uint32_t)M, c->d_quat, c->d_scale);
+    CR(cudaGetLastError());
+    CR(cudaStreamSynchronize(c->stream));
+#undef CR
+    c->b_pos = c->d_pos;
+    c->b_quat = c->d_quat;
+    c->b_scale = c->d_scale;
+    *out = c;
+    return GSC_OK;
+}
+
+void gsc_destroy(gsc_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    void *bufs[] = { c->d_entity, c->d_gidx, c->d_kind, c->d_offset, c->d_size, c->d_pos, c->d_quat, c->d_scale, c->d_rec,
+                     c->d_rec_sorted, c->d_obb, c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1], c->d_cell_start,
+                     c->d_wide, c->d_pairs, c->d_cand_so, c->d_cand_oo, c->d_pairs_sorted, c->d_fb, c->d_lookback,
+                     c->d_halo_rec, c->d_halo_obb, c->d_halo_count };
+    for (void *b : bufs)
+        if (b) cudaFree(b);
+    if (c->h_fb) cudaFreeHost(c->h_fb);
+    for (auto &ev : c->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (c->ev_begin) cudaEventDestroy(c->ev_begin);
+    if (c->ev_end) cudaEventDestroy(c->ev_end);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+int gsc_upload_colliders(gsc_ctx *c, uint32_t n, const uint32_t *entity, const uint8_t *kind, const float *offset3,
+                         const float *size3, const uint32_t *global_index)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (n > c->cap) return fail(c, GSC_ERR_CAPACITY, "gsc_upload_colliders: %u colliders > max_colliders %u", n, c->cap);
+    if (n && (!entity || !kind || !offset3 || !size3)) return fail(c, GSC_ERR_INVALID, "gsc_upload_colliders: null array");
+    for (uint32_t i = 0; i < n; ++i)
+        if (kind[i] > GSC_BOX)
+            return fail(c, GSC_ERR_KIND, "collider %u is a Mesh: unimplemented!() in the reference (mod.rs:331)", i);
+    if (n) {
+        CU(c, cudaMemcpyAsync(c->d_entity, entity, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->d_kind, kind, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->d_offset, offset3, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->d_size, size3, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+        if (global_index) CU(c, cudaMemcpyAsync(c->d_gidx, global_index, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->n_local = n;
+    c->have_gidx = global_index != nullptr;
+    c->have_colliders = true;
+    c->have_transforms = false;
+    return GSC_OK;
+}
+
+int gsc_update_transforms(gsc_ctx *c, uint32_t n, const float *pos3, const float *quat4, const float *scale3)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!c->have_colliders || n != c->n_local)
+        return fail(c, GSC_ERR_INVALID, "gsc_update_transforms: n=%u does not match the %u uploaded colliders", n, c->n_local);
+    if (n && !pos3) return fail(c, GSC_ERR_INVALID, "gsc_update_transforms: null positions");
+    if (n) {
+        // the three arrays go over two streams so the copies overlap on the two DMA engines
+        CU(c, cudaMemcpyAsync(c->d_pos, pos3, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+        if (quat4) CU(c, cudaMemcpyAsync(c->d_quat, quat4, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+        if (scale3) CU(c, cudaMemcpyAsync(c->d_scale, scale3, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+    }
+    c->b_pos = c->d_pos;
+    c->b_quat = c->d_quat;
+    c->b_scale = c->d_scale;
+    c->have_transforms = true;
+    return GSC_OK;
+}
+
+int gsc_bind_device_transforms(gsc_ctx *c, uint32_t n, const float *d_pos3, const float *d_quat4, const float *d_scale3)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!c->have_colliders || n != c->n_local)
+        return fail(c, GSC_ERR_INVALID, "gsc_bind_device_transforms: n=%u does not match the %u uploaded colliders", n, c->n_local);
+    if (n && !d_pos3) return fail(c, GSC_ERR_INVALID, "gsc_bind_device_transforms: null positions");
+    if (d_quat4 && (reinterpret_cast<uintptr_t>(d_quat4) & 15))
+        return fail(c, GSC_ERR_INVALID, "gsc_bind_device_transforms: quaternions must be 16-byte aligned");
+    c->b_pos = d_pos3;
+    c->b_quat = d_quat4 ? d_quat4 : c->d_quat;
+    c->b_scale = d_scale3 ? d_scale3 : c->d_scale;
+    c->have_transforms = true;
+    return GSC_OK;
+}
+
+// ---- stages ------------------------------------------------------------------------------------------
+
+static int stage_bounds(gsc_ctx *c)
+{
+    if (!c->have_colliders || !c->have_transforms)
+        return fail(c, GSC_ERR_INVALID, "step before colliders and transforms were provided");
+    cudaStream_t s = c->stream;
+    CU(c, cudaEventRecord(c->ev_begin, s));
+    CU(c, cudaMemsetAsync(c->d_fb, 0, sizeof(FrameBlock), s));
+    c->n_ghost = 0;
+    const bool timing = c->cfg.flags & GSC_FLAG_TIMING;
+    if (timing) CU(c, cudaEventRecord(c->ev[0], s));
+    if (c->n_local) {
+        const uint32_t blocks = (c->n_local + kBvhThreads - 1) / kBvhThreads;
+        k_bvh_update<<<blocks, kBvhThreads, 0, s>>>(c->n_local, c->d_kind, c->d_offset, c->d_size, c->b_pos, c->b_quat,
+                                                   c->b_scale, c->d_entity, c->have_gidx ? c->d_gidx : nullptr, c->d_rec,
+                                                   c->d_obb, c->d_fb);
+    }
+    CU(c, cudaGetLastError());
+    if (timing) CU(c, cudaEventRecord(c->ev[1], s));
+    c->bounds_done = true;
+    c->global_bounds_set = false;
+    return GSC_OK;
+}
+
+static int stage_finish(gsc_ctx *c, gsc_step_out *out)
+{
+    cudaStream_t s = c->stream;
+    const bool timing = c->cfg.flags & GSC_FLAG_TIMING;
+    const uint32_t n_total = c->n_local + c->n_ghost;
+    FrameBlock *fb = c->d_fb;
+    CU(c, cudaMemsetAsync(c->d_lookback, 0, (size_t)kMaxPasses * tiles_for(n_total) * kRadix * sizeof(uint32_t), s));
+    k_grid_setup<<<1, 32, 0, s>>>(fb, c->max_cells, n_total);
+    if (n_total) {
+        const uint32_t kb = std::min<uint32_t>((n_total + kKeyThreads - 1) / kKeyThreads, kGridStrideBlocks);
+        k_cell_keys<<<kb, kKeyThreads, 0, s>>>(n_total, c->d_rec, c->d_keys[0], c->d_wide, fb);
+        if (timing) CU(c, cudaEventRecord(c->ev[2], s));
+        launch_sort(s, n_total, c->d_keys, c->d_vals, true, kMaxPasses, &fb->sort, &fb->hist[0][0], c->d_lookback,
+                    fb->tile_counter);
+        if (timing) CU(c, cudaEventRecord(c->ev[3], s));
+        const uint32_t tb = (n_total + 1 + kTableThreads - 1) / kTableThreads;
+        k_cell_table_permute<<<tb, kTableThreads, 0, s>>>(n_total, c->d_keys[0], c->d_vals[0], c->d_keys[1], c->d_vals[1],
+                                                         c->d_rec, c->d_rec_sorted, c->d_cell_start, fb);
+        if (timing) CU(c, cudaEventRecord(c->ev[4], s));
+        PairOut po{ c->d_pairs, c->d_cand_so, c->d_cand_oo, c->max_pairs, c->max_cands };
+        const uint32_t pb = (n_total + kPairThreads - 1) / kPairThreads;
+        k_pairs<<<pb, kPairThreads, 0, s>>>(n_total, c->d_keys[0], c->d_keys[1], c->d_rec_sorted, c->d_cell_start, po, fb);
+        if (timing) CU(c, cudaEventRecord(c->ev[5], s));
+        k_narrow_sphere_obb<<<kGridStrideBlocks, kNarrowThreads, 0, s>>>(c->d_cand_so, c->max_cands, c->d_rec, c->d_obb,
+                                                                       c->d_pairs, c->max_pairs, fb);
+        k_narrow_obb_obb<<<kGridStrideBlocks, kNarrowThreads, 0, s>>>(c->d_cand_oo, c->max_cands, c->d_obb, c->d_pairs,
+                                                                    c->max_pairs, fb);
+        k_wide_pairs<<<kGridStrideBlocks, kNarrowThreads, 0, s>>>(c->n_local, c->d_wide, c->d_rec, c->d_obb, c->d_pairs,
+                                                                c->max_pairs, fb);
+        if (timing) CU(c, cudaEventRecord(c->ev[6], s));
+    } else if (timing) {
+        for (int i = 2; i <= GSC_NUM_STAGES; ++i) CU(c, cudaEventRecord(c->ev[i], s));
+    }
+    CU(c, cudaGetLastError());
+    CU(c, cudaMemcpyAsync(c->h_fb, fb, sizeof(FrameBlock), cudaMemcpyDeviceToHost, s));
+    CU(c, cudaEventRecord(c->ev_end, s));
+    CU(c, cudaStreamSynchronize(s));
+    c->bounds_done = false;
+
+    const FrameBlock &h = *c->h_fb;
+    c->last_pairs = std::min<uint64_t>(h.n_pairs, c->max_pairs);
+    if (out) {
+        memset(out, 0, sizeof *out);
+        out->n_pairs = h.n_pairs;
+        out->n_sphere_obb = h.n_so;
+        out->n_obb_obb = h.n_oo;
+        out->n_cells = h.grid.num_cells;
+        out->cell_size = h.grid.cell_size;
+        out->n_wide = h.n_wide;
+        for (int a = 0; a < 3; ++a) {
+            out->grid_origin[a] = h.grid.origin[a];
+            out->grid_dims[a] = h.grid.dims[a];
+        }
+        out->sort_passes = (uint32_t)h.sort.num_passes;
+        out->status_flags = h.status;
+        out->d_pairs = reinterpret_cast<const uint32_t *>(c->d_pairs);
+        cudaEventElapsedTime(&out->step_ms, c->ev_begin, c->ev_end);
+        if (timing)
+            for (int i = 0; i < GSC_NUM_STAGES; ++i) cudaEventElapsedTime(&out->stage_ms[i], c->ev[i], c->ev[i + 1]);
+    }
+    if (int rc = status_to_error(c, h)) { c->last_pairs = 0; return rc; }
+    if (h.n_so > c->max_cands || h.n_oo > c->max_cands)
+        return fail(c, GSC_ERR_CAPACITY, "candidate list overflow: need %llu / %llu, have %llu (gsc_config.max_candidates)",
+                    (unsigned long long)h.n_so, (unsigned long long)h.n_oo, (unsigned long long)c->max_cands);
+    if (h.n_pairs > c->max_pairs)
+        return fail(c, GSC_ERR_CAPACITY, "pair buffer overflow: need %llu, have %llu (gsc_config.max_pairs)",
+                    (unsigned long long)h.n_pairs, (unsigned long long)c->max_pairs);
+    return GSC_OK;
+}
+
+int gsc_step(gsc_ctx *c, gsc_step_out *out)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (int rc = stage_bounds(c)) return rc;
+    return stage_finish(c, out);
+}
+
+int gsc_phase_bounds(gsc_ctx *c, gsc_bounds *local)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!local) return fail(c, GSC_ERR_INVALID, "gsc_phase_bounds: null output");
+    if (int rc = stage_bounds(c)) return rc;
+    CU(c, cudaMemcpyAsync(c->h_fb, c->d_fb, sizeof(FrameBlock), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    const FrameBlock &h = *c->h_fb;
+    local->status_flags = h.status;
+    if (c->n_local == 0 || h.bounds[0] == 0) {
+        local->longest_axis = 0.0f;
+        for (int a = 0; a < 3; ++a) { local->world_min[a] = INFINITY; local->world_max[a] = -INFINITY; }
+    } else {
+        local->longest_axis = ord2f(h.bounds[0]);
+        for (int a = 0; a < 3; ++a) {
+            local->world_min[a] = ord2f(~h.bounds[1 + a]);
+            local->world_max[a] = ord2f(h.bounds[4 + a]);
+        }
+    }
+    return GSC_OK;
+}
+
+static uint32_t host_f2ord(float f)
+{
+    uint32_t b;
+    memcpy(&b, &f, 4);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+int gsc_set_global_bounds(gsc_ctx *c, const gsc_bounds *g)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!g || !c->bounds_done) return fail(c, GSC_ERR_INVALID, "gsc_set_global_bounds: call gsc_phase_bounds first");
+    uint32_t enc[8] = { 0 };
+    enc[0] = host_f2ord(g->longest_axis);
+    for (int a = 0; a < 3; ++a) {
+        enc[1 + a] = ~host_f2ord(g->world_min[a]);
+        enc[4 + a] = host_f2ord(g->world_max[a]);
+    }
+    CU(c, cudaMemcpyAsync(c->d_fb, enc, sizeof enc, cudaMemcpyHostToDevice, c->stream));
+    if (g->status_flags) CU(c, cudaMemcpyAsync(&c->d_fb->status, &g->status_flags, 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));  // enc lives on this stack frame
+    c->global_bounds_set = true;
+    return GSC_OK;
+}
+
+int gsc_phase_finish(gsc_ctx *c, gsc_step_out *out)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!c->bounds_done) return fail(c, GSC_ERR_INVALID, "gsc_phase_finish: call gsc_phase_bounds first");
+    return stage_finish(c, out);
+}
+
+int gsc_local_x_range(gsc_ctx *c, int32_t *, int32_t *) { return fail(c, GSC_ERR_INVALID, "gsc_local_x_range: not built yet"); }
+int gsc_halo_select(gsc_ctx *c, int32_t, int32_t, uint32_t *, const void **, const void **) { return fail(c, GSC_ERR_INVALID, "gsc_halo_select: not built yet"); }
+int gsc_halo_append(gsc_ctx *c, uint32_t, const void *, const void *) { return fail(c, GSC_ERR_INVALID, "gsc_halo_append: not built yet"); }
+
+// ---- results -----------------------------------------------------------------------------------------
+
+}  // extern "C"
+
+namespace {
+__global__ void k_extract_field(const uint2 *pairs, const uint32_t *perm, uint32_t n, int field, uint32_t *out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint2 p = pairs[perm ? perm[i] : i];
+    out[i] = field ? p.y : p.x;
+}
+__global__ void k_gather_pairs(const uint2 *pairs, const uint32_t *perm, uint32_t n, uint2 *out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = pairs[perm[i]];
+}
+
+// standalone sort of n (key,value) pairs with full control over its scratch; result lands in buffer index *which
+int sort_standalone(gsc_ctx *c, cudaStream_t s, uint32_t n, uint32_t *keys[2], uint32_t *vals[2], bool identity, int key_bits,
+                    int *which)
+{
+    const int passes = radix_passes(key_bits);
+    *which = passes & 1;
+    if (n == 0 || passes == 0) { *which = 0; return GSC_OK; }
+    const uint32_t tiles = tiles_for(n);
+    uint32_t *scratch = nullptr;  // [hist 4*256][tile_counter 4][ctl 1][pad 3][lookback 4*tiles*256]
+    const size_t words = (size_t)kMaxPasses * kRadix + 8 + (size_t)kMaxPasses * tiles * kRadix;
+    CU(c, cudaMalloc((void **)&scratch, words * 4));
+    CU(c, cudaMemsetAsync(scratch, 0, words * 4, s));
+    uint32_t *hist = scratch, *tile_counter = scratch + kMaxPasses * kRadix;
+    SortControl *ctl = reinterpret_cast<SortControl *>(tile_counter + 4);
+    uint32_t *lookback = tile_counter + 8;
+    SortControl h{ passes };
+    CU(c, cudaMemcpyAsync(ctl, &h, sizeof h, cudaMemcpyHostToDevice, s));
+    const uint32_t hb = std::min<uint32_t>((n + 255) / 256, kGridStrideBlocks);
+    k_radix_histogram<<<hb, 256, 0, s>>>(keys[0], n, passes, hist);
+    launch_sort(s, n, keys, vals, identity, passes, ctl, hist, lookback, tile_counter);
+    CU(c, cudaGetLastError());
+    CU(c, cudaStreamSynchronize(s));
+    cudaFree(scratch);
+    return GSC_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int gsc_download_pairs(gsc_ctx *c, uint32_t *dst, uint64_t cap_pairs, int sorted, uint64_t *n_out)
+{
+    if (int rc = check_ctx(c)) return rc;
+    const uint64_t n = c->last_pairs;
+    if (n_out) *n_out = n;
+    if (n == 0 || (!dst && cap_pairs == 0)) return GSC_OK;  // (NULL, 0) only queries the count
+    if (!dst || cap_pairs < n) return fail(c, GSC_ERR_CAPACITY, "gsc_download_pairs: need room for %llu pairs", (unsigned long long)n);
+    cudaStream_t s = c->stream;
+    const uint2 *src = c->d_pairs;
+    if (sorted) {
+        if (n >= (1ull << 30)) return fail(c, GSC_ERR_CAPACITY, "sorted download supports < 2^30 pairs");
+        // LSD over the 64-bit tuple with the 32-bit sort: second entity first, then (stable) the first
+        const uint32_t m = (uint32_t)n;
+        uint32_t *k[2] = { nullptr, nullptr }, *v[2] = { nullptr, nullptr };
+        for (int i = 0; i < 2; ++i) {
+            CU(c, dmalloc(&k[i], m));
+            CU(c, dmalloc(&v[i], m));
+        }
+        if (!c->d_pairs_sorted) CU(c, dmalloc(&c->d_pairs_sorted, c->max_pairs));
+        const uint32_t blocks = (m + 255) / 256;
+        int w1 = 0, w2 = 0;
+        k_extract_field<<<blocks, 256, 0, s>>>(c->d_pairs, nullptr, m, 1, k[0]);
+        int rc = sort_standalone(c, s, m, k, v, true, 32, &w1);
+        if (rc == GSC_OK) {
+            if (w1 != 0) { std::swap(k[0], k[1]); std::swap(v[0], v[1]); }
+            k_extract_field<<<blocks, 256, 0, s>>>(c->d_pairs, v[0], m, 0, k[0]);
+            rc = sort_standalone(c, s, m, k, v, false, 32, &w2);
+        }
+        if (rc == GSC_OK) {
+            k_gather_pairs<<<blocks, 256, 0, s>>>(c->d_pairs, v[w2], m, c->d_pairs_sorted);
+            cudaError_t e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) rc = fail(c, GSC_ERR_CUDA, "sorted download: %s", cudaGetErrorString(e));
+        }
+        for (int i = 0; i < 2; ++i) { cudaFree(k[i]); cudaFree(v[i]); }
+        if (rc) return rc;
+        src = c->d_pairs_sorted;
+    }
+    CU(c, cudaMemcpyAsync(dst, src, n * sizeof(uint2), cudaMemcpyDeviceToHost, s));
+    CU(c, cudaStreamSynchronize(s));
+    return GSC_OK;
+}
+
+int gsc_debug_download(gsc_ctx *c, int what, void *dst, size_t dst_bytes)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!dst) return fail(c, GSC_ERR_INVALID, "gsc_debug_download: null destination");
+    const uint32_t n = c->n_local + c->n_ghost;
+    const FrameBlock &h = *c->h_fb;
+    const int which = h.sort.num_passes & 1;
+    const void *src = nullptr;
+    size_t bytes = 0;
+    switch (what) {
+    case GSC_DBG_AABB: {
+        bytes = (size_t)n * 24;
+        if (dst_bytes < bytes) return fail(c, GSC_ERR_CAPACITY, "gsc_debug_download: need %zu bytes", bytes);
+        if (n == 0) return GSC_OK;
+        float *tmp = nullptr;
+        CU(c, cudaMalloc((void **)&tmp, bytes));
+        k_decode_aabb<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_rec, tmp);
+        cudaError_t e = cudaMemcpyAsync(dst, tmp, bytes, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        cudaFree(tmp);
+        if (e != cudaSuccess) return fail(c, GSC_ERR_CUDA, "gsc_debug_download: %s", cudaGetErrorString(e));
+        return GSC_OK;
+    }
+    case GSC_DBG_SORTED_KEYS: src = c->d_keys[which]; bytes = (size_t)n * 4; break;
+    case GSC_DBG_SORTED_IDX: src = c->d_vals[which]; bytes = (size_t)n * 4; break;
+    case GSC_DBG_CELL_START: src = c->d_cell_start; bytes = ((size_t)h.grid.num_cells + 1) * 4; break;
+    case GSC_DBG_OBB: src = c->d_obb; bytes = (size_t)n * 64; break;
+    default: return fail(c, GSC_ERR_INVALID, "gsc_debug_download: unknown item %d", what);
+    }
+    if (dst_bytes < bytes) return fail(c, GSC_ERR_CAPACITY, "gsc_debug_download: need %zu bytes", bytes);
+    CU(c, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return GSC_OK;
+}
+
+// ---- micro-bench batches -------------------------------------------------------------------------------
+
+}  // extern "C"
+
+namespace {
+struct Scratch {
+    void *p[4] = { nullptr, nullptr, nullptr, nullptr };
+    ~Scratch() { for (void *q : p) if (q) cudaFree(q); }
+};
+int batch_fail(const char *what, cudaError_t e) { return fail(nullptr, GSC_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e)); }
+#define BT(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return batch_fail(#expr, e_); } while (0)
+
+template <class Launch>
+int run_batch(int device, size_t n, const void *a, size_t a_stride, const void *b, size_t b_stride, void *out,
+              size_t out_stride, Launch launch)
+{
+    if (n == 0) return GSC_OK;
+    if (!a || !out) return fail(nullptr, GSC_ERR_INVALID, "batch: null array");
+    BT(cudaSetDevice(device));
+    Scratch s;
+    BT(cudaMalloc(&s.p[0], n * a_stride));
+    BT(cudaMemcpy(s.p[0], a, n * a_stride, cudaMemcpyHostToDevice));
+    if (b) {
+        BT(cudaMalloc(&s.p[1], n * b_stride));
+        BT(cudaMemcpy(s.p[1], b, n * b_stride, cudaMemcpyHostToDevice));
+    }
+    BT(cudaMalloc(&s.p[2], n * out_stride));
+    launch(s.p[0], s.p[1], s.p[2], (unsigned)((n + 255) / 256));
+    BT(cudaGetLastError());
+    BT(cudaMemcpy(out, s.p[2], n * out_stride, cudaMemcpyDeviceToHost));
+    return GSC_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int gsc_test_sphere_sphere(int device, size_t n, const float *a4, const float *b4, uint8_t *out)
+{
+    return run_batch(device, n, a4, 16, b4, 16, out, 1, [&](void *a, void *b, void *o, unsigned g) {
+        k_batch_sphere_sphere<<<g, 256>>>(n, (const float4 *)a, (const float4 *)b, (uint8_t *)o);
+    });
+}
+int gsc_test_sphere_obb(int device, size_t n, const float *s4, const float *obb16, uint8_t *out)
+{
+    return run_batch(device, n, s4, 16, obb16, 64, out, 1, [&](void *a, void *b, void *o, unsigned g) {
+        k_batch_sphere_obb<<<g, 256>>>(n, (const float4 *)a, (const float *)b, (uint8_t *)o);
+    });
+}
+int gsc_test_obb_obb(int device, size_t n, const float *a16, const float *b16, uint8_t *out)
+{
+    return run_batch(device, n, a16, 64, b16, 64, out, 1, [&](void *a, void *b, void *o, unsigned g) {
+        k_batch_obb_obb<<<g, 256>>>(n, (const float *)a, (const float *)b, (uint8_t *)o);
+    });
+}
+int gsc_test_aabb_aabb(int device, size_t n, const float *a6, const float *b6, uint8_t *out)
+{
+    return run_batch(device, n, a6, 24, b6, 24, out, 1, [&](void *a, void *b, void *o, unsigned g) {
+        k_batch_aabb_aabb<<<g, 256>>>(n, (const float *)a, (const float *)b, (uint8_t *)o);
+    });
+}
+int gsc_fnv1a_gridcell(int device, size_t n, const int16_t *cells3, uint64_t *out)
+{
+    return run_batch(device, n, cells3, 6, nullptr, 0, out, 8, [&](void *a, void *, void *o, unsigned g) {
+        k_batch_fnv1a<<<g, 256>>>(n, (const int16_t *)a, (uint64_t *)o);
+    });
+}
+
+int gsc_sort_pairs_u32(int device, size_t n, uint32_t *keys, uint32_t *vals, int key_bits)
+{
+    if (n == 0) return GSC_OK;
+    if (!keys || !vals || key_bits < 1 || key_bits > 32 || n >= (1ull << 30))
+        return fail(nullptr, GSC_ERR_INVALID, "gsc_sort_pairs_u32: bad argument");
+    BT(cudaSetDevice(device));
+    gsc_ctx tmp;  // only for error text plumbing of sort_standalone
+    tmp.device = device;
+    uint32_t *k[2] = { nullptr, nullptr }, *v[2] = { nullptr, nullptr };
+    Scratch s;
+    for (int i = 0; i < 2; ++i) {
+        BT(cudaMalloc((void **)&k[i], n * 4));
+        s.p[i] = k[i];
+        BT(cudaMalloc((void **)&v[i], n * 4));
+        s.p[2 + i] = v[i];
+    }
+    BT(cudaMemcpy(k[0], keys, n * 4, cudaMemcpyHostToDevice));
+    BT(cudaMemcpy(v[0], vals, n * 4, cudaMemcpyHostToDevice));
+    int which = 0;
+    if (int rc = sort_standalone(&tmp, 0, (uint32_t)n, k, v, false, key_bits, &which)) {
+        g_create_error = tmp.err;
+        return rc;
+    }
+    BT(cudaMemcpy(keys, k[which], n * 4, cudaMemcpyDeviceToHost));
+    BT(cudaMemcpy(vals, v[which], n * 4, cudaMemcpyDeviceToHost));
+    return GSC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,665 @@
+// gsc_kernels.cuh -- the collision step as hand-written sm_100a kernels.
+//
+// Stage map (reference -> kernel):
+//   bvh_update (bounding_volume.rs:345-409)                      -> k_bvh_update
+//   longest_axis / cell size, grid extent                        -> k_grid_setup
+//   WorkUnit::world_to_grid (grid_collision.rs:329-335)          -> k_cell_keys (+ digit histograms)
+//   HashMap<GridCell, Vec<..>> grouping (grid_collision.rs:434)  -> k_onesweep_pass (gsc_sort.cuh)
+//   cell lookup                                                  -> k_cell_table_permute
+//   test_cell candidate generation + HashMap dedupe (:439-441,
+//   :497-511) + BoundVolume::test (bounding_volume.rs:124-132)   -> k_pairs, k_narrow_sphere_obb,
+//                                                                   k_narrow_obb_obb, k_wide_pairs
+//
+// Why neighbour search instead of the reference's 8-corner insertion: with cell = longest AABB
+// extent every AABB spans <= 2 cells per axis, so two volumes share a corner cell iff their home
+// cells (cell of aabb.min) differ by at most one per axis AND their AABBs allow it; the AABB test
+// itself is the exact filter.  Each volume is therefore entered ONCE, under its home
+// cell, and looks at the 13 "earlier" neighbour cells plus its own.  Volumes that rounding makes
+// span 3 cells ("wide", grid_collision.rs:403-410) leave that argument and are handled exactly by
+// k_wide_pairs, which restates the corner-cell rule literally.
+#pragma once
+#include "gsc_math.cuh"
+#include "gsc_sort.cuh"
+
+namespace gsc {
+
+// ---- status bits (FrameBlock::status) ----
+enum : uint32_t {
+    kStNonFinite = 1u << 0,
+    kStMesh = 1u << 1,
+    kStRange = 1u << 2,
+    kStCellSize = 1u << 3,
+    kStCells = 1u << 4,
+    kStPairs = 1u << 5,
+    kStCands = 1u << 6,
+};
+
+// ---- volume record: 32 B = 2 x float4, the unit the broadphase streams ----
+//   sphere: r0 = (cx, cy, cz, radius)          r1 = (entity bits, 0, global index bits, meta)
+//   box:    r0 = (min.x, min.y, min.z, max.x)  r1 = (max.y, max.z, global index bits, meta)
+//   meta = local index << 4 | flags
+constexpr uint32_t kMetaBox = 1u, kMetaGhost = 2u;
+
+struct Volume {
+    float mn[3], mx[3];
+    float cx, cy, cz, r;  // sphere only
+    uint32_t entity;      // sphere only
+    uint32_t gidx, meta;
+};
+
+GSC_DEV Volume volume_decode(const float4 r0, const float4 r1)
+{
+    Volume v;
+    v.gidx = __float_as_uint(r1.z);
+    v.meta = __float_as_uint(r1.w);
+    if (v.meta & kMetaBox) {
+        v.mn[0] = r0.x; v.mn[1] = r0.y; v.mn[2] = r0.z;
+        v.mx[0] = r0.w; v.mx[1] = r1.x; v.mx[2] = r1.y;
+        v.cx = v.cy = v.cz = v.r = 0.0f;
+        v.entity = 0;
+    } else {
+        // bounding_volume.rs:150-159: min = centre - (r,r,r), max = centre + (r,r,r)
+        v.cx = r0.x; v.cy = r0.y; v.cz = r0.z; v.r = r0.w;
+        v.mn[0] = sub(r0.x, r0.w); v.mn[1] = sub(r0.y, r0.w); v.mn[2] = sub(r0.z, r0.w);
+        v.mx[0] = add(r0.x, r0.w); v.mx[1] = add(r0.y, r0.w); v.mx[2] = add(r0.z, r0.w);
+        v.entity = __float_as_uint(r1.x);
+    }
+    return v;
+}
+
+struct GridParams {
+    float cell_size;
+    int32_t origin[3];
+    int32_t dims[3];
+    uint32_t num_cells;  // dims product; also the key given to wide volumes
+    int32_t valid;
+};
+
+// Per-step device control block.  Zeroed at the start of every step.
+struct FrameBlock {
+    uint32_t bounds[8];  // [0] ord(longest axis); [1..3] ~ord(world min xyz); [4..6] ord(world max xyz)
+    uint32_t status;
+    uint32_t n_wide;
+    unsigned long long n_pairs, n_so, n_oo;
+    uint32_t tile_counter[kMaxPasses];
+    uint32_t xrange[2];  // ~(min home x + 32768), (max home x + 32768) of local volumes
+    uint32_t pad[2];
+    GridParams grid;
+    SortControl sort;
+    uint32_t hist[kMaxPasses][kRadix];
+};
+
+// ---- block-aggregated stream compaction ------------------------------------------------------
+// Hits are ballot-compacted per warp into a warp-private shared-memory buffer; when the CTA is
+// done ONE atomicAdd per stream reserves the CTA's slice of the global output and every warp
+// copies its buffer out.  (A warp whose buffer fills mid-kernel spills with a warp-level atomic.)
+template <int WARPS, int CAP>
+struct EmitBuf {
+    uint2 items[WARPS][CAP];
+    uint32_t count[WARPS];
+    unsigned long long base;
+};
+
+template <int WARPS, int CAP>
+GSC_DEV void emit_init(EmitBuf<WARPS, CAP> &b)
+{
+    if (threadIdx.x < WARPS) b.count[threadIdx.x] = 0;
+}
+
+template <int WARPS, int CAP>
+GSC_DEV void emit(EmitBuf<WARPS, CAP> &b, bool pred, uint2 item, uint2 *__restrict__ out,
+                  unsigned long long *counter, unsigned long long cap)
+{
+    const uint32_t mask = __ballot_sync(0xffffffffu, pred);
+    if (mask == 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cnt = __popc(mask);
+    uint32_t have = b.count[warp];
+    if (have + cnt > CAP) {  // spill this warp's buffer
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)have);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (uint32_t i = lane; i < have; i += 32)
+            if (base + i < cap) out[base + i] = b.items[warp][i];
+        have = 0;
+        __syncwarp();
+    }
+    if (pred) b.items[warp][have + __popc(mask & ((1u << lane) - 1u))] = item;
+    __syncwarp();
+    if (lane == 0) b.count[warp] = have + cnt;
+    __syncwarp();
+}
+
+template <int WARPS, int CAP>
+GSC_DEV void emit_finish(EmitBuf<WARPS, CAP> &b, uint2 *__restrict__ out, unsigned long long *counter,
+                         unsigned long long cap)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+        for (int w = 0; w < WARPS; ++w) total += b.count[w];
+        b.base = total ? atomicAdd(counter, (unsigned long long)total) : 0ull;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long base = b.base;
+    for (int w = 0; w < warp; ++w) base += b.count[w];
+    const uint32_t have = b.count[warp];
+    for (uint32_t i = lane; i < have; i += 32)
+        if (base + i < cap) out[base + i] = b.items[warp][i];
+}
+
+// ---- stage 0: bvh_update -----------------------------------------------------------------------
+// One thread per collider: CachedCollider::from_collider_transform (mod.rs:311-333) +
+// AABB::from_collider (bounding_volume.rs:148-336) + the longest-axis fold (:365-381) and the world
+// bounds (needed to place the dense grid), reduced warp -> CTA -> one atomic per CTA.
+constexpr int kBvhThreads = 256;
+
+__global__ void __launch_bounds__(kBvhThreads)
+k_bvh_update(uint32_t n, const uint8_t *__restrict__ kind, const float *__restrict__ offset3,
+             const float *__restrict__ size3, const float *__restrict__ pos3, const float *__restrict__ quat4,
+             const float *__restrict__ scale3, const uint32_t *__restrict__ entity,
+             const uint32_t *__restrict__ gidx, float4 *__restrict__ rec, float4 *__restrict__ obb,
+             FrameBlock *__restrict__ fb)
+{
+    const uint32_t i = blockIdx.x * kBvhThreads + threadIdx.x;
+    float ext = 0.0f;
+    float mn[3] = { INFINITY, INFINITY, INFINITY }, mx[3] = { -INFINITY, -INFINITY, -INFINITY };
+    uint32_t st = 0;
+    if (i < n) {
+        const uint32_t k = kind[i];
+        const float ox = offset3[3 * i], oy = offset3[3 * i + 1], oz = offset3[3 * i + 2];
+        const float px = pos3[3 * i], py = pos3[3 * i + 1], pz = pos3[3 * i + 2];
+        const uint32_t e = entity[i];
+        const uint32_t g = gidx ? gidx[i] : i;
+        // mod.rs:315 / :321  centre = position_derived + offset
+        const float cx = add(px, ox), cy = add(py, oy), cz = add(pz, oz);
+        if (k == 0) {
+            const float r = size3[3 * i];  // mod.rs:316 radius is not scaled
+            mn[0] = sub(cx, r); mn[1] = sub(cy, r); mn[2] = sub(cz, r);
+            mx[0] = add(cx, r); mx[1] = add(cy, r); mx[2] = add(cz, r);
+            rec[2 * (size_t)i] = make_float4(cx, cy, cz, r);
+            rec[2 * (size_t)i + 1] = make_float4(__uint_as_float(e), 0.0f, __uint_as_float(g), __uint_as_float(i << 4));
+        } else if (k == 1) {
+            Obb o;
+            // mod.rs:320  half_widths = widths * scale * 0.5
+            o.hx = mul(mul(size3[3 * i], scale3[3 * i]), 0.5f);
+            o.hy = mul(mul(size3[3 * i + 1], scale3[3 * i + 1]), 0.5f);
+            o.hz = mul(mul(size3[3 * i + 2], scale3[3 * i + 2]), 0.5f);
+            o.cx = cx; o.cy = cy; o.cz = cz;
+            const float4 q = reinterpret_cast<const float4 *>(quat4)[i];
+            quat_to_mat3(q.x, q.y, q.z, q.w, o.m);  // mod.rs:322
+            obb_aabb(o, mn, mx);
+            obb_store(obb + 4 * (size_t)i, o, e);
+            rec[2 * (size_t)i] = make_float4(mn[0], mn[1], mn[2], mx[0]);
+            rec[2 * (size_t)i + 1] = make_float4(mx[1], mx[2], __uint_as_float(g), __uint_as_float((i << 4) | kMetaBox));
+        } else {
+            st |= kStMesh;  // mod.rs:331 unimplemented!()
+            // keep the record decodable: a zero-size sphere far away is never produced; mark and bail
+            rec[2 * (size_t)i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            rec[2 * (size_t)i + 1] = make_float4(__uint_as_float(e), 0.0f, __uint_as_float(g), __uint_as_float(i << 4));
+            mn[0] = mn[1] = mn[2] = mx[0] = mx[1] = mx[2] = 0.0f;
+        }
+        // bounding_volume.rs:365-381: longest_axis = max(0, every diff), strict > from 0.0
+        const float dx = sub(mx[0], mn[0]), dy = sub(mx[1], mn[1]), dz = sub(mx[2], mn[2]);
+        ext = fmaxf(fmaxf(fmaxf(0.0f, dx), dy), dz);
+        const float chk = mn[0] + mn[1] + mn[2] + mx[0] + mx[1] + mx[2];
+        if (!(fabsf(chk) <= 3.0e38f)) st |= kStNonFinite;  // NaN or Inf anywhere
+    }
+    // warp reduce
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ext = fmaxf(ext, __shfl_xor_sync(0xffffffffu, ext, o));
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+        }
+        st |= __shfl_xor_sync(0xffffffffu, st, o);
+    }
+    __shared__ float s_red[kBvhThreads / 32][7];
+    __shared__ uint32_t s_st[kBvhThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        s_red[warp][0] = ext;
+        for (int a = 0; a < 3; ++a) { s_red[warp][1 + a] = mn[a]; s_red[warp][4 + a] = mx[a]; }
+        s_st[warp] = st;
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        const int c = threadIdx.x;
+        float v = s_red[0][c];
+        for (int w = 1; w < kBvhThreads / 32; ++w) v = (c >= 1 && c <= 3) ? fminf(v, s_red[w][c]) : fmaxf(v, s_red[w][c]);
+        if (c >= 1 && c <= 3) {
+            if (v != INFINITY) atomicMax(&fb->bounds[c], ~f2ord(v));
+        } else if (c == 0 || v != -INFINITY) {
+            atomicMax(&fb->bounds[c], f2ord(v));
+        }
+    }
+    if (threadIdx.x == 32) {
+        uint32_t s = 0;
+        for (int w = 0; w < kBvhThreads / 32; ++w) s |= s_st[w];
+        if (s) atomicOr(&fb->status, s);
+    }
+}
+
+// ---- grid placement: one thread -----------------------------------------------------------------
+// cell size = longest axis (grid_collision.rs:238-240); dense grid covers floor(world min / cell) ..
+// floor(world max / cell), which bounds every home cell because floor(fl(p / c)) is monotone in p.
+__global__ void k_grid_setup(FrameBlock *fb, unsigned long long max_cells, uint32_t n_total)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    GridParams g;
+    g.valid = 0;
+    g.num_cells = 0;
+    g.cell_size = ord2f(fb->bounds[0]);
+    for (int a = 0; a < 3; ++a) { g.origin[a] = 0; g.dims[a] = 0; }
+    fb->sort.num_passes = 0;
+    uint32_t st = 0;
+    if (n_total == 0 || fb->bounds[0] == 0) {  // nothing to do (no colliders): valid stays 0, not an error
+        fb->grid = g;
+        return;
+    }
+    if (!(g.cell_size > 0.0f)) st |= kStCellSize;
+    if (fb->status & (kStNonFinite | kStMesh)) st |= fb->status;
+    if (st == 0) {
+        unsigned long long cells = 1;
+        for (int a = 0; a < 3; ++a) {
+            const float lo = cell_coord_f(ord2f(~fb->bounds[1 + a]), g.cell_size);
+            const float hi = cell_coord_f(ord2f(fb->bounds[4 + a]), g.cell_size);
+            // GridCoord = i16 (grid_collision.rs:535): outside it the reference's cast is undefined
+            if (!(lo >= -32768.0f) || !(hi <= 32767.0f)) { st |= kStRange; break; }
+            g.origin[a] = (int32_t)lo;
+            g.dims[a] = (int32_t)hi - (int32_t)lo + 1;
+            cells *= (unsigned long long)g.dims[a];
+        }
+        if (st == 0) {
+            if (cells > max_cells || cells >= (1ull << 31)) st |= kStCells;
+            else {
+                g.num_cells = (uint32_t)cells;
+                g.valid = 1;
+                int bits = 0;
+                while ((1ull << bits) <= cells) ++bits;  // keys take values 0..cells (cells == wide)
+                fb->sort.num_passes = radix_passes(bits);
+            }
+        }
+    }
+    if (st) atomicOr(&fb->status, st);
+    fb->grid = g;
+}
+
+GSC_DEV bool home_cell(const Volume &v, const GridParams &g, int c_mn[3], int c_mx[3])
+{
+    bool wide = false;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        c_mn[a] = (int)cell_coord_f(v.mn[a], g.cell_size) - g.origin[a];
+        c_mx[a] = (int)cell_coord_f(v.mx[a], g.cell_size) - g.origin[a];
+        wide |= (c_mx[a] - c_mn[a]) > 1;
+    }
+    return wide;
+}
+
+// ---- stage 1: cell keys + digit histograms of every radix pass ------------------------------------
+// key = (x * dims.y + y) * dims.z + z of the home cell: x is the major axis, so x-slabs of the
+// multi-GPU partition are contiguous key ranges and cells of one (x,y) row are contiguous in z.
+constexpr int kKeyThreads = 256;
+
+__global__ void __launch_bounds__(kKeyThreads)
+k_cell_keys(uint32_t n_total, const float4 *__restrict__ rec, uint32_t *__restrict__ keys,
+            uint32_t *__restrict__ wide_list, FrameBlock *__restrict__ fb)
+{
+    __shared__ uint32_t s_hist[kMaxPasses][kRadix];
+    const GridParams g = fb->grid;
+    if (!g.valid) return;
+    const int passes = fb->sort.num_passes;
+    for (int i = threadIdx.x; i < kMaxPasses * kRadix; i += kKeyThreads) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * kKeyThreads + threadIdx.x; i < n_total; i += gridDim.x * kKeyThreads) {
+        const Volume v = volume_decode(__ldg(rec + 2 * (size_t)i), __ldg(rec + 2 * (size_t)i + 1));
+        int c0[3], c1[3];
+        const bool wide = home_cell(v, g, c0, c1);
+        uint32_t key;
+        if (wide) {
+            key = g.num_cells;
+            if (!(v.meta & kMetaGhost)) wide_list[atomicAdd(&fb->n_wide, 1u)] = i;
+        } else {
+            key = ((uint32_t)c0[0] * (uint32_t)g.dims[1] + (uint32_t)c0[1]) * (uint32_t)g.dims[2] + (uint32_t)c0[2];
+        }
+        keys[i] = key;
+        for (int p = 0; p < passes; ++p) atomicAdd(&s_hist[p][(key >> (8 * p)) & 255u], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < passes * kRadix; i += kKeyThreads) {
+        const uint32_t c = (&s_hist[0][0])[i];
+        if (c) atomicAdd(&fb->hist[0][0] + i, c);
+    }
+}
+
+// ---- stage 3: cell start table + cell-order permutation of the volume records ---------------------
+// start[c] = first sorted position whose key >= c, for c in [0, num_cells]; thread p fills the gap
+// (key[p-1], key[p]].  Long gaps (empty space) are filled by the whole warp.
+constexpr int kTableThreads = 256;
+
+__global__ void __launch_bounds__(kTableThreads)
+k_cell_table_permute(uint32_t n_total, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ vals_a,
+                     const uint32_t *__restrict__ keys_b, const uint32_t *__restrict__ vals_b,
+                     const float4 *__restrict__ rec, float4 *__restrict__ rec_sorted,
+                     uint32_t *__restrict__ cell_start, const FrameBlock *__restrict__ fb)
+{
+    const GridParams g = fb->grid;
+    if (!g.valid) return;
+    const bool in_b = fb->sort.num_passes & 1;  // ping-pong parity of the sort
+    const uint32_t *keys = in_b ? keys_b : keys_a;
+    const uint32_t *vals = in_b ? vals_b : vals_a;
+    const uint32_t p = blockIdx.x * kTableThreads + threadIdx.x;  // p in [0, n_total]
+    const uint32_t C = g.num_cells;
+    int64_t lo = 0, hi = -1;
+    if (p <= n_total) {
+        const uint32_t k = p < n_total ? min(keys[p], C) : C;
+        lo = p > 0 ? (int64_t)keys[p - 1] + 1 : 0;
+        hi = k;
+    }
+    if (p < n_total) {
+        const uint32_t i = vals[p];
+        const float4 r0 = __ldg(rec + 2 * (size_t)i), r1 = __ldg(rec + 2 * (size_t)i + 1);
+        rec_sorted[2 * (size_t)p] = r0;
+        rec_sorted[2 * (size_t)p + 1] = r1;
+    }
+    const int64_t len = hi - lo + 1;
+    const bool is_long = len > 8;
+    if (!is_long)
+        for (int64_t c = lo; c <= hi; ++c) cell_start[c] = p;
+    uint32_t long_mask = __ballot_sync(0xffffffffu, is_long);
+    const int lane = threadIdx.x & 31;
+    while (long_mask) {
+        const int src = __ffs(long_mask) - 1;
+        long_mask &= long_mask - 1;
+        const int64_t slo = __shfl_sync(0xffffffffu, lo, src);
+        const int64_t shi = __shfl_sync(0xffffffffu, hi, src);
+        const uint32_t sp = __shfl_sync(0xffffffffu, p, src);
+        for (int64_t c = slo + lane; c <= shi; c += 32) cell_start[c] = sp;
+    }
+}
+
+// ---- stage 4: neighbour-cell pair enumeration + AABB test + sphere-sphere --------------------------
+// One thread per cell-sorted volume A.  Candidates B are the volumes of the 13 cells that precede A's
+// home cell in key order among its 26 neighbours (5 z-rows) plus A's own cell; a pair inside one cell
+// is taken by the member with the larger global index.  So every unordered pair is visited exactly
+// once -- the sort order itself is the dedupe that the reference does with a HashMap
+// (grid_collision.rs:497-511).  Sphere-sphere pairs are finished here; pairs involving a box that
+// pass the AABB test are deferred to the SAT kernels (uniform work there, no divergence here).
+constexpr int kPairThreads = 256;
+constexpr int kPairWarps = kPairThreads / 32;
+constexpr int kPairCap = 96;
+
+struct PairOut {
+    uint2 *pairs;
+    uint2 *cand_so;
+    uint2 *cand_oo;
+    unsigned long long cap_pairs, cap_cands;
+};
+
+__global__ void __launch_bounds__(kPairThreads)
+k_pairs(uint32_t n_total, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ keys_b,
+        const float4 *__restrict__ rec_sorted, const uint32_t *__restrict__ cell_start, PairOut out,
+        FrameBlock *__restrict__ fb)
+{
+    __shared__ EmitBuf<kPairWarps, kPairCap> s_pairs, s_so, s_oo;
+    const GridParams g = fb->grid;
+    if (!g.valid) return;
+    const uint32_t *keys = (fb->sort.num_passes & 1) ? keys_b : keys_a;
+    emit_init(s_pairs);
+    emit_init(s_so);
+    emit_init(s_oo);
+    __syncthreads();
+
+    const uint32_t p = blockIdx.x * kPairThreads + threadIdx.x;
+    bool active = p < n_total;
+    Volume A;
+    uint32_t key = 0;
+    if (active) {
+        A = volume_decode(__ldg(rec_sorted + 2 * (size_t)p), __ldg(rec_sorted + 2 * (size_t)p + 1));
+        key = keys[p];
+        // ghosts only serve as the earlier volume; wide volumes (key == num_cells) go to k_wide_pairs
+        if ((A.meta & kMetaGhost) || key >= g.num_cells) active = false;
+    }
+    const uint32_t dy = (uint32_t)g.dims[1], dz = (uint32_t)g.dims[2];
+    const int x = (int)(key / (dy * dz));
+    const uint32_t rem = key - (uint32_t)x * dy * dz;
+    const int y = (int)(rem / dz);
+    const int z = (int)(rem - (uint32_t)y * dz);
+
+#pragma unroll 1
+    for (int r = 0; r < 5; ++r) {
+        const int xx = x + (r < 3 ? -1 : 0);
+        const int yy = y + (r < 3 ? r - 1 : r - 4);
+        uint32_t q = 0, qe = 0, qsame = 0xffffffffu;
+        if (active && xx >= 0 && yy >= 0 && yy < (int)dy) {
+            const uint32_t base = ((uint32_t)xx * dy + (uint32_t)yy) * dz;
+            const int z0 = max(z - 1, 0);
+            const int z1 = (r == 4) ? z : min(z + 1, (int)dz - 1);
+            q = __ldg(cell_start + base + z0);
+            qe = __ldg(cell_start + base + z1 + 1);
+            if (r == 4) qsame = __ldg(cell_start + base + z);
+        }
+        while (__any_sync(0xffffffffu, q < qe)) {
+            bool hit = false, so = false, oo = false;
+            uint2 item = make_uint2(0, 0);
+            if (q < qe) {
+                const Volume B = volume_decode(__ldg(rec_sorted + 2 * (size_t)q), __ldg(rec_sorted + 2 * (size_t)q + 1));
+                const bool take = (q < qsame) || (B.gidx < A.gidx);
+                if (take && test_aabb(A.mn, A.mx, B.mn, B.mx)) {
+                    const bool a_hi = A.gidx > B.gidx;  // tuple = (later index, earlier index), grid_collision.rs:440,497
+                    const bool a_box = A.meta & kMetaBox, b_box = B.meta & kMetaBox;
+                    if (!a_box && !b_box) {
+                        hit = test_sphere_sphere(A.cx, A.cy, A.cz, A.r, B.cx, B.cy, B.cz, B.r);
+                        item = a_hi ? make_uint2(A.entity, B.entity) : make_uint2(B.entity, A.entity);
+                    } else {
+                        const uint32_t la = A.meta >> 4, lb = B.meta >> 4;
+                        const uint32_t hi = a_hi ? la : lb, lo = a_hi ? lb : la;
+                        if (a_box && b_box) {
+                            oo = true;
+                            item = make_uint2(hi, lo);
+                        } else {
+                            so = true;
+                            const bool hi_is_sphere = a_hi ? !a_box : !b_box;
+                            item = make_uint2(hi | (hi_is_sphere ? 0x80000000u : 0u), lo);
+                        }
+                    }
+                }
+                ++q;
+            }
+            emit(s_pairs, hit, item, out.pairs, &fb->n_pairs, out.cap_pairs);
+            emit(s_so, so, item, out.cand_so, &fb->n_so, out.cap_cands);
+            emit(s_oo, oo, item, out.cand_oo, &fb->n_oo, out.cap_cands);
+        }
+    }
+    emit_finish(s_pairs, out.pairs, &fb->n_pairs, out.cap_pairs);
+    emit_finish(s_so, out.cand_so, &fb->n_so, out.cap_cands);
+    emit_finish(s_oo, out.cand_oo, &fb->n_oo, out.cap_cands);
+}
+
+// ---- stage 5: SAT narrowphase over the deferred candidates ------------------------------------------
+constexpr int kNarrowThreads = 256;
+constexpr int kNarrowWarps = kNarrowThreads / 32;
+constexpr int kNarrowCap = 96;
+
+// Sphere::test_obb (mod.rs:391-394) -- either order of the pair calls sphere.test_obb(obb) (mod.rs:378,407)
+__global__ void __launch_bounds__(kNarrowThreads)
+k_narrow_sphere_obb(const uint2 *__restrict__ cand, unsigned long long cap_cands, const float4 *__restrict__ rec,
+                    const float4 *__restrict__ obb, uint2 *__restrict__ pairs, unsigned long long cap_pairs,
+                    FrameBlock *__restrict__ fb)
+{
+    __shared__ EmitBuf<kNarrowWarps, kNarrowCap> s_out;
+    emit_init(s_out);
+    __syncthreads();
+    const unsigned long long n = min(fb->n_so, cap_cands);
+    const unsigned long long stride = (unsigned long long)gridDim.x * kNarrowThreads;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * kNarrowThreads; b < n; b += stride) {
+        const unsigned long long i = b + threadIdx.x;
+        bool hit = false;
+        uint2 item = make_uint2(0, 0);
+        if (i < n) {
+            const uint2 c = cand[i];
+            const bool hi_is_sphere = c.x >> 31;
+            const uint32_t hi = c.x & 0x7fffffffu, lo = c.y;
+            const uint32_t si = hi_is_sphere ? hi : lo, oi = hi_is_sphere ? lo : hi;
+            const float4 s0 = __ldg(rec + 2 * (size_t)si), s1 = __ldg(rec + 2 * (size_t)si + 1);
+            uint32_t oe;
+            const Obb o = obb_load(obb + 4 * (size_t)oi, &oe);
+            hit = test_sphere_obb(s0.x, s0.y, s0.z, s0.w, o);
+            const uint32_t se = __float_as_uint(s1.x);
+            item = hi_is_sphere ? make_uint2(se, oe) : make_uint2(oe, se);
+        }
+        emit(s_out, hit, item, pairs, &fb->n_pairs, cap_pairs);
+    }
+    emit_finish(s_out, pairs, &fb->n_pairs, cap_pairs);
+}
+
+// OBB::test_obb (mod.rs:413-546) evaluated as later.test_obb(earlier) (grid_collision.rs:505, mod.rs:408)
+__global__ void __launch_bounds__(kNarrowThreads)
+k_narrow_obb_obb(const uint2 *__restrict__ cand, unsigned long long cap_cands, const float4 *__restrict__ obb,
+                 uint2 *__restrict__ pairs, unsigned long long cap_pairs, FrameBlock *__restrict__ fb)
+{
+    __shared__ EmitBuf<kNarrowWarps, kNarrowCap> s_out;
+    emit_init(s_out);
+    __syncthreads();
+    const unsigned long long n = min(fb->n_oo, cap_cands);
+    const unsigned long long stride = (unsigned long long)gridDim.x * kNarrowThreads;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * kNarrowThreads; b < n; b += stride) {
+        const unsigned long long i = b + threadIdx.x;
+        bool hit = false;
+        uint2 item = make_uint2(0, 0);
+        if (i < n) {
+            const uint2 c = cand[i];
+            uint32_t ea, eb;
+            const Obb a = obb_load(obb + 4 * (size_t)c.x, &ea);
+            const Obb bb = obb_load(obb + 4 * (size_t)c.y, &eb);
+            hit = test_obb_obb(a, bb);
+            item = make_uint2(ea, eb);
+        }
+        emit(s_out, hit, item, pairs, &fb->n_pairs, cap_pairs);
+    }
+    emit_finish(s_out, pairs, &fb->n_pairs, cap_pairs);
+}
+
+// full BoundVolume::test (bounding_volume.rs:124-132) between two arbitrary volumes, `hi` = later index
+GSC_DEV bool test_volume_full(const Volume &hi, const Volume &lo, const float4 *__restrict__ obb, uint32_t *e_hi,
+                              uint32_t *e_lo)
+{
+    if (!test_aabb(hi.mn, hi.mx, lo.mn, lo.mx)) return false;
+    const bool hb = hi.meta & kMetaBox, lb = lo.meta & kMetaBox;
+    if (!hb && !lb) {
+        *e_hi = hi.entity; *e_lo = lo.entity;
+        return test_sphere_sphere(hi.cx, hi.cy, hi.cz, hi.r, lo.cx, lo.cy, lo.cz, lo.r);
+    }
+    if (hb && lb) {
+        const Obb a = obb_load(obb + 4 * (size_t)(hi.meta >> 4), e_hi);
+        const Obb b = obb_load(obb + 4 * (size_t)(lo.meta >> 4), e_lo);
+        return test_obb_obb(a, b);
+    }
+    if (hb) {
+        const Obb o = obb_load(obb + 4 * (size_t)(hi.meta >> 4), e_hi);
+        *e_lo = lo.entity;
+        return test_sphere_obb(lo.cx, lo.cy, lo.cz, lo.r, o);
+    }
+    const Obb o = obb_load(obb + 4 * (size_t)(lo.meta >> 4), e_lo);
+    *e_hi = hi.entity;
+    return test_sphere_obb(hi.cx, hi.cy, hi.cz, hi.r, o);
+}
+
+// Volumes that span 3 cells on an axis (possible only through rounding of p / cell_size): the
+// reference enters them in their CORNER cells only (grid_collision.rs:447-480), so they collide with
+// another volume iff the two share a corner cell.  Restated literally, wide x everything.
+__global__ void __launch_bounds__(kNarrowThreads)
+k_wide_pairs(uint32_t n_local, const uint32_t *__restrict__ wide_list, const float4 *__restrict__ rec,
+             const float4 *__restrict__ obb, uint2 *__restrict__ pairs, unsigned long long cap_pairs,
+             FrameBlock *__restrict__ fb)
+{
+    __shared__ EmitBuf<kNarrowWarps, kNarrowCap> s_out;
+    const GridParams g = fb->grid;
+    const uint32_t n_wide = fb->n_wide;
+    if (!g.valid || n_wide == 0) return;
+    emit_init(s_out);
+    __syncthreads();
+    const unsigned long long total = (unsigned long long)n_wide * n_local;
+    const unsigned long long stride = (unsigned long long)gridDim.x * kNarrowThreads;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * kNarrowThreads; b < total; b += stride) {
+        const unsigned long long t = b + threadIdx.x;
+        bool hit = false;
+        uint2 item = make_uint2(0, 0);
+        if (t < total) {
+            const uint32_t wi = wide_list[t / n_local];
+            const uint32_t j = (uint32_t)(t % n_local);
+            if (wi != j) {
+                const Volume W = volume_decode(__ldg(rec + 2 * (size_t)wi), __ldg(rec + 2 * (size_t)wi + 1));
+                const Volume J = volume_decode(__ldg(rec + 2 * (size_t)j), __ldg(rec + 2 * (size_t)j + 1));
+                int w0[3], w1[3], j0[3], j1[3];
+                home_cell(W, g, w0, w1);
+                const bool j_wide = home_cell(J, g, j0, j1);
+                // a wide-wide pair is taken once, by the iteration whose J is the later volume
+                bool take = !j_wide || (W.gidx < J.gidx);
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+                    take &= (w0[a] == j0[a]) || (w0[a] == j1[a]) || (w1[a] == j0[a]) || (w1[a] == j1[a]);
+                if (take) {
+                    const bool w_hi = W.gidx > J.gidx;
+                    uint32_t eh = 0, el = 0;
+                    hit = w_hi ? test_volume_full(W, J, obb, &eh, &el) : test_volume_full(J, W, obb, &eh, &el);
+                    item = make_uint2(eh, el);
+                }
+            }
+        }
+        emit(s_out, hit, item, pairs, &fb->n_pairs, cap_pairs);
+    }
+    emit_finish(s_out, pairs, &fb->n_pairs, cap_pairs);
+}
+
+// ---- micro-bench parity kernels (benches/collision.rs, benches/grid_collision.rs) -------------------
+__global__ void k_batch_sphere_sphere(size_t n, const float4 *a, const float4 *b, uint8_t *out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = a[i], q = b[i];
+    out[i] = test_sphere_sphere(p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w);
+}
+GSC_DEV Obb obb_from16(const float *f)
+{
+    Obb o;
+    o.cx = f[0]; o.cy = f[1]; o.cz = f[2];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) o.m[i][j] = f[3 + 3 * i + j];
+    o.hx = f[12]; o.hy = f[13]; o.hz = f[14];
+    return o;
+}
+__global__ void k_batch_sphere_obb(size_t n, const float4 *s, const float *o16, uint8_t *out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = s[i];
+    out[i] = test_sphere_obb(p.x, p.y, p.z, p.w, obb_from16(o16 + 16 * i));
+}
+__global__ void k_batch_obb_obb(size_t n, const float *a16, const float *b16, uint8_t *out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = test_obb_obb(obb_from16(a16 + 16 * i), obb_from16(b16 + 16 * i));
+}
+__global__ void k_batch_aabb_aabb(size_t n, const float *a6, const float *b6, uint8_t *out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *a = a6 + 6 * i, *b = b6 + 6 * i;
+    const float amn[3] = { a[0], a[1], a[2] }, amx[3] = { a[3], a[4], a[5] };
+    const float bmn[3] = { b[0], b[1], b[2] }, bmx[3] = { b[3], b[4], b[5] };
+    out[i] = test_aabb(amn, amx, bmn, bmx);
+}
+__global__ void k_batch_fnv1a(size_t n, const int16_t *cells, uint64_t *out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = fnv1a_gridcell(cells[3 * i], cells[3 * i + 1], cells[3 * i + 2]);
+}
+
+}  // namespace gsc

@@ -1,0 +1,243 @@
+// gsc_math.cuh -- device-side f32 arithmetic of the collision path, bit-exact with the reference.
+//
+// Every expression below is written with the explicit round-to-nearest intrinsics
+// (__fmul_rn / __fadd_rn / __fsub_rn / __fdiv_rn), which the compiler never contracts into FMA,
+// so the result equals the Rust source's separate-multiply-and-add evaluation regardless of
+// -fmad.  Association is left-to-right exactly as the reference writes it.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gsc {
+
+#define GSC_DEV __device__ __forceinline__
+
+constexpr float kEpsilon = 1e-6f;  // lib/polygon_math/src/lib.rs:24
+
+GSC_DEV float mul(float a, float b) { return __fmul_rn(a, b); }
+GSC_DEV float add(float a, float b) { return __fadd_rn(a, b); }
+GSC_DEV float sub(float a, float b) { return __fsub_rn(a, b); }
+
+// vector.rs:190-196  Dot: x*x' + y*y' + z*z'
+GSC_DEV float dot3(float ax, float ay, float az, float bx, float by, float bz)
+{
+    return add(add(mul(ax, bx), mul(ay, by)), mul(az, bz));
+}
+
+// World-space oriented box: OBB (mod.rs:397-402).  m is the row-major Matrix3 (matrix.rs:293-295);
+// the box axes are its COLUMNS (mod.rs:419,555).
+struct Obb {
+    float cx, cy, cz;
+    float m[3][3];
+    float hx, hy, hz;
+};
+
+// 64-byte storage record of an Obb: 4 x float4.
+//   q0 = (cx, cy, cz, m00)  q1 = (m01, m02, m10, m11)  q2 = (m12, m20, m21, m22)  q3 = (hx, hy, hz, entity bits)
+GSC_DEV void obb_store(float4 *dst, const Obb &o, uint32_t entity)
+{
+    dst[0] = make_float4(o.cx, o.cy, o.cz, o.m[0][0]);
+    dst[1] = make_float4(o.m[0][1], o.m[0][2], o.m[1][0], o.m[1][1]);
+    dst[2] = make_float4(o.m[1][2], o.m[2][0], o.m[2][1], o.m[2][2]);
+    dst[3] = make_float4(o.hx, o.hy, o.hz, __uint_as_float(entity));
+}
+
+GSC_DEV Obb obb_load(const float4 *src, uint32_t *entity)
+{
+    const float4 q0 = __ldg(src + 0), q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3);
+    Obb o;
+    o.cx = q0.x; o.cy = q0.y; o.cz = q0.z;
+    o.m[0][0] = q0.w; o.m[0][1] = q1.x; o.m[0][2] = q1.y;
+    o.m[1][0] = q1.z; o.m[1][1] = q1.w; o.m[1][2] = q2.x;
+    o.m[2][0] = q2.y; o.m[2][1] = q2.z; o.m[2][2] = q2.w;
+    o.hx = q3.x; o.hy = q3.y; o.hz = q3.z;
+    if (entity) *entity = __float_as_uint(q3.w);
+    return o;
+}
+
+// matrix.rs:392-402  From<Orientation> for Matrix3, q = (x,y,z,w)
+GSC_DEV void quat_to_mat3(float x, float y, float z, float w, float m[3][3])
+{
+    const float ww = mul(w, w), xx = mul(x, x), yy = mul(y, y), zz = mul(z, z);
+    const float x2 = mul(2.0f, x), y2 = mul(2.0f, y), w2 = mul(2.0f, w);
+    m[0][0] = sub(sub(add(ww, xx), yy), zz);
+    m[0][1] = sub(mul(x2, y), mul(w2, z));
+    m[0][2] = add(mul(x2, z), mul(w2, y));
+    m[1][0] = add(mul(x2, y), mul(w2, z));
+    m[1][1] = sub(add(sub(ww, xx), yy), zz);
+    m[1][2] = sub(mul(y2, z), mul(w2, x));
+    m[2][0] = sub(mul(x2, z), mul(w2, y));
+    m[2][1] = add(mul(y2, z), mul(w2, x));
+    m[2][2] = add(sub(sub(ww, xx), yy), zz);
+}
+
+// bounding_volume.rs:161-327  AABB of an OBB: 8 vertices centre + M.(half*sign) in the reference's
+// sign order, running min/max with `if v < min {..} else if v > max {..}`.
+GSC_DEV void obb_aabb(const Obb &o, float mn[3], float mx[3])
+{
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float sx = (k & 4) ? -1.0f : 1.0f, sy = (k & 2) ? -1.0f : 1.0f, sz = (k & 1) ? -1.0f : 1.0f;
+        const float vx = mul(o.hx, sx), vy = mul(o.hy, sy), vz = mul(o.hz, sz);
+        // matrix.rs:453-463  M.v row by row
+        const float px = add(o.cx, add(add(mul(o.m[0][0], vx), mul(o.m[0][1], vy)), mul(o.m[0][2], vz)));
+        const float py = add(o.cy, add(add(mul(o.m[1][0], vx), mul(o.m[1][1], vy)), mul(o.m[1][2], vz)));
+        const float pz = add(o.cz, add(add(mul(o.m[2][0], vx), mul(o.m[2][1], vy)), mul(o.m[2][2], vz)));
+        if (k == 0) {
+            mn[0] = mx[0] = px; mn[1] = mx[1] = py; mn[2] = mx[2] = pz;
+        } else {
+            if (px < mn[0]) mn[0] = px; else if (px > mx[0]) mx[0] = px;
+            if (py < mn[1]) mn[1] = py; else if (py > mx[1]) mx[1] = py;
+            if (pz < mn[2]) mn[2] = pz; else if (pz > mx[2]) mx[2] = pz;
+        }
+    }
+}
+
+// bounding_volume.rs:411-419
+GSC_DEV bool test_ranges(float min_a, float max_a, float min_b, float max_b)
+{
+    return !(min_a > max_b || min_b > max_a || max_a < min_b || max_b < min_a);
+}
+
+// bounding_volume.rs:338-343 (inclusive: touching boxes overlap)
+GSC_DEV bool test_aabb(const float amn[3], const float amx[3], const float bmn[3], const float bmx[3])
+{
+    return test_ranges(amn[0], amx[0], bmn[0], bmx[0]) && test_ranges(amn[1], amx[1], bmn[1], bmx[1]) &&
+           test_ranges(amn[2], amx[2], bmn[2], bmx[2]);
+}
+
+// mod.rs:383-389  Sphere::test_sphere
+GSC_DEV bool test_sphere_sphere(float ax, float ay, float az, float ar, float bx, float by, float bz, float br)
+{
+    const float dx = sub(ax, bx), dy = sub(ay, by), dz = sub(az, bz);
+    const float dist_sqr = add(add(mul(dx, dx), mul(dy, dy)), mul(dz, dz));
+    const float rs = add(ar, br);
+    const float diff = sub(dist_sqr, mul(rs, rs));
+    return diff < 0.0f || fabsf(diff) < kEpsilon;
+}
+
+// mod.rs:391-394 + 549-574  Sphere::test_obb via OBB::closest_point (strict <)
+GSC_DEV bool test_sphere_obb(float sx, float sy, float sz, float sr, const Obb &o)
+{
+    const float dx = sub(sx, o.cx), dy = sub(sy, o.cy), dz = sub(sz, o.cz);
+    float rx = o.cx, ry = o.cy, rz = o.cz;
+    const float h[3] = { o.hx, o.hy, o.hz };
+#pragma unroll
+    for (int axis = 0; axis < 3; ++axis) {
+        const float ax = o.m[0][axis], ay = o.m[1][axis], az = o.m[2][axis];  // column `axis`
+        float dist = dot3(dx, dy, dz, ax, ay, az);
+        dist = fminf(fmaxf(dist, -h[axis]), h[axis]);  // lib.rs:41-45 clamp
+        rx = add(rx, mul(ax, dist));
+        ry = add(ry, mul(ay, dist));
+        rz = add(rz, mul(az, dist));
+    }
+    const float ex = sub(sx, rx), ey = sub(sy, ry), ez = sub(sz, rz);
+    const float dist_sqr = add(add(mul(ex, ex), mul(ey, ey)), mul(ez, ez));
+    return dist_sqr < mul(sr, sr);
+}
+
+// mod.rs:413-546  OBB::test_obb -- `a` is self, `b` the argument.  15-axis SAT.
+GSC_DEV bool test_obb_obb(const Obb &a, const Obb &b)
+{
+    float r[3][3], ar[3][3];
+#pragma unroll
+    for (int row = 0; row < 3; ++row)
+#pragma unroll
+        for (int col = 0; col < 3; ++col) {
+            // a.col(row) . b.col(col)
+            r[row][col] = dot3(a.m[0][row], a.m[1][row], a.m[2][row], b.m[0][col], b.m[1][col], b.m[2][col]);
+            ar[row][col] = add(fabsf(r[row][col]), kEpsilon);
+        }
+    const float tx = sub(b.cx, a.cx), ty = sub(b.cy, a.cy), tz = sub(b.cz, a.cz);
+    float t[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)  // t * a.orientation.transpose(): row i of A^T is column i of A
+        t[i] = add(add(mul(a.m[0][i], tx), mul(a.m[1][i], ty)), mul(a.m[2][i], tz));
+    const float ah[3] = { a.hx, a.hy, a.hz };
+    const float bh[3] = { b.hx, b.hy, b.hz };
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {  // L = A_i
+        const float rb = add(add(mul(bh[0], ar[i][0]), mul(bh[1], ar[i][1])), mul(bh[2], ar[i][2]));
+        if (fabsf(t[i]) > add(ah[i], rb)) return false;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {  // L = B_i
+        const float ra = add(add(mul(ah[0], ar[0][i]), mul(ah[1], ar[1][i])), mul(ah[2], ar[2][i]));
+        const float proj = add(add(mul(t[0], r[0][i]), mul(t[1], r[1][i])), mul(t[2], r[2][i]));
+        if (fabsf(proj) > add(ra, bh[i])) return false;
+    }
+    float ra, rb;
+    // A0 x B0
+    ra = add(mul(ah[1], ar[2][0]), mul(ah[2], ar[1][0]));
+    rb = add(mul(bh[1], ar[0][2]), mul(bh[2], ar[0][1]));
+    if (fabsf(sub(mul(t[2], r[1][0]), mul(t[1], r[2][0]))) > add(ra, rb)) return false;
+    // A0 x B1
+    ra = add(mul(ah[1], ar[2][1]), mul(ah[2], ar[1][1]));
+    rb = add(mul(bh[0], ar[0][2]), mul(bh[2], ar[0][0]));
+    if (fabsf(sub(mul(t[2], r[1][1]), mul(t[1], r[2][1]))) > add(ra, rb)) return false;
+    // A0 x B2
+    ra = add(mul(ah[1], ar[2][2]), mul(ah[2], ar[1][2]));
+    rb = add(mul(bh[0], ar[0][1]), mul(bh[1], ar[0][0]));
+    if (fabsf(sub(mul(t[2], r[1][2]), mul(t[1], r[2][2]))) > add(ra, rb)) return false;
+    // A1 x B0
+    ra = add(mul(ah[0], ar[2][0]), mul(ah[2], ar[0][0]));
+    rb = add(mul(bh[1], ar[1][2]), mul(bh[2], ar[1][1]));
+    if (fabsf(sub(mul(t[0], r[2][0]), mul(t[2], r[0][0]))) > add(ra, rb)) return false;
+    // A1 x B1
+    ra = add(mul(ah[0], ar[2][1]), mul(ah[2], ar[0][1]));
+    rb = add(mul(bh[0], ar[1][2]), mul(bh[2], ar[1][0]));
+    if (fabsf(sub(mul(t[0], r[2][1]), mul(t[2], r[0][1]))) > add(ra, rb)) return false;
+    // A1 x B2
+    ra = add(mul(ah[0], ar[2][2]), mul(ah[2], ar[0][2]));
+    rb = add(mul(bh[0], ar[1][1]), mul(bh[1], ar[1][0]));
+    if (fabsf(sub(mul(t[0], r[2][2]), mul(t[2], r[0][2]))) > add(ra, rb)) return false;
+    // A2 x B0
+    ra = add(mul(ah[0], ar[1][0]), mul(ah[1], ar[0][0]));
+    rb = add(mul(bh[1], ar[2][2]), mul(bh[2], ar[2][1]));
+    if (fabsf(sub(mul(t[1], r[0][0]), mul(t[0], r[1][0]))) > add(ra, rb)) return false;
+    // A2 x B1
+    ra = add(mul(ah[0], ar[1][1]), mul(ah[1], ar[0][1]));
+    rb = add(mul(bh[0], ar[2][2]), mul(bh[2], ar[2][0]));
+    if (fabsf(sub(mul(t[1], r[0][1]), mul(t[0], r[1][1]))) > add(ra, rb)) return false;
+    // A2 x B2
+    ra = add(mul(ah[0], ar[1][2]), mul(ah[1], ar[0][2]));
+    rb = add(mul(bh[0], ar[2][1]), mul(bh[1], ar[2][0]));
+    if (fabsf(sub(mul(t[1], r[0][2]), mul(t[0], r[1][2]))) > add(ra, rb)) return false;
+    return true;
+}
+
+// grid_collision.rs:329-335  (p / cell_size).floor(), IEEE divide
+GSC_DEV float cell_coord_f(float p, float cell_size) { return floorf(__fdiv_rn(p, cell_size)); }
+
+// lib/hash/src/fnv.rs:21-38 over the six little-endian bytes of GridCell{x,y,z: i16}
+GSC_DEV uint64_t fnv1a_gridcell(int16_t x, int16_t y, int16_t z)
+{
+    uint64_t h = 0xcbf29ce484222325ull;
+    const uint16_t v[3] = { (uint16_t)x, (uint16_t)y, (uint16_t)z };
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        h = (h ^ (uint64_t)(v[i] & 0xff)) * 0x100000001b3ull;
+        h = (h ^ (uint64_t)(v[i] >> 8)) * 0x100000001b3ull;
+    }
+    return h;
+}
+
+// monotone float <-> uint mapping for atomicMin/atomicMax on floats of either sign
+GSC_DEV uint32_t f2ord(float f)
+{
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ inline float ord2f(uint32_t u)
+{
+    const uint32_t b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+#endif
+}
+
+}  // namespace gsc

@@ -1,0 +1,181 @@
+/*
+ * gunship_collision.h -- C ABI of the B200-native Gunship collision step.
+ *
+ * This is the drop-in boundary for the one data-parallel hot path of randomPoison/gunship-rs:
+ * `CollisionSystem::update` = `bvh_update` + `GridCollisionSystem::update`
+ * (src/component/collider/mod.rs:590-611, bounding_volume.rs:345-409, grid_collision.rs:218-285).
+ * Everything above it (Collider / ColliderManager / CollisionSystem / callbacks) stays in the host
+ * language; everything below it is hand-written CUDA for sm_100a.  Plain pointers and sizes only:
+ * no C++ types, no torch types.  Every entry point returns an `int` status (GSC_OK == 0) and never
+ * throws or aborts across the boundary; the reference panics in the same situations
+ * (Cargo.toml:27-40 `panic = "abort"`), so a host wrapper turns a non-zero status into a panic.
+ *
+ * Threading: a context is owned by one caller thread (the reference's `update(&mut self, ..)`,
+ * src/old/engine.rs:193); distinct contexts are independent.
+ *
+ * Ownership: input host arrays are borrowed for the duration of the call only.  The library owns
+ * all device buffers; device pointers it hands out stay valid until the next gsc_step / gsc_destroy.
+ */
+#ifndef GUNSHIP_COLLISION_H
+#define GUNSHIP_COLLISION_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSC_ABI_VERSION 1
+
+/* status codes */
+enum {
+    GSC_OK           = 0,
+    GSC_ERR_INVALID  = 1, /* bad argument / call order */
+    GSC_ERR_CUDA     = 2, /* CUDA runtime failure (message in gsc_last_error) */
+    GSC_ERR_NCCL     = 3, /* reserved: collective failure in the multi-GPU host layer */
+    GSC_ERR_CAPACITY = 4, /* pair / candidate / cell-table capacity exceeded; needed sizes are in gsc_step_out */
+    GSC_ERR_RANGE    = 5, /* a grid coordinate leaves i16 (grid_collision.rs:530-535), cell size is not
+                             positive, or an input is NaN/Inf -- the reference's behaviour is undefined there */
+    GSC_ERR_KIND     = 6  /* Collider::Mesh: `unimplemented!()` in the reference (mod.rs:331,343) */
+};
+
+/* collider kinds -- `enum Collider` (mod.rs:139-183) */
+enum { GSC_SPHERE = 0, GSC_BOX = 1, GSC_MESH = 2 };
+
+/* gsc_config.flags */
+enum {
+    GSC_FLAG_TIMING = 1u << 0, /* record per-stage CUDA-event times in gsc_step_out.stage_ms */
+    GSC_FLAG_GRAPH  = 1u << 1  /* replay the step as one CUDA graph (launch-bound small scenes) */
+};
+
+/* stages of one step, in launch order (names follow the reference's Stopwatch scopes) */
+enum {
+    GSC_STAGE_BVH_UPDATE = 0, /* "BVH Update": world shapes, AABBs, longest axis, world bounds */
+    GSC_STAGE_CELL_KEYS  = 1, /* world_to_grid + cell keys + digit histograms */
+    GSC_STAGE_SORT       = 2, /* radix sort of (cell, collider) */
+    GSC_STAGE_CELL_TABLE = 3, /* cell start table + cell-order permutation of the volumes */
+    GSC_STAGE_PAIRS      = 4, /* neighbour-cell pair enumeration + AABB test + sphere-sphere */
+    GSC_STAGE_NARROW     = 5, /* sphere-OBB and OBB-OBB SAT over the deferred candidates (+ wide volumes) */
+    GSC_NUM_STAGES       = 6
+};
+
+typedef struct gsc_ctx gsc_ctx;
+
+typedef struct gsc_config {
+    int32_t  device;         /* CUDA device ordinal */
+    uint32_t max_colliders;  /* capacity: local colliders + ghosts received from other slabs */
+    uint64_t max_pairs;      /* capacity of the contact-pair buffer (0 = 8 * max_colliders + 65536) */
+    uint64_t max_candidates; /* capacity of each deferred box-candidate list (0 = 8 * max_colliders + 65536) */
+    uint64_t max_cells;      /* capacity of the dense cell table (0 = 16 * max_colliders + 2^20) */
+    uint32_t flags;          /* GSC_FLAG_* */
+    uint32_t reserved;
+} gsc_config;
+
+typedef struct gsc_step_out {
+    uint64_t n_pairs;        /* contact pairs found (may exceed max_pairs on GSC_ERR_CAPACITY) */
+    uint64_t n_sphere_obb;   /* AABB-overlapping sphere/box candidates handed to the SAT stage */
+    uint64_t n_obb_obb;      /* AABB-overlapping box/box candidates handed to the SAT stage */
+    uint64_t n_cells;        /* cells of the dense grid this frame */
+    float    cell_size;      /* BoundingVolumeManager::longest_axis (bounding_volume.rs:365-381) */
+    uint32_t n_wide;         /* volumes whose AABB spans > 2 cells on an axis (debug_assert grid_collision.rs:403-410) */
+    int32_t  grid_origin[3]; /* min cell coordinate per axis */
+    int32_t  grid_dims[3];   /* cells per axis */
+    uint32_t sort_passes;    /* 8-bit radix passes run on the cell keys */
+    uint32_t status_flags;   /* raw device error bits (diagnostics) */
+    float    stage_ms[GSC_NUM_STAGES]; /* only with GSC_FLAG_TIMING */
+    float    step_ms;        /* device time of the whole step (always) */
+    const uint32_t *d_pairs; /* DEVICE pointer: n_pairs x (entity of higher index, entity of lower index) */
+} gsc_step_out;
+
+/* ---- lifetime ---- */
+int  gsc_create(const gsc_config *cfg, gsc_ctx **out);
+void gsc_destroy(gsc_ctx *ctx);
+/* last error text of this context (never NULL); ctx == NULL gives the last gsc_create failure */
+const char *gsc_last_error(const gsc_ctx *ctx);
+int  gsc_abi_version(void);
+
+/* ---- collider registration: ColliderManager::assign over the whole dense array
+ *      (mod.rs:221-223; iteration order = index order, struct_component_manager.rs:112-117) ----
+ * entity[n]; kind[n] (GSC_SPHERE/GSC_BOX); offset3[3n]; size3[3n] = (radius,-,-) or box widths.
+ * global_index may be NULL (index i) -- it is the collider's position in the reference's
+ * BoundingVolumeManager.components, which orients every output tuple (grid_collision.rs:440,497). */
+int gsc_upload_colliders(gsc_ctx *ctx, uint32_t n, const uint32_t *entity, const uint8_t *kind,
+                         const float *offset3, const float *size3, const uint32_t *global_index);
+
+/* ---- per-frame derived transforms (TransformManager position/rotation/scale_derived,
+ *      component/transform.rs:441-459) from HOST memory; quat is (x,y,z,w).
+ *      quat4 / scale3 may be NULL to keep the previous values. ---- */
+int gsc_update_transforms(gsc_ctx *ctx, uint32_t n, const float *pos3, const float *quat4, const float *scale3);
+
+/* same, from DEVICE memory that the caller keeps alive until the next bind (no copy is made) */
+int gsc_bind_device_transforms(gsc_ctx *ctx, uint32_t n, const float *d_pos3, const float *d_quat4, const float *d_scale3);
+
+/* ---- the step: CollisionSystem::update (mod.rs:590-611) minus the callback dispatch ---- */
+int gsc_step(gsc_ctx *ctx, gsc_step_out *out);
+
+/* copy the contact pairs of the last step to host memory: dst[2*i] = entity of the later (higher
+ * index) volume, dst[2*i+1] = entity of the earlier one -- the tuple order of
+ * GridCollisionSystem::collisions (grid_collision.rs:119,497).  sorted != 0 orders them ascending by
+ * (first << 32 | second) on the device first.  *n_out receives the pair count; dst == NULL with
+ * cap_pairs == 0 only queries it. */
+int gsc_download_pairs(gsc_ctx *ctx, uint32_t *dst, uint64_t cap_pairs, int sorted, uint64_t *n_out);
+
+/* ---- stage-level read-back for parity tests (host buffers) ---- */
+enum {
+    GSC_DBG_AABB        = 0, /* float[6n]: min xyz, max xyz per collider (AABB::from_collider) */
+    GSC_DBG_SORTED_KEYS = 1, /* uint32[n]: dense cell ids of world_to_grid(aabb.min) after the radix sort
+                                (x-major; wide volumes carry n_cells) */
+    GSC_DBG_SORTED_IDX  = 2, /* uint32[n]: collider indices after the radix sort */
+    GSC_DBG_CELL_START  = 3, /* uint32[n_cells+1]: first sorted position of each cell */
+    GSC_DBG_OBB         = 4  /* float[16n]: centre xyz, orientation row-major 9, half widths 3, entity bits */
+};
+int gsc_debug_download(gsc_ctx *ctx, int what, void *dst, size_t dst_bytes);
+
+/* ---- micro-bench parity: the functions benches/collision.rs and benches/grid_collision.rs call,
+ *      batched over n independent inputs (HOST arrays; results in out[n]) ---- */
+/* Sphere::test_sphere (mod.rs:383-389); spheres as (cx,cy,cz,r) */
+int gsc_test_sphere_sphere(int device, size_t n, const float *a4, const float *b4, uint8_t *out);
+/* Sphere::test_obb (mod.rs:391-394); OBB as 16 floats (centre 3, orientation row-major 9, half widths 3, pad) */
+int gsc_test_sphere_obb(int device, size_t n, const float *s4, const float *obb16, uint8_t *out);
+/* OBB::test_obb (mod.rs:413-546): a.test_obb(&b) */
+int gsc_test_obb_obb(int device, size_t n, const float *a16, const float *b16, uint8_t *out);
+/* AABB::test_aabb (bounding_volume.rs:338-343); AABBs as (min xyz, max xyz) */
+int gsc_test_aabb_aabb(int device, size_t n, const float *a6, const float *b6, uint8_t *out);
+/* FnvHasher over GridCell (lib/hash/src/fnv.rs:21-38, grid_collision.rs:523-528); cells as i16 xyz */
+int gsc_fnv1a_gridcell(int device, size_t n, const int16_t *cells3, uint64_t *out);
+/* the radix sort used on (cell, collider) keys, exposed for testing: stable LSD over `key_bits` bits */
+int gsc_sort_pairs_u32(int device, size_t n, uint32_t *keys, uint32_t *vals, int key_bits);
+
+/* ---- multi-GPU slab support (x-slab partition, one context per GPU, host layer does the exchange) ----
+ * A step on rank r is:  gsc_phase_bounds -> [all-reduce of 7 floats] -> gsc_set_global_bounds ->
+ * gsc_halo_select(x range of a neighbour) -> [send/recv of halo records] -> gsc_halo_append ->
+ * gsc_phase_finish.  Single-GPU callers use gsc_step, which runs the same stages back to back. */
+typedef struct gsc_bounds {
+    float longest_axis;  /* max AABB extent over the local colliders */
+    float world_min[3];  /* min over local AABB mins */
+    float world_max[3];  /* max over local AABB maxs */
+    uint32_t status_flags;
+} gsc_bounds;
+
+/* stage 0 on the local colliders; returns the local bounds */
+int gsc_phase_bounds(gsc_ctx *ctx, gsc_bounds *local);
+/* install the globally reduced bounds (max of longest_axis, min of world_min, max of world_max) */
+int gsc_set_global_bounds(gsc_ctx *ctx, const gsc_bounds *global);
+/* local min/max x-cell of the local colliders' home cells (needs global bounds) */
+int gsc_local_x_range(gsc_ctx *ctx, int32_t *x_min, int32_t *x_max);
+/* gather into a device staging buffer the local colliders whose home x-cell lies in
+ * [x_lo, x_hi]; returns the count and DEVICE pointers to packed records:
+ * rec (32 B each) and obb (64 B each) in matching order */
+int gsc_halo_select(gsc_ctx *ctx, int32_t x_lo, int32_t x_hi, uint32_t *count,
+                    const void **d_rec32, const void **d_obb64);
+/* append `count` ghost colliders (records produced by gsc_halo_select on another rank, DEVICE
+ * memory); ghosts take part as the earlier volume of a pair only */
+int gsc_halo_append(gsc_ctx *ctx, uint32_t count, const void *d_rec32, const void *d_obb64);
+/* stages 1..5 on local + ghost colliders */
+int gsc_phase_finish(gsc_ctx *ctx, gsc_step_out *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GUNSHIP_COLLISION_H */
