@@ -100,7 +100,7 @@ def workload_name(cfg: int, n: int) -> str:
     return f"configs[{cfg - 1}]: {n} colliders, {names[cfg]}"
 
 
-def stage_bytes(n, f_box, n_cells, passes, n_pairs, n_so, n_oo, neigh_reads):
+def stage_bytes(n, f_box, n_cells, passes, n_pairs, n_so, n_oo, n_ss):
     """Algorithmic HBM bytes per stage: every array a stage must read or write once."""
     b = {}
     # bvh_update: kind 1 + offset 12 + size 12 + pos 12 + entity 4 (+ quat 16 + scale 12 for boxes); writes rec 32 (+ obb 64)
@@ -111,10 +111,10 @@ def stage_bytes(n, f_box, n_cells, passes, n_pairs, n_so, n_oo, neigh_reads):
     b["sort"] = n * (12 + 16 * max(passes - 1, 0))
     # cell table + permute: read key 4 + idx 4 + rec 32 (gather), write rec 32 + table 4 per cell
     b["cell_table"] = n * 72 + n_cells * 4
-    # pairs: read sorted rec 32 + key 4 once (neighbour re-reads are served by L1/L2), table lookups, write pairs/candidates
-    b["pairs"] = n * 36 + n_pairs * 8 + (n_so + n_oo) * 8
-    # narrow: read candidates 8, sphere rec 32 + obb 64 / 2 x obb 64 per candidate, write hits
-    b["narrow"] = n_so * (8 + 96) + n_oo * (8 + 128)
+    # pairs: read sorted rec 32 + key 4 once (neighbour re-reads are served by L1/L2), write the candidate lists
+    b["pairs"] = n * 36 + (n_ss + n_so + n_oo) * 8
+    # narrow: read candidates 8 + 2 x sphere rec 32 / sphere rec 32 + obb 64 / 2 x obb 64 per candidate, write hits
+    b["narrow"] = n_ss * (8 + 64) + n_so * (8 + 96) + n_oo * (8 + 128) + n_pairs * 8
     return b
 
 
@@ -224,7 +224,7 @@ def main():
         out = step_resident(args.warmup + i)
         dev_ms.append(out.step_ms)
         stage_ms += np.array(list(out.stage_ms))
-        outs.append((out.n_pairs, out.n_sphere_obb, out.n_obb_obb, out.n_cells, out.sort_passes))
+        outs.append((out.n_pairs, out.n_sphere_obb, out.n_obb_obb, out.n_cells, out.sort_passes, out.n_sphere_sphere))
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -264,7 +264,7 @@ def main():
     peak, peak_kind = measured_peak_gbs()
     mean = np.mean(np.array(outs, dtype=np.float64), axis=0)
     from gunship_rs_b200._native import STAGE_NAMES
-    sb = stage_bytes(n, f_box, mean[3], int(mean[4]), mean[0], mean[1], mean[2], 0)
+    sb = stage_bytes(n, f_box, mean[3], int(mean[4]), mean[0], mean[1], mean[2], mean[5])
     dom = int(np.argmax(stage_ms))
     dom_name = STAGE_NAMES[dom]
     launches_in_stage = {"sort": int(mean[4])}.get(dom_name, 1)
@@ -283,7 +283,7 @@ def main():
         "p50_step_ms": float(np.median(dev_ms)), "device_ms_per_step": float(np.mean(dev_ms)),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": 1e3 * wall_e2e / args.steps,
                 "h2d_bytes_per_step": n * 28, "d2h_bytes_per_step": int(d2h / args.steps)},
-        "gpu_launches": 12 * args.steps,
+        "gpu_launches": 13 * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,

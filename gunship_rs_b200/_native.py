@@ -37,7 +37,7 @@ class GscConfig(C.Structure):
 
 
 class GscStepOut(C.Structure):
-    _fields_ = [("n_pairs", C.c_uint64), ("n_sphere_obb", C.c_uint64), ("n_obb_obb", C.c_uint64),
+    _fields_ = [("n_pairs", C.c_uint64), ("n_sphere_sphere", C.c_uint64), ("n_sphere_obb", C.c_uint64), ("n_obb_obb", C.c_uint64),
                 ("n_cells", C.c_uint64), ("cell_size", C.c_float), ("n_wide", C.c_uint32),
                 ("grid_origin", C.c_int32 * 3), ("grid_dims", C.c_int32 * 3), ("sort_passes", C.c_uint32),
                 ("status_flags", C.c_uint32), ("stage_ms", C.c_float * GSC_NUM_STAGES), ("step_ms", C.c_float),

@@ -54,7 +54,7 @@ struct gsc_ctx {
     float4 *d_rec = nullptr, *d_rec_sorted = nullptr, *d_obb = nullptr;
     uint32_t *d_keys[2] = { nullptr, nullptr }, *d_vals[2] = { nullptr, nullptr };
     uint32_t *d_cell_start = nullptr, *d_wide = nullptr;
-    uint2 *d_pairs = nullptr, *d_cand_so = nullptr, *d_cand_oo = nullptr;
+    uint2 *d_pairs = nullptr, *d_cand_ss = nullptr, *d_cand_so = nullptr, *d_cand_oo = nullptr;
     uint2 *d_pairs_sorted = nullptr;
     FrameBlock *d_fb = nullptr;
     FrameBlock *h_fb = nullptr;  // pinned
@@ -211,6 +211,7 @@ int gsc_create(const gsc_config *cfg, gsc_ctx **out)
     CR(dmalloc(&c->d_cell_start, c->max_cells + 2));
     CR(dmalloc(&c->d_wide, M));
     CR(dmalloc(&c->d_pairs, c->max_pairs));
+    CR(dmalloc(&c->d_cand_ss, c->max_cands));
     CR(dmalloc(&c->d_cand_so, c->max_cands));
     CR(dmalloc(&c->d_cand_oo, c->max_cands));
     CR(dmalloc(&c->d_fb, 1));
@@ -239,7 +240,7 @@ void gsc_destroy(gsc_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *bufs[] = { c->d_entity, c->d_gidx, c->d_kind, c->d_offset, c->d_size, c->d_pos, c->d_quat, c->d_scale, c->d_rec,
                      c->d_rec_sorted, c->d_obb, c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1], c->d_cell_start,
-                     c->d_wide, c->d_pairs, c->d_cand_so, c->d_cand_oo, c->d_pairs_sorted, c->d_fb, c->d_lookback,
+                     c->d_wide, c->d_pairs, c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->d_pairs_sorted, c->d_fb, c->d_lookback,
                      c->d_halo_rec, c->d_halo_obb, c->d_halo_count };
     for (void *b : bufs)
         if (b) cudaFree(b);
@@ -352,13 +353,16 @@ static int stage_finish(gsc_ctx *c, gsc_step_out *out)
                     fb->tile_counter);
         if (timing) CU(c, cudaEventRecord(c->ev[3], s));
         const uint32_t tb = (n_total + 1 + kTableThreads - 1) / kTableThreads;
+        SortedVolumes sv{ c->d_rec_sorted, c->d_rec_sorted + c->cap };
         k_cell_table_permute<<<tb, kTableThreads, 0, s>>>(n_total, c->d_keys[0], c->d_vals[0], c->d_keys[1], c->d_vals[1],
-                                                         c->d_rec, c->d_rec_sorted, c->d_cell_start, fb);
+                                                         c->d_rec, sv, c->d_cell_start, fb);
         if (timing) CU(c, cudaEventRecord(c->ev[4], s));
-        PairOut po{ c->d_pairs, c->d_cand_so, c->d_cand_oo, c->max_pairs, c->max_cands };
+        PairOut po{ c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands };
         const uint32_t pb = (n_total + kPairThreads - 1) / kPairThreads;
-        k_pairs<<<pb, kPairThreads, 0, s>>>(n_total, c->d_keys[0], c->d_keys[1], c->d_rec_sorted, c->d_cell_start, po, fb);
+        k_pairs<<<pb, kPairThreads, 0, s>>>(n_total, c->d_keys[0], c->d_keys[1], sv, c->d_cell_start, po, fb);
         if (timing) CU(c, cudaEventRecord(c->ev[5], s));
+        k_narrow_sphere_sphere<<<kGridStrideBlocks, kNarrowThreads, 0, s>>>(c->d_cand_ss, c->max_cands, c->d_rec, c->d_pairs,
+                                                                          c->max_pairs, fb);
         k_narrow_sphere_obb<<<kGridStrideBlocks, kNarrowThreads, 0, s>>>(c->d_cand_so, c->max_cands, c->d_rec, c->d_obb,
                                                                        c->d_pairs, c->max_pairs, fb);
         k_narrow_obb_obb<<<kGridStrideBlocks, kNarrowThreads, 0, s>>>(c->d_cand_oo, c->max_cands, c->d_obb, c->d_pairs,
@@ -380,6 +384,7 @@ static int stage_finish(gsc_ctx *c, gsc_step_out *out)
     if (out) {
         memset(out, 0, sizeof *out);
         out->n_pairs = h.n_pairs;
+        out->n_sphere_sphere = h.n_ss;
         out->n_sphere_obb = h.n_so;
         out->n_obb_obb = h.n_oo;
         out->n_cells = h.grid.num_cells;
@@ -397,9 +402,10 @@ static int stage_finish(gsc_ctx *c, gsc_step_out *out)
             for (int i = 0; i < GSC_NUM_STAGES; ++i) cudaEventElapsedTime(&out->stage_ms[i], c->ev[i], c->ev[i + 1]);
     }
     if (int rc = status_to_error(c, h)) { c->last_pairs = 0; return rc; }
-    if (h.n_so > c->max_cands || h.n_oo > c->max_cands)
-        return fail(c, GSC_ERR_CAPACITY, "candidate list overflow: need %llu / %llu, have %llu (gsc_config.max_candidates)",
-                    (unsigned long long)h.n_so, (unsigned long long)h.n_oo, (unsigned long long)c->max_cands);
+    if (h.n_ss > c->max_cands || h.n_so > c->max_cands || h.n_oo > c->max_cands)
+        return fail(c, GSC_ERR_CAPACITY, "candidate list overflow: need %llu / %llu / %llu, have %llu (gsc_config.max_candidates)",
+                    (unsigned long long)h.n_ss, (unsigned long long)h.n_so, (unsigned long long)h.n_oo,
+                    (unsigned long long)c->max_cands);
     if (h.n_pairs > c->max_pairs)
         return fail(c, GSC_ERR_CAPACITY, "pair buffer overflow: need %llu, have %llu (gsc_config.max_pairs)",
                     (unsigned long long)h.n_pairs, (unsigned long long)c->max_pairs);

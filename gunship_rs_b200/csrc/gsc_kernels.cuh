@@ -80,7 +80,7 @@ struct FrameBlock {
     uint32_t bounds[8];  // [0] ord(longest axis); [1..3] ~ord(world min xyz); [4..6] ord(world max xyz)
     uint32_t status;
     uint32_t n_wide;
-    unsigned long long n_pairs, n_so, n_oo;
+    unsigned long long n_pairs, n_ss, n_so, n_oo;
     uint32_t tile_counter[kMaxPasses];
     uint32_t xrange[2];  // ~(min home x + 32768), (max home x + 32768) of local volumes
     uint32_t pad[2];
@@ -269,8 +269,9 @@ __global__ void k_grid_setup(FrameBlock *fb, unsigned long long max_cells, uint3
             const float hi = cell_coord_f(ord2f(fb->bounds[4 + a]), g.cell_size);
             // GridCoord = i16 (grid_collision.rs:535): outside it the reference's cast is undefined
             if (!(lo >= -32768.0f) || !(hi <= 32767.0f)) { st |= kStRange; break; }
-            g.origin[a] = (int32_t)lo;
-            g.dims[a] = (int32_t)hi - (int32_t)lo + 1;
+            // one apron cell on every side: neighbour keys of any home cell are valid cells (k_pairs)
+            g.origin[a] = (int32_t)lo - 1;
+            g.dims[a] = (int32_t)hi - (int32_t)lo + 3;
             cells *= (unsigned long long)g.dims[a];
         }
         if (st == 0) {
@@ -336,6 +337,16 @@ k_cell_keys(uint32_t n_total, const float4 *__restrict__ rec, uint32_t *__restri
     }
 }
 
+// Cell-ordered volumes, the arrays k_pairs streams (two float4 planes, 32 B per volume):
+//   a = (min.x, min.y, min.z, max.x)   b = (max.y, max.z, global index bits, meta)
+// meta of the sorted copy additionally carries kMetaReachY / kMetaReachZ: the AABB's max corner lies in
+// the next cell along y / z (cell(max) > cell(min)), which is what lets k_pairs prune rows exactly.
+constexpr uint32_t kMetaReachY = 4u, kMetaReachZ = 8u;
+
+struct SortedVolumes {
+    float4 *a, *b;
+};
+
 // ---- stage 3: cell start table + cell-order permutation of the volume records ---------------------
 // start[c] = first sorted position whose key >= c, for c in [0, num_cells]; thread p fills the gap
 // (key[p-1], key[p]].  Long gaps (empty space) are filled by the whole warp.
@@ -344,7 +355,7 @@ constexpr int kTableThreads = 256;
 __global__ void __launch_bounds__(kTableThreads)
 k_cell_table_permute(uint32_t n_total, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ vals_a,
                      const uint32_t *__restrict__ keys_b, const uint32_t *__restrict__ vals_b,
-                     const float4 *__restrict__ rec, float4 *__restrict__ rec_sorted,
+                     const float4 *__restrict__ rec, SortedVolumes sv,
                      uint32_t *__restrict__ cell_start, const FrameBlock *__restrict__ fb)
 {
     const GridParams g = fb->grid;
@@ -362,9 +373,12 @@ k_cell_table_permute(uint32_t n_total, const uint32_t *__restrict__ keys_a, cons
     }
     if (p < n_total) {
         const uint32_t i = vals[p];
-        const float4 r0 = __ldg(rec + 2 * (size_t)i), r1 = __ldg(rec + 2 * (size_t)i + 1);
-        rec_sorted[2 * (size_t)p] = r0;
-        rec_sorted[2 * (size_t)p + 1] = r1;
+        const Volume v = volume_decode(__ldg(rec + 2 * (size_t)i), __ldg(rec + 2 * (size_t)i + 1));
+        uint32_t meta = v.meta;
+        if (cell_coord_f(v.mx[1], g.cell_size) > cell_coord_f(v.mn[1], g.cell_size)) meta |= kMetaReachY;
+        if (cell_coord_f(v.mx[2], g.cell_size) > cell_coord_f(v.mn[2], g.cell_size)) meta |= kMetaReachZ;
+        sv.a[p] = make_float4(v.mn[0], v.mn[1], v.mn[2], v.mx[0]);
+        sv.b[p] = make_float4(v.mx[1], v.mx[2], __uint_as_float(v.gidx), __uint_as_float(meta));
     }
     const int64_t len = hi - lo + 1;
     const bool is_long = len > 8;
@@ -382,108 +396,189 @@ k_cell_table_permute(uint32_t n_total, const uint32_t *__restrict__ keys_a, cons
     }
 }
 
-// ---- stage 4: neighbour-cell pair enumeration + AABB test + sphere-sphere --------------------------
+// ---- stage 4: neighbour-cell pair enumeration + AABB filter ----------------------------------------
 // One thread per cell-sorted volume A.  Candidates B are the volumes of the 13 cells that precede A's
-// home cell in key order among its 26 neighbours (5 z-rows) plus A's own cell; a pair inside one cell
-// is taken by the member with the larger global index.  So every unordered pair is visited exactly
-// once -- the sort order itself is the dedupe that the reference does with a HashMap
-// (grid_collision.rs:497-511).  Sphere-sphere pairs are finished here; pairs involving a box that
-// pass the AABB test are deferred to the SAT kernels (uniform work there, no divergence here).
+// home cell in key order among its 26 neighbours plus A's own cell; a pair inside one cell is taken by
+// the member with the larger global index.  Every unordered pair is therefore visited exactly once --
+// the sort order itself is the dedupe that the reference does with a HashMap (grid_collision.rs:497-511).
+//
+// Because keys are x-major / z-minor and start[] is monotone, the candidates of A are FIVE contiguous
+// runs of the cell-sorted arrays, one per (dx, dy) row: (-1,-1) (-1,0) (-1,+1) (0,-1) (0,0), each
+// covering cells z-1 .. z+1 (z-1 .. z for the own row).  The grid carries a one-cell apron of empty
+// cells, so neighbour keys are plain offsets of A's key and never need a bounds check.  Rows / cells
+// that A's own AABB cannot reach are pruned exactly: B in row y+1 (or cell z+1) means
+// cell(B.min) > cell(A.max) there, hence B.min > A.max by monotonicity of floor(fl(p / c)), hence
+// test_ranges fails.
+//
+// The kernel is an instruction-issue-bound filter (22 AABB tests per volume on the clustered scene, 1.3
+// survive), so the loop is kept minimal: each lane walks its five runs as one flat loop doing only the
+// inclusive AABB overlap test on the precomputed boxes; the rare survivor is classified by the two
+// kinds and pushed into a CTA-wide shared-memory list per class.  When the CTA is done ONE atomicAdd
+// per class reserves its slice of the global candidate lists and the lists are copied out coalesced;
+// the shape tests then run as separate, perfectly balanced kernels over those lists (stage 5).
 constexpr int kPairThreads = 256;
-constexpr int kPairWarps = kPairThreads / 32;
-constexpr int kPairCap = 96;
+constexpr int kPairRows = 5;
+constexpr int kPairCapSS = 768, kPairCapSO = 1024, kPairCapOO = 768;  // survivors staged per CTA and class
+constexpr int kPairCapAll = kPairCapSS + kPairCapSO + kPairCapOO;
 
 struct PairOut {
-    uint2 *pairs;
+    uint2 *cand_ss;
     uint2 *cand_so;
     uint2 *cand_oo;
-    unsigned long long cap_pairs, cap_cands;
+    unsigned long long cap_cands;
 };
 
-__global__ void __launch_bounds__(kPairThreads)
+struct PairShared {
+    uint2 buf[kPairCapAll];
+    uint32_t rq[kPairRows - 1][kPairThreads], rqe[kPairRows - 1][kPairThreads];
+    uint32_t cnt[4];
+    unsigned long long base[3];
+};
+
+__global__ void __launch_bounds__(kPairThreads, 6)
 k_pairs(uint32_t n_total, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ keys_b,
-        const float4 *__restrict__ rec_sorted, const uint32_t *__restrict__ cell_start, PairOut out,
-        FrameBlock *__restrict__ fb)
+        SortedVolumes sv, const uint32_t *__restrict__ cell_start, PairOut out, FrameBlock *__restrict__ fb)
 {
-    __shared__ EmitBuf<kPairWarps, kPairCap> s_pairs, s_so, s_oo;
+    __shared__ PairShared sh;
     const GridParams g = fb->grid;
     if (!g.valid) return;
     const uint32_t *keys = (fb->sort.num_passes & 1) ? keys_b : keys_a;
-    emit_init(s_pairs);
-    emit_init(s_so);
-    emit_init(s_oo);
+    const int tid = threadIdx.x;
+    if (tid < 4) sh.cnt[tid] = 0;
     __syncthreads();
 
-    const uint32_t p = blockIdx.x * kPairThreads + threadIdx.x;
-    bool active = p < n_total;
-    Volume A;
-    uint32_t key = 0;
-    if (active) {
-        A = volume_decode(__ldg(rec_sorted + 2 * (size_t)p), __ldg(rec_sorted + 2 * (size_t)p + 1));
-        key = keys[p];
+    const uint32_t p = blockIdx.x * kPairThreads + tid;
+    float amn0 = 0.f, amn1 = 0.f, amn2 = 0.f, amx0 = 0.f, amx1 = 0.f, amx2 = 0.f;
+    uint32_t a_gidx = 0, a_meta = 0;
+    uint32_t q = 0, qe = 0, qsame = 0;
+    if (p < n_total) {
+        const float4 a0 = __ldg(sv.a + p), a1 = __ldg(sv.b + p);
+        const uint32_t key = keys[p];
+        a_meta = __float_as_uint(a1.w);
+        a_gidx = __float_as_uint(a1.z);
+        amn0 = a0.x; amn1 = a0.y; amn2 = a0.z;
+        amx0 = a0.w; amx1 = a1.x; amx2 = a1.y;
         // ghosts only serve as the earlier volume; wide volumes (key == num_cells) go to k_wide_pairs
-        if ((A.meta & kMetaGhost) || key >= g.num_cells) active = false;
+        const bool active = !(a_meta & kMetaGhost) && key < g.num_cells;
+        const uint32_t dz = (uint32_t)g.dims[2], dydz = (uint32_t)g.dims[1] * dz;
+        const uint32_t zhi = (a_meta & kMetaReachZ) ? 2u : 1u;  // end = start[kk + zhi]
+        const bool ry = a_meta & kMetaReachY;
+        uint32_t lo[kPairRows], hi[kPairRows];
+#pragma unroll
+        for (int r = 0; r < kPairRows; ++r) {
+            // row base key kk = key + dx * dims.y * dims.z + dy * dims.z  (apron => always a valid cell)
+            const uint32_t kk = key - (r < 3 ? dydz : 0u) + (r == 2 ? dz : 0u) - ((r == 0 || r == 3) ? dz : 0u);
+            const bool use = active && (r != 2 || ry);
+            lo[r] = use ? __ldg(cell_start + kk - 1) : 0u;
+            hi[r] = use ? __ldg(cell_start + kk + (r == 4 ? 1u : zhi)) : 0u;
+        }
+        qsame = active ? __ldg(cell_start + key) : 0u;
+        q = lo[0];
+        qe = hi[0];
+#pragma unroll
+        for (int r = 1; r < kPairRows; ++r) {
+            sh.rq[r - 1][tid] = lo[r];
+            sh.rqe[r - 1][tid] = hi[r];
+        }
+    } else {
+#pragma unroll
+        for (int r = 1; r < kPairRows; ++r) {
+            sh.rq[r - 1][tid] = 0;
+            sh.rqe[r - 1][tid] = 0;
+        }
     }
-    const uint32_t dy = (uint32_t)g.dims[1], dz = (uint32_t)g.dims[2];
-    const int x = (int)(key / (dy * dz));
-    const uint32_t rem = key - (uint32_t)x * dy * dz;
-    const int y = (int)(rem / dz);
-    const int z = (int)(rem - (uint32_t)y * dz);
 
-#pragma unroll 1
-    for (int r = 0; r < 5; ++r) {
-        const int xx = x + (r < 3 ? -1 : 0);
-        const int yy = y + (r < 3 ? r - 1 : r - 4);
-        uint32_t q = 0, qe = 0, qsame = 0xffffffffu;
-        if (active && xx >= 0 && yy >= 0 && yy < (int)dy) {
-            const uint32_t base = ((uint32_t)xx * dy + (uint32_t)yy) * dz;
-            const int z0 = max(z - 1, 0);
-            const int z1 = (r == 4) ? z : min(z + 1, (int)dz - 1);
-            q = __ldg(cell_start + base + z0);
-            qe = __ldg(cell_start + base + z1 + 1);
-            if (r == 4) qsame = __ldg(cell_start + base + z);
+    const uint32_t a_local = a_meta >> 4;
+    const bool a_box = a_meta & kMetaBox;
+    int r = 0;
+    for (;;) {
+        if (q >= qe) {
+            if (r == kPairRows - 1) break;
+            q = sh.rq[r][tid];
+            qe = sh.rqe[r][tid];
+            ++r;
+            continue;
         }
-        while (__any_sync(0xffffffffu, q < qe)) {
-            bool hit = false, so = false, oo = false;
-            uint2 item = make_uint2(0, 0);
-            if (q < qe) {
-                const Volume B = volume_decode(__ldg(rec_sorted + 2 * (size_t)q), __ldg(rec_sorted + 2 * (size_t)q + 1));
-                const bool take = (q < qsame) || (B.gidx < A.gidx);
-                if (take && test_aabb(A.mn, A.mx, B.mn, B.mx)) {
-                    const bool a_hi = A.gidx > B.gidx;  // tuple = (later index, earlier index), grid_collision.rs:440,497
-                    const bool a_box = A.meta & kMetaBox, b_box = B.meta & kMetaBox;
-                    if (!a_box && !b_box) {
-                        hit = test_sphere_sphere(A.cx, A.cy, A.cz, A.r, B.cx, B.cy, B.cz, B.r);
-                        item = a_hi ? make_uint2(A.entity, B.entity) : make_uint2(B.entity, A.entity);
-                    } else {
-                        const uint32_t la = A.meta >> 4, lb = B.meta >> 4;
-                        const uint32_t hi = a_hi ? la : lb, lo = a_hi ? lb : la;
-                        if (a_box && b_box) {
-                            oo = true;
-                            item = make_uint2(hi, lo);
-                        } else {
-                            so = true;
-                            const bool hi_is_sphere = a_hi ? !a_box : !b_box;
-                            item = make_uint2(hi | (hi_is_sphere ? 0x80000000u : 0u), lo);
-                        }
-                    }
-                }
-                ++q;
+        const float4 b0 = __ldg(sv.a + q), b1 = __ldg(sv.b + q);
+        const uint32_t b_gidx = __float_as_uint(b1.z);
+        // AABB::test_aabb (bounding_volume.rs:338-343, 411-419), inclusive
+        const bool sep = amn0 > b0.w || b0.x > amx0 || amn1 > b1.x || b0.y > amx1 || amn2 > b1.y || b0.z > amx2;
+        const bool take = (q < qsame) || (b_gidx < a_gidx);
+        ++q;
+        if (!sep && take) {
+            const uint32_t b_meta = __float_as_uint(b1.w);
+            const bool b_box = b_meta & kMetaBox;
+            const uint32_t b_local = b_meta >> 4;
+            const bool a_hi = a_gidx > b_gidx;  // tuple = (later index, earlier index), grid_collision.rs:440,497
+            uint32_t hi_l = a_hi ? a_local : b_local;
+            const uint32_t lo_l = a_hi ? b_local : a_local;
+            const int cls = (int)a_box + (int)b_box;  // 0 sphere-sphere, 1 sphere-box, 2 box-box
+            if (cls == 1 && (a_hi ? !a_box : !b_box)) hi_l |= 0x80000000u;  // the later volume is the sphere
+            const uint32_t off = cls == 0 ? 0u : (cls == 1 ? (uint32_t)kPairCapSS : (uint32_t)(kPairCapSS + kPairCapSO));
+            const uint32_t cap = cls == 0 ? (uint32_t)kPairCapSS : (cls == 1 ? (uint32_t)kPairCapSO : (uint32_t)kPairCapOO);
+            const uint32_t slot = atomicAdd(&sh.cnt[cls], 1u);
+            if (slot < cap) {
+                sh.buf[off + slot] = make_uint2(hi_l, lo_l);
+            } else {  // CTA list full (very dense cells): straight to the global list
+                unsigned long long *ctr = cls == 0 ? &fb->n_ss : (cls == 1 ? &fb->n_so : &fb->n_oo);
+                uint2 *dst = cls == 0 ? out.cand_ss : (cls == 1 ? out.cand_so : out.cand_oo);
+                const unsigned long long at = atomicAdd(ctr, 1ull);
+                if (at < out.cap_cands) dst[at] = make_uint2(hi_l, lo_l);
             }
-            emit(s_pairs, hit, item, out.pairs, &fb->n_pairs, out.cap_pairs);
-            emit(s_so, so, item, out.cand_so, &fb->n_so, out.cap_cands);
-            emit(s_oo, oo, item, out.cand_oo, &fb->n_oo, out.cap_cands);
         }
     }
-    emit_finish(s_pairs, out.pairs, &fb->n_pairs, out.cap_pairs);
-    emit_finish(s_so, out.cand_so, &fb->n_so, out.cap_cands);
-    emit_finish(s_oo, out.cand_oo, &fb->n_oo, out.cap_cands);
+    __syncthreads();
+    if (tid < 3) {
+        const uint32_t cap = tid == 0 ? (uint32_t)kPairCapSS : (tid == 1 ? (uint32_t)kPairCapSO : (uint32_t)kPairCapOO);
+        const uint32_t have = min(sh.cnt[tid], cap);
+        sh.cnt[tid] = have;
+        unsigned long long *ctr = tid == 0 ? &fb->n_ss : (tid == 1 ? &fb->n_so : &fb->n_oo);
+        sh.base[tid] = have ? atomicAdd(ctr, (unsigned long long)have) : 0ull;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int cls = 0; cls < 3; ++cls) {
+        const uint32_t off = cls == 0 ? 0u : (cls == 1 ? (uint32_t)kPairCapSS : (uint32_t)(kPairCapSS + kPairCapSO));
+        uint2 *dst = cls == 0 ? out.cand_ss : (cls == 1 ? out.cand_so : out.cand_oo);
+        const uint32_t have = sh.cnt[cls];
+        const unsigned long long base = sh.base[cls];
+        for (uint32_t i = tid; i < have; i += kPairThreads)
+            if (base + i < out.cap_cands) dst[base + i] = sh.buf[off + i];
+    }
 }
 
 // ---- stage 5: SAT narrowphase over the deferred candidates ------------------------------------------
 constexpr int kNarrowThreads = 256;
 constexpr int kNarrowWarps = kNarrowThreads / 32;
 constexpr int kNarrowCap = 96;
+
+// Sphere::test_sphere (mod.rs:383-389): later.test_sphere(earlier); spheres come from the volume records
+__global__ void __launch_bounds__(kNarrowThreads)
+k_narrow_sphere_sphere(const uint2 *__restrict__ cand, unsigned long long cap_cands, const float4 *__restrict__ rec,
+                       uint2 *__restrict__ pairs, unsigned long long cap_pairs, FrameBlock *__restrict__ fb)
+{
+    __shared__ EmitBuf<kNarrowWarps, kNarrowCap> s_out;
+    emit_init(s_out);
+    __syncthreads();
+    const unsigned long long n = min(fb->n_ss, cap_cands);
+    const unsigned long long stride = (unsigned long long)gridDim.x * kNarrowThreads;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * kNarrowThreads; b < n; b += stride) {
+        const unsigned long long i = b + threadIdx.x;
+        bool hit = false;
+        uint2 item = make_uint2(0, 0);
+        if (i < n) {
+            const uint2 c = cand[i];
+            const float4 h0 = __ldg(rec + 2 * (size_t)c.x), l0 = __ldg(rec + 2 * (size_t)c.y);
+            hit = test_sphere_sphere(h0.x, h0.y, h0.z, h0.w, l0.x, l0.y, l0.z, l0.w);
+            if (hit) {
+                const float4 h1 = __ldg(rec + 2 * (size_t)c.x + 1), l1 = __ldg(rec + 2 * (size_t)c.y + 1);
+                item = make_uint2(__float_as_uint(h1.x), __float_as_uint(l1.x));
+            }
+        }
+        emit(s_out, hit, item, pairs, &fb->n_pairs, cap_pairs);
+    }
+    emit_finish(s_out, pairs, &fb->n_pairs, cap_pairs);
+}
 
 // Sphere::test_obb (mod.rs:391-394) -- either order of the pair calls sphere.test_obb(obb) (mod.rs:378,407)
 __global__ void __launch_bounds__(kNarrowThreads)

@@ -55,8 +55,8 @@ enum {
     GSC_STAGE_CELL_KEYS  = 1, /* world_to_grid + cell keys + digit histograms */
     GSC_STAGE_SORT       = 2, /* radix sort of (cell, collider) */
     GSC_STAGE_CELL_TABLE = 3, /* cell start table + cell-order permutation of the volumes */
-    GSC_STAGE_PAIRS      = 4, /* neighbour-cell pair enumeration + AABB test + sphere-sphere */
-    GSC_STAGE_NARROW     = 5, /* sphere-OBB and OBB-OBB SAT over the deferred candidates (+ wide volumes) */
+    GSC_STAGE_PAIRS      = 4, /* neighbour-cell pair enumeration + AABB test -> candidate lists per shape pair */
+    GSC_STAGE_NARROW     = 5, /* sphere-sphere, sphere-OBB and OBB-OBB SAT over the candidates (+ wide volumes) */
     GSC_NUM_STAGES       = 6
 };
 
@@ -66,7 +66,7 @@ typedef struct gsc_config {
     int32_t  device;         /* CUDA device ordinal */
     uint32_t max_colliders;  /* capacity: local colliders + ghosts received from other slabs */
     uint64_t max_pairs;      /* capacity of the contact-pair buffer (0 = 8 * max_colliders + 65536) */
-    uint64_t max_candidates; /* capacity of each deferred box-candidate list (0 = 8 * max_colliders + 65536) */
+    uint64_t max_candidates; /* capacity of each of the three candidate lists (0 = 8 * max_colliders + 65536) */
     uint64_t max_cells;      /* capacity of the dense cell table (0 = 16 * max_colliders + 2^20) */
     uint32_t flags;          /* GSC_FLAG_* */
     uint32_t reserved;
@@ -74,6 +74,7 @@ typedef struct gsc_config {
 
 typedef struct gsc_step_out {
     uint64_t n_pairs;        /* contact pairs found (may exceed max_pairs on GSC_ERR_CAPACITY) */
+    uint64_t n_sphere_sphere;/* AABB-overlapping sphere/sphere candidates handed to the shape-test stage */
     uint64_t n_sphere_obb;   /* AABB-overlapping sphere/box candidates handed to the SAT stage */
     uint64_t n_obb_obb;      /* AABB-overlapping box/box candidates handed to the SAT stage */
     uint64_t n_cells;        /* cells of the dense grid this frame */
