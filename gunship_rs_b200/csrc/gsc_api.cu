@@ -353,7 +353,7 @@ static int stage_finish(gsc_ctx *c, gsc_step_out *out)
                     fb->tile_counter);
         if (timing) CU(c, cudaEventRecord(c->ev[3], s));
         const uint32_t tb = (n_total + 1 + kTableThreads - 1) / kTableThreads;
-        SortedVolumes sv{ c->d_rec_sorted, c->d_rec_sorted + c->cap };
+        SortedVolumes sv{ c->d_rec_sorted };
         k_cell_table_permute<<<tb, kTableThreads, 0, s>>>(n_total, c->d_keys[0], c->d_vals[0], c->d_keys[1], c->d_vals[1],
                                                          c->d_rec, sv, c->d_cell_start, fb);
         if (timing) CU(c, cudaEventRecord(c->ev[4], s));
