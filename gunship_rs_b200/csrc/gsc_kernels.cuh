@@ -411,16 +411,18 @@ k_cell_table_permute(uint32_t n_total, const uint32_t *__restrict__ keys_a, cons
 // test_ranges fails.
 //
 // The kernel is an instruction-issue-bound filter (22 AABB tests per volume on the clustered scene, 1.3
-// survive), so the loop is kept minimal: each lane walks its five runs doing only the inclusive AABB
-// overlap test on the precomputed boxes; the rare survivor is pushed as a bare (A position, B position)
-// pair into a CTA-wide shared-memory list.  When the CTA is done, all its threads classify the listed pairs by
-// the two kinds, orient them by global index and append them -- one atomicAdd per class and CTA -- to
-// the three global candidate lists; the shape tests then run as separate, perfectly balanced kernels
-// over those lists (stage 5).  Shared memory is kept small on purpose: the candidate boxes are read
-// through L1, which needs the carve-out.
+// survive), so the loop is kept minimal and branch-free: each lane walks its runs doing only the
+// inclusive AABB overlap test on the precomputed boxes; a survivor's position is stored with a
+// predicated write into a few PRIVATE shared-memory slots of the lane (no atomics, no divergent branch).
+// When the CTA is done the private slots are compacted into one CTA list (warp scan + one shared atomic
+// per warp); then all threads classify the listed (A, B) pairs by the two kinds, orient them by global
+// index and append them -- one atomicAdd per class and CTA -- to the three global candidate lists.  The
+// shape tests run as separate, perfectly balanced kernels over those lists (stage 5).  Shared memory is
+// kept small on purpose: the candidate boxes are read through L1, which needs the carve-out.
 constexpr int kPairThreads = 256;
 constexpr int kPairWarps = kPairThreads / 32;
 constexpr int kPairRows = 5;
+constexpr int kPairPriv = 8;    // private survivor slots per lane; a lane that fills them drains early
 constexpr int kPairCap = 1024;  // survivors staged per CTA (4 per volume); denser CTAs spill one by one
 
 struct PairOut {
@@ -431,9 +433,9 @@ struct PairOut {
 };
 
 struct PairShared {
+    uint32_t priv[kPairPriv * kPairThreads];  // slot-major: lane t owns priv[j * kPairThreads + t]
     uint2 list[kPairCap];
     uint32_t count;
-    uint32_t cls_count[3];
     uint32_t warp_cls[kPairWarps][3];
     unsigned long long base[3];
 };
@@ -464,7 +466,19 @@ __device__ __noinline__ void pair_spill(uint32_t p, uint32_t q, const float4 *__
     if (at < out.cap_cands) dst[at] = item;
 }
 
-__global__ void __launch_bounds__(kPairThreads, 6)
+// a lane whose private slots are (nearly) full moves them to the CTA list (rare: >= kPairPriv - 1 survivors)
+__device__ __noinline__ void pair_drain_lane(PairShared &sh, uint32_t p, uint32_t cnt, int tid, const float4 *__restrict__ sv,
+                                             PairOut out, FrameBlock *fb)
+{
+    const uint32_t at = atomicAdd(&sh.count, cnt);
+    for (uint32_t j = 0; j < cnt; ++j) {
+        const uint32_t q = sh.priv[j * kPairThreads + tid];
+        if (at + j < (uint32_t)kPairCap) sh.list[at + j] = make_uint2(p, q);
+        else pair_spill(p, q, sv, out, fb);
+    }
+}
+
+__global__ void __launch_bounds__(kPairThreads, 5)
 k_pairs(uint32_t n_total, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ keys_b,
         SortedVolumes sv, const uint32_t *__restrict__ cell_start, PairOut out, FrameBlock *__restrict__ fb)
 {
@@ -472,9 +486,8 @@ k_pairs(uint32_t n_total, const uint32_t *__restrict__ keys_a, const uint32_t *_
     const GridParams g = fb->grid;
     if (!g.valid) return;
     const uint32_t *keys = (fb->sort.num_passes & 1) ? keys_b : keys_a;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) sh.count = 0;
-    if (tid < 3) sh.cls_count[tid] = 0;
     __syncthreads();
 
     const uint32_t p = blockIdx.x * kPairThreads + tid;
@@ -509,28 +522,69 @@ k_pairs(uint32_t n_total, const uint32_t *__restrict__ keys_a, const uint32_t *_
     // The five runs are walked one after the other (row-outer): a warp then spends sum_r max_lane(len_r)
     // iterations instead of max_lane(sum_r len_r) -- 15% more on the clustered scene -- but the loop body
     // has no run-switching logic at all, and only the own row needs the same-cell ordering rule.
+    // next free private slot, as a shared-window byte address (st.shared with a plain register address)
+    const uint32_t pa0 = (uint32_t)__cvta_generic_to_shared(&sh.priv[tid]);
+    constexpr uint32_t kSlotStride = kPairThreads * 4u;
+    uint32_t pa = pa0;
+    auto test = [&](uint32_t q, const float4 b0, const float4 b1, bool own) {
+        // AABB::test_aabb (bounding_volume.rs:338-343, 411-419), inclusive
+        const bool sep = amn0 > b0.w || b0.x > amx0 || amn1 > b1.x || b0.y > amx1 || amn2 > b1.y || b0.z > amx2;
+        const bool take = !own || (q < qsame) || (__float_as_uint(b1.z) < a_gidx);
+        if (!sep && take) {
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(pa), "r"(q) : "memory");
+            pa += kSlotStride;
+        }
+    };
 #pragma unroll
     for (int r = 0; r < kPairRows; ++r) {
         const uint32_t qe = hi[r];
+        uint32_t q = lo[r];
+        const bool own = r == kPairRows - 1;
 #pragma unroll 1
-        for (uint32_t q = lo[r]; q < qe; ++q) {
-            const float4 b0 = __ldg(sv.v + 2 * (size_t)q), b1 = __ldg(sv.v + 2 * (size_t)q + 1);
-            // AABB::test_aabb (bounding_volume.rs:338-343, 411-419), inclusive
-            const bool sep = amn0 > b0.w || b0.x > amx0 || amn1 > b1.x || b0.y > amx1 || amn2 > b1.y || b0.z > amx2;
-            const bool take = (r < kPairRows - 1) || (q < qsame) || (__float_as_uint(b1.z) < a_gidx);
-            if (!sep && take) {
-                const uint32_t slot = atomicAdd(&sh.count, 1u);
-                if (slot < (uint32_t)kPairCap) sh.list[slot] = make_uint2(p, q);
-                else pair_spill(p, q, sv.v, out, fb);
+        for (; q + 1 < qe; q += 2) {  // two candidates per trip: both loads in flight before either test
+            const float4 *v = sv.v + 2 * (size_t)q;
+            const float4 b0 = __ldg(v), b1 = __ldg(v + 1), c0 = __ldg(v + 2), c1 = __ldg(v + 3);
+            test(q, b0, b1, own);
+            test(q + 1, c0, c1, own);
+            if (pa - pa0 >= (kPairPriv - 1) * kSlotStride) {  // fewer than two free slots left
+                pair_drain_lane(sh, p, (pa - pa0) / kSlotStride, tid, sv.v, out, fb);
+                pa = pa0;
+            }
+        }
+        if (q < qe) {
+            const float4 *v = sv.v + 2 * (size_t)q;
+            test(q, __ldg(v), __ldg(v + 1), own);
+            if (pa - pa0 >= (kPairPriv - 1) * kSlotStride) {
+                pair_drain_lane(sh, p, (pa - pa0) / kSlotStride, tid, sv.v, out, fb);
+                pa = pa0;
             }
         }
         __syncwarp();  // reconverge before the next run: lanes must walk each run together
+    }
+
+    // ---- compact the private slots into the CTA list: warp scan + one shared atomic per warp ----
+    {
+        const uint32_t cnt = (pa - pa0) / kSlotStride;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        uint32_t wbase = 0;
+        if (lane == 31 && incl) wbase = atomicAdd(&sh.count, incl);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        const uint32_t at = wbase + incl - cnt;
+        for (uint32_t j = 0; j < cnt; ++j) {
+            const uint32_t q = sh.priv[j * kPairThreads + tid];
+            if (at + j < (uint32_t)kPairCap) sh.list[at + j] = make_uint2(p, q);
+            else pair_spill(p, q, sv.v, out, fb);
+        }
     }
     __syncthreads();
 
     // ---- classify + append the CTA's survivors to the three global lists ----
     const uint32_t have = min(sh.count, (uint32_t)kPairCap);
-    const int lane = tid & 31, warp = tid >> 5;
     for (uint32_t base = 0; base < have; base += kPairThreads) {
         const uint32_t i = base + tid;
         int cls = 3;
