@@ -185,7 +185,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         from gunship_rs_b200 import slabs
         return slabs.bench_multi_gpu(args, n, rank, world, local_rank, METRIC, UNIT, workload_name, measured_peak_gbs,
-                                     ClockSampler)
+                                     ClockSampler, stage_bytes)
 
     from gunship_rs_b200 import context as G
     scene = make_scene(args.config, n)

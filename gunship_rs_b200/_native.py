@@ -15,6 +15,7 @@ GSC_OK, GSC_ERR_INVALID, GSC_ERR_CUDA, GSC_ERR_NCCL, GSC_ERR_CAPACITY, GSC_ERR_R
 GSC_SPHERE, GSC_BOX, GSC_MESH = 0, 1, 2
 GSC_FLAG_TIMING, GSC_FLAG_GRAPH = 1, 2
 GSC_NUM_STAGES = 6
+GSC_HALO_RECORD_BYTES = 96
 STAGE_NAMES = ("bvh_update", "cell_keys", "sort", "cell_table", "pairs", "narrow")
 (GSC_DBG_AABB, GSC_DBG_SORTED_KEYS, GSC_DBG_SORTED_IDX, GSC_DBG_CELL_START, GSC_DBG_OBB) = range(5)
 
@@ -92,8 +93,8 @@ def load():
     L.gsc_phase_bounds.argtypes = [vp, C.POINTER(GscBounds)]
     L.gsc_set_global_bounds.argtypes = [vp, C.POINTER(GscBounds)]
     L.gsc_local_x_range.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
-    L.gsc_halo_select.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_uint32), C.POINTER(vp), C.POINTER(vp)]
-    L.gsc_halo_append.argtypes = [vp, C.c_uint32, vp, vp]
+    L.gsc_halo_select.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_uint32, C.POINTER(C.c_uint32)]
+    L.gsc_halo_append.argtypes = [vp, C.c_uint32, vp]
     L.gsc_phase_finish.argtypes = [vp, C.POINTER(GscStepOut)]
     for name in EXPORTS:
         fn = getattr(L, name)  # raises AttributeError if the .so does not export it

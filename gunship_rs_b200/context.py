@@ -119,6 +119,26 @@ class CollisionContext:
     def set_global_bounds(self, b: N.GscBounds):
         self._check(self._lib.gsc_set_global_bounds(self._h, C.byref(b)))
 
+    def local_x_range(self):
+        lo, hi = C.c_int32(0), C.c_int32(0)
+        self._check(self._lib.gsc_local_x_range(self._h, C.byref(lo), C.byref(hi)))
+        return int(lo.value), int(hi.value)
+
+    def halo_select(self, x_lo: int, x_hi: int, d_records: int, cap_records: int) -> int:
+        """Pack local colliders with home x-cell in [x_lo, x_hi] into the DEVICE buffer at `d_records`.
+        Returns the count; raises GscError(GSC_ERR_CAPACITY) with .needed set when the buffer is too small."""
+        cnt = C.c_uint32(0)
+        rc = self._lib.gsc_halo_select(self._h, x_lo, x_hi, d_records or None, cap_records, C.byref(cnt))
+        if rc == N.GSC_ERR_CAPACITY:
+            err = GscError(rc, self._lib.gsc_last_error(self._h).decode())
+            err.needed = int(cnt.value)
+            raise err
+        self._check(rc)
+        return int(cnt.value)
+
+    def halo_append(self, count: int, d_records: int):
+        self._check(self._lib.gsc_halo_append(self._h, count, d_records or None))
+
     def phase_finish(self) -> N.GscStepOut:
         out = N.GscStepOut()
         rc = self._lib.gsc_phase_finish(self._h, C.byref(out))

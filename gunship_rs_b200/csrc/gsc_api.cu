@@ -460,6 +460,9 @@ int gsc_set_global_bounds(gsc_ctx *c, const gsc_bounds *g)
     }
     CU(c, cudaMemcpyAsync(c->d_fb, enc, sizeof enc, cudaMemcpyHostToDevice, c->stream));
     if (g->status_flags) CU(c, cudaMemcpyAsync(&c->d_fb->status, &g->status_flags, 4, cudaMemcpyHostToDevice, c->stream));
+    // place the (global) grid now: gsc_local_x_range / gsc_halo_select need the cell size
+    k_grid_setup<<<1, 32, 0, c->stream>>>(c->d_fb, c->max_cells, c->cap);
+    CU(c, cudaGetLastError());
     CU(c, cudaStreamSynchronize(c->stream));  // enc lives on this stack frame
     c->global_bounds_set = true;
     return GSC_OK;
@@ -472,9 +475,64 @@ int gsc_phase_finish(gsc_ctx *c, gsc_step_out *out)
     return stage_finish(c, out);
 }
 
-int gsc_local_x_range(gsc_ctx *c, int32_t *, int32_t *) { return fail(c, GSC_ERR_INVALID, "gsc_local_x_range: not built yet"); }
-int gsc_halo_select(gsc_ctx *c, int32_t, int32_t, uint32_t *, const void **, const void **) { return fail(c, GSC_ERR_INVALID, "gsc_halo_select: not built yet"); }
-int gsc_halo_append(gsc_ctx *c, uint32_t, const void *, const void *) { return fail(c, GSC_ERR_INVALID, "gsc_halo_append: not built yet"); }
+int gsc_local_x_range(gsc_ctx *c, int32_t *x_min, int32_t *x_max)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!x_min || !x_max) return fail(c, GSC_ERR_INVALID, "gsc_local_x_range: null output");
+    if (!c->global_bounds_set) return fail(c, GSC_ERR_INVALID, "gsc_local_x_range: call gsc_set_global_bounds first");
+    cudaStream_t s = c->stream;
+    CU(c, cudaMemsetAsync(c->d_fb->xrange, 0, sizeof(uint32_t) * 2, s));
+    if (c->n_local) k_local_x_range<<<kGridStrideBlocks, 256, 0, s>>>(c->n_local, c->d_rec, c->d_fb);
+    CU(c, cudaGetLastError());
+    CU(c, cudaMemcpyAsync(c->h_fb, c->d_fb, sizeof(FrameBlock), cudaMemcpyDeviceToHost, s));
+    CU(c, cudaStreamSynchronize(s));
+    const FrameBlock &h = *c->h_fb;
+    if (int rc = status_to_error(c, h)) return rc;
+    if (h.xrange[1] == 0) {  // no local volumes (or no grid): empty range
+        *x_min = 1;
+        *x_max = 0;
+    } else {
+        *x_min = (int32_t)(~h.xrange[0]) - 32768;
+        *x_max = (int32_t)h.xrange[1] - 32768;
+    }
+    return GSC_OK;
+}
+
+int gsc_halo_select(gsc_ctx *c, int32_t x_lo, int32_t x_hi, void *d_records, uint32_t cap_records, uint32_t *count)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!count || (cap_records && !d_records)) return fail(c, GSC_ERR_INVALID, "gsc_halo_select: null argument");
+    if (!c->global_bounds_set) return fail(c, GSC_ERR_INVALID, "gsc_halo_select: call gsc_set_global_bounds first");
+    if (reinterpret_cast<uintptr_t>(d_records) & 15) return fail(c, GSC_ERR_INVALID, "gsc_halo_select: buffer must be 16-byte aligned");
+    cudaStream_t s = c->stream;
+    CU(c, cudaMemsetAsync(c->d_halo_count, 0, sizeof(uint32_t), s));
+    if (c->n_local && x_lo <= x_hi)
+        k_halo_select<<<kGridStrideBlocks, 256, 0, s>>>(c->n_local, c->d_rec, c->d_obb, x_lo, x_hi, (float4 *)d_records,
+                                                      cap_records, c->d_halo_count, c->d_fb);
+    CU(c, cudaGetLastError());
+    CU(c, cudaMemcpyAsync(count, c->d_halo_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CU(c, cudaStreamSynchronize(s));
+    if (*count > cap_records)
+        return fail(c, GSC_ERR_CAPACITY, "gsc_halo_select: %u records selected, buffer holds %u", *count, cap_records);
+    return GSC_OK;
+}
+
+int gsc_halo_append(gsc_ctx *c, uint32_t count, const void *d_records)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!c->bounds_done) return fail(c, GSC_ERR_INVALID, "gsc_halo_append: call gsc_phase_bounds first");
+    if (count == 0) return GSC_OK;
+    if (!d_records || (reinterpret_cast<uintptr_t>(d_records) & 15)) return fail(c, GSC_ERR_INVALID, "gsc_halo_append: bad buffer");
+    if ((uint64_t)c->n_local + c->n_ghost + count > c->cap)
+        return fail(c, GSC_ERR_CAPACITY, "gsc_halo_append: %u local + %u ghost + %u new > max_colliders %u", c->n_local, c->n_ghost,
+                    count, c->cap);
+    k_halo_append<<<(count + 255) / 256, 256, 0, c->stream>>>(count, (const float4 *)d_records, c->n_local + c->n_ghost, c->d_rec,
+                                                              c->d_obb);
+    CU(c, cudaGetLastError());
+    CU(c, cudaStreamSynchronize(c->stream));  // the caller may reuse d_records right away
+    c->n_ghost += count;
+    return GSC_OK;
+}
 
 // ---- results -----------------------------------------------------------------------------------------
 

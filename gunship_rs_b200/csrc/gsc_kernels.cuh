@@ -18,6 +18,8 @@
 // span 3 cells ("wide", grid_collision.rs:403-410) leave that argument and are handled exactly by
 // k_wide_pairs, which restates the corner-cell rule literally.
 #pragma once
+#include <limits.h>
+
 #include "gsc_math.cuh"
 #include "gsc_sort.cuh"
 
@@ -784,6 +786,89 @@ k_wide_pairs(uint32_t n_local, const uint32_t *__restrict__ wide_list, const flo
         emit(s_out, hit, item, pairs, &fb->n_pairs, cap_pairs);
     }
     emit_finish(s_out, pairs, &fb->n_pairs, cap_pairs);
+}
+
+// ---- multi-GPU slab support: home-x range, halo selection, ghost append ------------------------------
+// Home x-cell range of the local volumes, in absolute cell coordinates (floor(aabb.min.x / cell)).
+__global__ void __launch_bounds__(256)
+k_local_x_range(uint32_t n_local, const float4 *__restrict__ rec, FrameBlock *__restrict__ fb)
+{
+    const GridParams g = fb->grid;
+    if (!g.valid) return;
+    int lo = INT_MAX, hi = INT_MIN;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += gridDim.x * blockDim.x) {
+        const Volume v = volume_decode(__ldg(rec + 2 * (size_t)i), __ldg(rec + 2 * (size_t)i + 1));
+        const int x = (int)cell_coord_f(v.mn[0], g.cell_size);
+        lo = min(lo, x);
+        hi = max(hi, x);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0 && lo <= hi) {
+        atomicMax(&fb->xrange[0], ~(uint32_t)(lo + 32768));
+        atomicMax(&fb->xrange[1], (uint32_t)(hi + 32768));
+    }
+}
+
+// Halo record = 96 B: the 32 B volume record followed by the 64 B OBB record (undefined for spheres).
+// Selects the local volumes whose home x-cell lies in [x_lo, x_hi] (absolute cells) into `out`,
+// warp-aggregated; *count keeps counting past `cap` so the caller can size the buffer.
+__global__ void __launch_bounds__(256)
+k_halo_select(uint32_t n_local, const float4 *__restrict__ rec, const float4 *__restrict__ obb, int x_lo, int x_hi,
+              float4 *__restrict__ out, uint32_t cap, uint32_t *__restrict__ count, const FrameBlock *__restrict__ fb)
+{
+    const GridParams g = fb->grid;
+    if (!g.valid) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_round = (n_local + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        bool sel = false;
+        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+        if (i < n_local) {
+            r0 = __ldg(rec + 2 * (size_t)i);
+            r1 = __ldg(rec + 2 * (size_t)i + 1);
+            const Volume v = volume_decode(r0, r1);
+            const int x = (int)cell_coord_f(v.mn[0], g.cell_size);
+            sel = x >= x_lo && x <= x_hi;
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, sel);
+        if (m == 0) continue;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(count, (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t at = base + __popc(m & ((1u << lane) - 1u));
+        if (sel && at < cap) {
+            float4 *d = out + 6 * (size_t)at;
+            d[0] = r0;
+            d[1] = r1;
+            if (__float_as_uint(r1.w) & kMetaBox) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) d[2 + k] = __ldg(obb + 4 * (size_t)i + k);
+            }
+        }
+    }
+}
+
+// Appends ghosts received from another slab behind the local volumes: new local index, ghost flag.
+__global__ void __launch_bounds__(256)
+k_halo_append(uint32_t count, const float4 *__restrict__ in, uint32_t first, float4 *__restrict__ rec, float4 *__restrict__ obb)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    const float4 *s = in + 6 * (size_t)j;
+    const uint32_t i = first + j;
+    float4 r0 = s[0], r1 = s[1];
+    const uint32_t box = __float_as_uint(r1.w) & kMetaBox;
+    r1.w = __uint_as_float((i << 4) | box | kMetaGhost);
+    rec[2 * (size_t)i] = r0;
+    rec[2 * (size_t)i + 1] = r1;
+    if (box) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) obb[4 * (size_t)i + k] = s[2 + k];
+    }
 }
 
 // ---- micro-bench parity kernels (benches/collision.rs, benches/grid_collision.rs) -------------------

@@ -148,10 +148,19 @@ int gsc_fnv1a_gridcell(int device, size_t n, const int16_t *cells3, uint64_t *ou
 /* the radix sort used on (cell, collider) keys, exposed for testing: stable LSD over `key_bits` bits */
 int gsc_sort_pairs_u32(int device, size_t n, uint32_t *keys, uint32_t *vals, int key_bits);
 
-/* ---- multi-GPU slab support (x-slab partition, one context per GPU, host layer does the exchange) ----
- * A step on rank r is:  gsc_phase_bounds -> [all-reduce of 7 floats] -> gsc_set_global_bounds ->
- * gsc_halo_select(x range of a neighbour) -> [send/recv of halo records] -> gsc_halo_append ->
- * gsc_phase_finish.  Single-GPU callers use gsc_step, which runs the same stages back to back. */
+/* ---- multi-GPU slab support (x-slab partition, one context per GPU; the host layer does the exchange,
+ *      gunship_rs_b200/slabs.py over torch.distributed/NCCL) ----
+ * The reference already decomposes space (8 octant work units that each see every volume and dedupe at the
+ * merge, grid_collision.rs:60-86,161-193,262-272).  Here each rank owns a subset of the colliders, ideally an
+ * x-slab.  A pair is reported by exactly one rank: the owner of its "taker" -- the volume that comes later in
+ * (home cell key, global index) order -- which only ever looks at home x-cells {x-1, x}.  So rank r needs as
+ * ghosts the volumes of other ranks whose home x-cell lies in [xmin_r - 1, xmax_r].  One step on rank r:
+ *   gsc_phase_bounds -> [all-reduce: max longest_axis, min world_min, max world_max] -> gsc_set_global_bounds
+ *   -> gsc_local_x_range -> [all-gather of the ranges] -> for every rank s that needs some of mine:
+ *   gsc_halo_select(xmin_s - 1, xmax_s) -> [send/recv] -> gsc_halo_append -> gsc_phase_finish.
+ * The union of the ranks' pair lists is the single-GPU pair set; no cross-rank dedupe is needed.
+ * Volumes that span 3 cells through rounding (n_wide, expected 0) are only matched within their own rank.
+ * Single-GPU callers use gsc_step, which runs the same stages back to back. */
 typedef struct gsc_bounds {
     float longest_axis;  /* max AABB extent over the local colliders */
     float world_min[3];  /* min over local AABB mins */
@@ -159,20 +168,20 @@ typedef struct gsc_bounds {
     uint32_t status_flags;
 } gsc_bounds;
 
+#define GSC_HALO_RECORD_BYTES 96 /* 32 B volume record + 64 B OBB record */
+
 /* stage 0 on the local colliders; returns the local bounds */
 int gsc_phase_bounds(gsc_ctx *ctx, gsc_bounds *local);
 /* install the globally reduced bounds (max of longest_axis, min of world_min, max of world_max) */
 int gsc_set_global_bounds(gsc_ctx *ctx, const gsc_bounds *global);
-/* local min/max x-cell of the local colliders' home cells (needs global bounds) */
+/* min/max home x-cell (floor(aabb.min.x / cell), absolute) of the local colliders; empty => *x_min > *x_max */
 int gsc_local_x_range(gsc_ctx *ctx, int32_t *x_min, int32_t *x_max);
-/* gather into a device staging buffer the local colliders whose home x-cell lies in
- * [x_lo, x_hi]; returns the count and DEVICE pointers to packed records:
- * rec (32 B each) and obb (64 B each) in matching order */
-int gsc_halo_select(gsc_ctx *ctx, int32_t x_lo, int32_t x_hi, uint32_t *count,
-                    const void **d_rec32, const void **d_obb64);
-/* append `count` ghost colliders (records produced by gsc_halo_select on another rank, DEVICE
- * memory); ghosts take part as the earlier volume of a pair only */
-int gsc_halo_append(gsc_ctx *ctx, uint32_t count, const void *d_rec32, const void *d_obb64);
+/* pack into the caller's DEVICE buffer (16-byte aligned, cap_records * GSC_HALO_RECORD_BYTES) the local
+ * colliders whose home x-cell lies in [x_lo, x_hi]; *count receives how many (GSC_ERR_CAPACITY if > cap) */
+int gsc_halo_select(gsc_ctx *ctx, int32_t x_lo, int32_t x_hi, void *d_records, uint32_t cap_records, uint32_t *count);
+/* append `count` ghost colliders (records produced by gsc_halo_select on another rank, DEVICE memory);
+ * ghosts take part as the earlier volume of a pair only */
+int gsc_halo_append(gsc_ctx *ctx, uint32_t count, const void *d_records);
 /* stages 1..5 on local + ghost colliders */
 int gsc_phase_finish(gsc_ctx *ctx, gsc_step_out *out);
 

@@ -1,0 +1,74 @@
+"""Multi-GPU path on the box's GPU(s): the slab driver with real CUDA contexts.  Two ranks (two processes,
+gloo rendezvous on 127.0.0.1, both on cuda:0 when the box has one GPU -- the halo then travels through host
+staging) must together report exactly the single-context pair set, which is the oracle's."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, cfg, n, frames, out_dir, ownership):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from gunship_rs_b200 import context as G
+    from gunship_rs_b200 import scenes, slabs
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    dev = rank % torch.cuda.device_count()
+    s = scenes.by_config(cfg, n)
+    if ownership == "slabs":
+        owner = slabs.partition_x_slabs(s.pos[:, 0], world)
+    else:  # scattered ownership: correct, merely a bigger halo
+        owner = (np.arange(s.n) % world).astype(np.int32)
+    mine = np.nonzero(owner == rank)[0]
+    with G.CollisionContext(s.n, device=dev) as ctx:
+        ctx.upload_colliders(s.entity[mine], s.kind[mine], s.offset[mine], s.size[mine], global_index=mine.astype(np.uint32))
+        drv = slabs.SlabDriver(slabs.GpuSlabBackend(ctx, dev, host_staging=True))
+        for f in frames:
+            pos, quat = s.frame(f)
+            ctx.update_transforms(pos[mine], quat[mine], s.scale[mine])
+            out = drv.step()
+            assert out.n_wide == 0
+            np.save(os.path.join(out_dir, f"pairs_{ownership}_{f}_{rank}.npy"), ctx.pairs_packed(sorted=True))
+            np.save(os.path.join(out_dir, f"halo_{ownership}_{f}_{rank}.npy"), np.array([drv.last_halo_in, drv.last_halo_out, len(mine)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cfg,n,ownership", [(4, 60000, "slabs"), (3, 30000, "slabs"), (2, 30000, "scattered")])
+def test_two_ranks_report_the_single_context_pair_set(tmp_path, cfg, n, ownership):
+    import torch.multiprocessing as mp
+    import oracle_lib as O
+    from gunship_rs_b200 import scenes
+    frames = (0, 2)
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), cfg, n, frames, str(tmp_path), ownership), nprocs=world, join=True)
+    s = scenes.by_config(cfg, n)
+    oracle = O.OracleSystem()
+    for f in frames:
+        pos, quat = s.frame(f)
+        want = oracle.step(s, pos, quat)
+        parts = [np.load(tmp_path / f"pairs_{ownership}_{f}_{r}.npy") for r in range(world)]
+        got = np.sort(np.concatenate(parts))
+        assert len(got) == len(want) and np.array_equal(got, want)         # union == oracle, no duplicates
+        assert all(len(p) > 0 for p in parts)
+        halo = [np.load(tmp_path / f"halo_{ownership}_{f}_{r}.npy") for r in range(world)]
+        if ownership == "slabs":
+            # the halo flows in +x: rank 1 receives the boundary layer (two cell columns), rank 0 only the
+            # foreign volumes of the one cell column the cut runs through
+            assert 0 < halo[1][0] < 0.35 * halo[1][2] and halo[0][0] < halo[1][0]
+    oracle.close()
