@@ -47,7 +47,7 @@ class GscStepOut(C.Structure):
 
 class GscBounds(C.Structure):
     _fields_ = [("longest_axis", C.c_float), ("world_min", C.c_float * 3), ("world_max", C.c_float * 3),
-                ("status_flags", C.c_uint32)]
+                ("status_flags", C.c_uint32), ("home_x_max", C.c_float)]
 
 
 # every symbol include/gunship_collision.h declares
@@ -56,7 +56,7 @@ EXPORTS = (
     "gsc_update_transforms", "gsc_bind_device_transforms", "gsc_step", "gsc_download_pairs", "gsc_debug_download",
     "gsc_test_sphere_sphere", "gsc_test_sphere_obb", "gsc_test_obb_obb", "gsc_test_aabb_aabb", "gsc_fnv1a_gridcell",
     "gsc_sort_pairs_u32", "gsc_phase_bounds", "gsc_set_global_bounds", "gsc_local_x_range", "gsc_halo_select",
-    "gsc_halo_append", "gsc_phase_finish",
+    "gsc_halo_append", "gsc_phase_finish", "gsc_set_x_window",
 )
 
 _lib = None
@@ -96,6 +96,7 @@ def load():
     L.gsc_halo_select.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_uint32, C.POINTER(C.c_uint32)]
     L.gsc_halo_append.argtypes = [vp, C.c_uint32, vp]
     L.gsc_phase_finish.argtypes = [vp, C.POINTER(GscStepOut)]
+    L.gsc_set_x_window.argtypes = [vp, C.c_int32, C.c_int32]
     for name in EXPORTS:
         fn = getattr(L, name)  # raises AttributeError if the .so does not export it
         if name not in ("gsc_destroy", "gsc_last_error"):

@@ -119,6 +119,9 @@ class CollisionContext:
     def set_global_bounds(self, b: N.GscBounds):
         self._check(self._lib.gsc_set_global_bounds(self._h, C.byref(b)))
 
+    def set_x_window(self, x_lo: int, x_hi: int):
+        self._check(self._lib.gsc_set_x_window(self._h, x_lo, x_hi))
+
     def local_x_range(self):
         lo, hi = C.c_int32(0), C.c_int32(0)
         self._check(self._lib.gsc_local_x_range(self._h, C.byref(lo), C.byref(hi)))

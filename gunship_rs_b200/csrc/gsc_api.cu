@@ -54,6 +54,9 @@ struct gsc_ctx {
     float4 *d_rec = nullptr, *d_rec_sorted = nullptr, *d_obb = nullptr;
     uint32_t *d_keys[2] = { nullptr, nullptr }, *d_vals[2] = { nullptr, nullptr };
     uint32_t *d_cell_start = nullptr, *d_wide = nullptr;
+    uint4 *d_gaps = nullptr;
+    bool have_window = false;
+    int32_t win_lo = 0, win_hi = 0;
     uint2 *d_pairs = nullptr, *d_cand_ss = nullptr, *d_cand_so = nullptr, *d_cand_oo = nullptr;
     uint2 *d_pairs_sorted = nullptr;
     FrameBlock *d_fb = nullptr;
@@ -149,6 +152,7 @@ int status_to_error(gsc_ctx *c, const FrameBlock &fb)
     if (st & kStNonFinite) return fail(c, GSC_ERR_RANGE, "a collider produced a NaN/Inf bounding box");
     if (st & kStCellSize) return fail(c, GSC_ERR_RANGE, "cell size (longest AABB axis) is not positive: %g", (double)fb.grid.cell_size);
     if (st & kStRange) return fail(c, GSC_ERR_RANGE, "a grid coordinate leaves the i16 range of GridCoord (grid_collision.rs:535)");
+    if (st & kStWindow) return fail(c, GSC_ERR_INVALID, "gsc_set_x_window does not cover the home cell of a local collider");
     if (st & kStCells) return fail(c, GSC_ERR_CAPACITY, "dense cell table too small: raise gsc_config.max_cells (have %llu)", (unsigned long long)c->max_cells);
     return GSC_OK;
 }
@@ -210,6 +214,7 @@ int gsc_create(const gsc_config *cfg, gsc_ctx **out)
     }
     CR(dmalloc(&c->d_cell_start, c->max_cells + 2));
     CR(dmalloc(&c->d_wide, M));
+    CR(dmalloc(&c->d_gaps, (size_t)kGapCap));
     CR(dmalloc(&c->d_pairs, c->max_pairs));
     CR(dmalloc(&c->d_cand_ss, c->max_cands));
     CR(dmalloc(&c->d_cand_so, c->max_cands));
@@ -240,7 +245,7 @@ void gsc_destroy(gsc_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *bufs[] = { c->d_entity, c->d_gidx, c->d_kind, c->d_offset, c->d_size, c->d_pos, c->d_quat, c->d_scale, c->d_rec,
                      c->d_rec_sorted, c->d_obb, c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1], c->d_cell_start,
-                     c->d_wide, c->d_pairs, c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->d_pairs_sorted, c->d_fb, c->d_lookback,
+                     c->d_wide, c->d_gaps, c->d_pairs, c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->d_pairs_sorted, c->d_fb, c->d_lookback,
                      c->d_halo_rec, c->d_halo_obb, c->d_halo_count };
     for (void *b : bufs)
         if (b) cudaFree(b);
@@ -334,6 +339,7 @@ static int stage_bounds(gsc_ctx *c)
     if (timing) CU(c, cudaEventRecord(c->ev[1], s));
     c->bounds_done = true;
     c->global_bounds_set = false;
+    c->have_window = false;
     return GSC_OK;
 }
 
@@ -344,7 +350,7 @@ static int stage_finish(gsc_ctx *c, gsc_step_out *out)
     const uint32_t n_total = c->n_local + c->n_ghost;
     FrameBlock *fb = c->d_fb;
     CU(c, cudaMemsetAsync(c->d_lookback, 0, (size_t)kMaxPasses * tiles_for(n_total) * kRadix * sizeof(uint32_t), s));
-    k_grid_setup<<<1, 32, 0, s>>>(fb, c->max_cells, n_total);
+    k_grid_setup<<<1, 32, 0, s>>>(fb, c->max_cells, n_total, c->have_window ? 1 : 0, c->win_lo, c->win_hi);
     if (n_total) {
         const uint32_t kb = std::min<uint32_t>((n_total + kKeyThreads - 1) / kKeyThreads, kGridStrideBlocks);
         k_cell_keys<<<kb, kKeyThreads, 0, s>>>(n_total, c->d_rec, c->d_keys[0], c->d_wide, fb);
@@ -355,7 +361,8 @@ static int stage_finish(gsc_ctx *c, gsc_step_out *out)
         const uint32_t tb = (n_total + 1 + kTableThreads - 1) / kTableThreads;
         SortedVolumes sv{ c->d_rec_sorted };
         k_cell_table_permute<<<tb, kTableThreads, 0, s>>>(n_total, c->d_keys[0], c->d_vals[0], c->d_keys[1], c->d_vals[1],
-                                                         c->d_rec, sv, c->d_cell_start, fb);
+                                                         c->d_rec, sv, c->d_cell_start, c->d_gaps, fb);
+        k_fill_gaps<<<148 * 2, 256, 0, s>>>(c->d_cell_start, c->d_gaps, fb);
         if (timing) CU(c, cudaEventRecord(c->ev[4], s));
         PairOut po{ c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands };
         const uint32_t pb = (n_total + kPairThreads - 1) / kPairThreads;
@@ -431,7 +438,9 @@ int gsc_phase_bounds(gsc_ctx *c, gsc_bounds *local)
     if (c->n_local == 0 || h.bounds[0] == 0) {
         local->longest_axis = 0.0f;
         for (int a = 0; a < 3; ++a) { local->world_min[a] = INFINITY; local->world_max[a] = -INFINITY; }
+        local->home_x_max = -INFINITY;
     } else {
+        local->home_x_max = ord2f(h.bounds[7]);
         local->longest_axis = ord2f(h.bounds[0]);
         for (int a = 0; a < 3; ++a) {
             local->world_min[a] = ord2f(~h.bounds[1 + a]);
@@ -452,7 +461,7 @@ int gsc_set_global_bounds(gsc_ctx *c, const gsc_bounds *g)
 {
     if (int rc = check_ctx(c)) return rc;
     if (!g || !c->bounds_done) return fail(c, GSC_ERR_INVALID, "gsc_set_global_bounds: call gsc_phase_bounds first");
-    uint32_t enc[8] = { 0 };
+    uint32_t enc[7] = { 0 };
     enc[0] = host_f2ord(g->longest_axis);
     for (int a = 0; a < 3; ++a) {
         enc[1 + a] = ~host_f2ord(g->world_min[a]);
@@ -461,10 +470,20 @@ int gsc_set_global_bounds(gsc_ctx *c, const gsc_bounds *g)
     CU(c, cudaMemcpyAsync(c->d_fb, enc, sizeof enc, cudaMemcpyHostToDevice, c->stream));
     if (g->status_flags) CU(c, cudaMemcpyAsync(&c->d_fb->status, &g->status_flags, 4, cudaMemcpyHostToDevice, c->stream));
     // place the (global) grid now: gsc_local_x_range / gsc_halo_select need the cell size
-    k_grid_setup<<<1, 32, 0, c->stream>>>(c->d_fb, c->max_cells, c->cap);
+    k_grid_setup<<<1, 32, 0, c->stream>>>(c->d_fb, c->max_cells, c->cap, 0, 0, 0);
     CU(c, cudaGetLastError());
     CU(c, cudaStreamSynchronize(c->stream));  // enc lives on this stack frame
     c->global_bounds_set = true;
+    return GSC_OK;
+}
+
+int gsc_set_x_window(gsc_ctx *c, int32_t x_lo, int32_t x_hi)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!c->bounds_done) return fail(c, GSC_ERR_INVALID, "gsc_set_x_window: call gsc_phase_bounds first");
+    c->have_window = true;
+    c->win_lo = x_lo;
+    c->win_hi = x_hi;
     return GSC_OK;
 }
 

@@ -34,6 +34,7 @@ enum : uint32_t {
     kStCells = 1u << 4,
     kStPairs = 1u << 5,
     kStCands = 1u << 6,
+    kStWindow = 1u << 7,
 };
 
 // ---- volume record: 32 B = 2 x float4, the unit the broadphase streams ----
@@ -79,13 +80,14 @@ struct GridParams {
 
 // Per-step device control block.  Zeroed at the start of every step.
 struct FrameBlock {
-    uint32_t bounds[8];  // [0] ord(longest axis); [1..3] ~ord(world min xyz); [4..6] ord(world max xyz)
+    uint32_t bounds[8];  // [0] ord(longest axis); [1..3] ~ord(world min xyz); [4..6] ord(world max xyz); [7] ord(max aabb.min.x)
     uint32_t status;
     uint32_t n_wide;
     unsigned long long n_pairs, n_ss, n_so, n_oo;
     uint32_t tile_counter[kMaxPasses];
     uint32_t xrange[2];  // ~(min home x + 32768), (max home x + 32768) of local volumes
-    uint32_t pad[2];
+    uint32_t n_gaps;  // long empty key gaps queued for k_fill_gaps
+    uint32_t pad[1];
     GridParams grid;
     SortControl sort;
     uint32_t hist[kMaxPasses][kRadix];
@@ -165,7 +167,7 @@ k_bvh_update(uint32_t n, const uint8_t *__restrict__ kind, const float *__restri
              FrameBlock *__restrict__ fb)
 {
     const uint32_t i = blockIdx.x * kBvhThreads + threadIdx.x;
-    float ext = 0.0f;
+    float ext = 0.0f, mnx_max = -INFINITY;
     float mn[3] = { INFINITY, INFINITY, INFINITY }, mx[3] = { -INFINITY, -INFINITY, -INFINITY };
     uint32_t st = 0;
     if (i < n) {
@@ -205,6 +207,7 @@ k_bvh_update(uint32_t n, const uint8_t *__restrict__ kind, const float *__restri
         // bounding_volume.rs:365-381: longest_axis = max(0, every diff), strict > from 0.0
         const float dx = sub(mx[0], mn[0]), dy = sub(mx[1], mn[1]), dz = sub(mx[2], mn[2]);
         ext = fmaxf(fmaxf(fmaxf(0.0f, dx), dy), dz);
+        mnx_max = mn[0];
         const float chk = mn[0] + mn[1] + mn[2] + mx[0] + mx[1] + mx[2];
         if (!(fabsf(chk) <= 3.0e38f)) st |= kStNonFinite;  // NaN or Inf anywhere
     }
@@ -212,6 +215,7 @@ k_bvh_update(uint32_t n, const uint8_t *__restrict__ kind, const float *__restri
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         ext = fmaxf(ext, __shfl_xor_sync(0xffffffffu, ext, o));
+        mnx_max = fmaxf(mnx_max, __shfl_xor_sync(0xffffffffu, mnx_max, o));
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
@@ -219,16 +223,17 @@ k_bvh_update(uint32_t n, const uint8_t *__restrict__ kind, const float *__restri
         }
         st |= __shfl_xor_sync(0xffffffffu, st, o);
     }
-    __shared__ float s_red[kBvhThreads / 32][7];
+    __shared__ float s_red[kBvhThreads / 32][8];
     __shared__ uint32_t s_st[kBvhThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
         s_red[warp][0] = ext;
+        s_red[warp][7] = mnx_max;
         for (int a = 0; a < 3; ++a) { s_red[warp][1 + a] = mn[a]; s_red[warp][4 + a] = mx[a]; }
         s_st[warp] = st;
     }
     __syncthreads();
-    if (threadIdx.x < 7) {
+    if (threadIdx.x < 8) {
         const int c = threadIdx.x;
         float v = s_red[0][c];
         for (int w = 1; w < kBvhThreads / 32; ++w) v = (c >= 1 && c <= 3) ? fminf(v, s_red[w][c]) : fmaxf(v, s_red[w][c]);
@@ -248,7 +253,8 @@ k_bvh_update(uint32_t n, const uint8_t *__restrict__ kind, const float *__restri
 // ---- grid placement: one thread -----------------------------------------------------------------
 // cell size = longest axis (grid_collision.rs:238-240); dense grid covers floor(world min / cell) ..
 // floor(world max / cell), which bounds every home cell because floor(fl(p / c)) is monotone in p.
-__global__ void k_grid_setup(FrameBlock *fb, unsigned long long max_cells, uint32_t n_total)
+// `has_window`: the caller (multi-GPU slab layer) restricts the grid to home x-cells [x_lo, x_hi] (absolute).
+__global__ void k_grid_setup(FrameBlock *fb, unsigned long long max_cells, uint32_t n_total, int has_window, int x_lo, int x_hi)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     GridParams g;
@@ -267,8 +273,12 @@ __global__ void k_grid_setup(FrameBlock *fb, unsigned long long max_cells, uint3
     if (st == 0) {
         unsigned long long cells = 1;
         for (int a = 0; a < 3; ++a) {
-            const float lo = cell_coord_f(ord2f(~fb->bounds[1 + a]), g.cell_size);
-            const float hi = cell_coord_f(ord2f(fb->bounds[4 + a]), g.cell_size);
+            float lo = cell_coord_f(ord2f(~fb->bounds[1 + a]), g.cell_size);
+            float hi = cell_coord_f(ord2f(fb->bounds[4 + a]), g.cell_size);
+            if (a == 0 && has_window) {  // only the slab's columns get cells; home cells outside are dropped by k_cell_keys
+                lo = fmaxf(lo, (float)x_lo);
+                hi = fminf(fmaxf(hi, lo), fmaxf((float)x_hi, lo));
+            }
             // GridCoord = i16 (grid_collision.rs:535): outside it the reference's cast is undefined
             if (!(lo >= -32768.0f) || !(hi <= 32767.0f)) { st |= kStRange; break; }
             // one apron cell on every side: neighbour keys of any home cell are valid cells (k_pairs)
@@ -323,7 +333,12 @@ k_cell_keys(uint32_t n_total, const float4 *__restrict__ rec, uint32_t *__restri
         int c0[3], c1[3];
         const bool wide = home_cell(v, g, c0, c1);
         uint32_t key;
-        if (wide) {
+        if (c0[0] < 1 || c0[0] > g.dims[0] - 2) {
+            // outside the slab's x window: a ghost there cannot meet any local taker -- park it behind the
+            // cells; a LOCAL volume there means the caller's window is wrong
+            key = g.num_cells;
+            if (!(v.meta & kMetaGhost)) atomicOr(&fb->status, kStWindow);
+        } else if (wide) {
             key = g.num_cells;
             if (!(v.meta & kMetaGhost)) wide_list[atomicAdd(&fb->n_wide, 1u)] = i;
         } else {
@@ -353,12 +368,14 @@ struct SortedVolumes {
 // start[c] = first sorted position whose key >= c, for c in [0, num_cells]; thread p fills the gap
 // (key[p-1], key[p]].  Long gaps (empty space) are filled by the whole warp.
 constexpr int kTableThreads = 256;
+constexpr int kGapLong = 1 << 14;  // empty-cell runs longer than this are filled by the whole grid
+constexpr int kGapCap = 4096;
 
 __global__ void __launch_bounds__(kTableThreads)
 k_cell_table_permute(uint32_t n_total, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ vals_a,
                      const uint32_t *__restrict__ keys_b, const uint32_t *__restrict__ vals_b,
                      const float4 *__restrict__ rec, SortedVolumes sv,
-                     uint32_t *__restrict__ cell_start, const FrameBlock *__restrict__ fb)
+                     uint32_t *__restrict__ cell_start, uint4 *__restrict__ gaps, FrameBlock *__restrict__ fb)
 {
     const GridParams g = fb->grid;
     if (!g.valid) return;
@@ -383,7 +400,14 @@ k_cell_table_permute(uint32_t n_total, const uint32_t *__restrict__ keys_a, cons
         sv.v[2 * (size_t)p + 1] = make_float4(v.mx[1], v.mx[2], __uint_as_float(v.gidx), __uint_as_float(meta));
     }
     const int64_t len = hi - lo + 1;
-    const bool is_long = len > 8;
+    if (len > kGapLong) {  // a huge run of empty cells (space between clusters / slabs): hand it to k_fill_gaps
+        const uint32_t slot = atomicAdd(&fb->n_gaps, 1u);
+        if (slot < (uint32_t)kGapCap) {
+            gaps[slot] = make_uint4((uint32_t)lo, (uint32_t)hi, p, 0u);
+            hi = lo - 1;
+        }
+    }
+    const bool is_long = hi - lo + 1 > 8;
     if (!is_long)
         for (int64_t c = lo; c <= hi; ++c) cell_start[c] = p;
     uint32_t long_mask = __ballot_sync(0xffffffffu, is_long);
@@ -395,6 +419,17 @@ k_cell_table_permute(uint32_t n_total, const uint32_t *__restrict__ keys_a, cons
         const int64_t shi = __shfl_sync(0xffffffffu, hi, src);
         const uint32_t sp = __shfl_sync(0xffffffffu, p, src);
         for (int64_t c = slo + lane; c <= shi; c += 32) cell_start[c] = sp;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_fill_gaps(uint32_t *__restrict__ cell_start, const uint4 *__restrict__ gaps, const FrameBlock *__restrict__ fb)
+{
+    const uint32_t n = min(fb->n_gaps, (uint32_t)kGapCap);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t k = 0; k < n; ++k) {
+        const uint4 gp = gaps[k];
+        for (uint64_t c = (uint64_t)gp.x + blockIdx.x * blockDim.x + threadIdx.x; c <= gp.y; c += stride) cell_start[c] = gp.z;
     }
 }
 

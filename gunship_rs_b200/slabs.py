@@ -11,8 +11,8 @@ Here the same idea is laid out for 8 GPUs without the merge:
 * a contact pair is reported by exactly one rank, the owner of its *taker*: the volume that comes later in
   (home-cell key, global index) order.  The taker only ever looks at home x-cells {x-1, x}, so rank r needs
   as ghosts the foreign volumes whose home x-cell lies in [xmin_r - 1, xmax_r];
-* per step the ranks agree on the cell size and the grid (one 7-float max-all-reduce), all-gather their home
-  x-ranges, and exchange the ghost records point to point.  No collective touches the pair lists: the union
+* per step ONE small all-gather of the local bounds gives every rank the global cell size, the world box and
+  all ranks' home x-ranges; then the ghost counts are all-gathered and the ghost records go point to point.  No collective touches the pair lists: the union
   of the per-rank lists IS the single-GPU pair set.
 
 The device work is behind a small backend interface so the same driver runs on the CUDA contexts
@@ -53,9 +53,9 @@ def needed_range(x_min: int, x_max: int):
 class SlabDriver:
     """One collision step across `world` ranks.  `backend` does the device work of this rank:
 
-    phase_bounds() -> (longest_axis, world_min[3], world_max[3], status_flags)
+    phase_bounds() -> (longest_axis, world_min[3], world_max[3], status_flags, home_x_max)
     set_global_bounds(longest_axis, world_min, world_max, status_flags)
-    local_x_range() -> (x_min, x_max)                      empty => x_min > x_max
+    set_x_window(x_lo, x_hi)                                home x-cells this rank's grid must cover
     halo_select(x_lo, x_hi) -> (count, tensor)              uint8 tensor, count * RECORD_BYTES valid bytes
     new_buffer(count) -> tensor                             receive buffer on the backend's device
     halo_append(count, tensor)
@@ -77,20 +77,29 @@ class SlabDriver:
         import torch
         dist, be = self.dist, self.backend
         dev = be.tensor_device
-        longest, wmin, wmax, status = be.phase_bounds()
-        # one max-all-reduce: longest axis, -world_min, world_max, status bits (as a float count is unsafe: send bits separately)
-        t = torch.tensor([longest, -wmin[0], -wmin[1], -wmin[2], wmax[0], wmax[1], wmax[2]], dtype=torch.float32, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-        st = torch.tensor([int(status)], dtype=torch.int32, device=dev)
-        dist.all_reduce(st, op=dist.ReduceOp.BOR if dev.type == "cpu" else dist.ReduceOp.MAX, group=self.group)
-        g = t.cpu().numpy()
-        be.set_global_bounds(float(g[0]), (-g[1:4]).tolist(), g[4:7].tolist(), int(st.item()))
-
-        x_min, x_max = be.local_x_range()
-        mine = torch.tensor([x_min, x_max], dtype=torch.int32, device=dev)
-        ranges = [torch.zeros(2, dtype=torch.int32, device=dev) for _ in range(self.world)]
-        dist.all_gather(ranges, mine, group=self.group)
-        ranges = [tuple(int(v) for v in r.cpu().tolist()) for r in ranges]
+        longest, wmin, wmax, status, home_x_max = be.phase_bounds()
+        # ONE all-gather carries everything the ranks must agree on: the global cell size (max longest axis) and
+        # world box (they place the grid), and every rank's home x-range in world units
+        mine = torch.tensor([longest, *wmin, *wmax, home_x_max, float(status)], dtype=torch.float32, device=dev)
+        allb = [torch.zeros(9, dtype=torch.float32, device=dev) for _ in range(self.world)]
+        dist.all_gather(allb, mine, group=self.group)
+        allb = torch.stack(allb).cpu().numpy()                       # [world, 9] float32
+        cell = np.float32(allb[:, 0].max())
+        g_min = allb[:, 1:4].min(axis=0)
+        g_max = allb[:, 4:7].max(axis=0)
+        g_status = int(np.bitwise_or.reduce(allb[:, 8].astype(np.int64)))
+        be.set_global_bounds(float(cell), g_min.tolist(), g_max.tolist(), g_status)
+        # home x-cell = floor(fl(aabb.min.x / cell)) (grid_collision.rs:329-335): IEEE f32 divide, same as the device
+        ranges = []
+        for r in range(self.world):
+            if not (allb[r, 0] > 0) or not np.isfinite(allb[r, 1]) or not (cell > 0):
+                ranges.append((1, 0))  # no colliders on that rank
+            else:
+                with np.errstate(all="ignore"):
+                    ranges.append((int(np.floor(np.float32(allb[r, 1]) / cell)), int(np.floor(np.float32(allb[r, 7]) / cell))))
+        x_min, x_max = ranges[self.rank]
+        if x_min <= x_max:
+            be.set_x_window(*needed_range(x_min, x_max))
 
         # what each other rank needs from me
         send = {}
@@ -151,7 +160,7 @@ class GpuSlabBackend:
 
     def phase_bounds(self):
         b = self.ctx.phase_bounds()
-        return float(b.longest_axis), list(b.world_min), list(b.world_max), int(b.status_flags)
+        return float(b.longest_axis), list(b.world_min), list(b.world_max), int(b.status_flags), float(b.home_x_max)
 
     def set_global_bounds(self, longest, wmin, wmax, status):
         b = N.GscBounds()
@@ -162,8 +171,8 @@ class GpuSlabBackend:
         b.status_flags = status
         self.ctx.set_global_bounds(b)
 
-    def local_x_range(self):
-        return self.ctx.local_x_range()
+    def set_x_window(self, x_lo, x_hi):
+        self.ctx.set_x_window(x_lo, x_hi)
 
     def _device_buffer(self, count):
         return self.torch.empty(max(count, 1) * RECORD_BYTES, dtype=self.torch.uint8, device=self.cuda)

@@ -155,8 +155,8 @@ int gsc_sort_pairs_u32(int device, size_t n, uint32_t *keys, uint32_t *vals, int
  * x-slab.  A pair is reported by exactly one rank: the owner of its "taker" -- the volume that comes later in
  * (home cell key, global index) order -- which only ever looks at home x-cells {x-1, x}.  So rank r needs as
  * ghosts the volumes of other ranks whose home x-cell lies in [xmin_r - 1, xmax_r].  One step on rank r:
- *   gsc_phase_bounds -> [all-reduce: max longest_axis, min world_min, max world_max] -> gsc_set_global_bounds
- *   -> gsc_local_x_range -> [all-gather of the ranges] -> for every rank s that needs some of mine:
+ *   gsc_phase_bounds -> [all-gather of the gsc_bounds: global cell size / world box, every rank's home x-range]
+ *   -> gsc_set_global_bounds -> gsc_set_x_window(xmin_r - 1, xmax_r) -> for every rank s that needs some of mine:
  *   gsc_halo_select(xmin_s - 1, xmax_s) -> [send/recv] -> gsc_halo_append -> gsc_phase_finish.
  * The union of the ranks' pair lists is the single-GPU pair set; no cross-rank dedupe is needed.
  * Volumes that span 3 cells through rounding (n_wide, expected 0) are only matched within their own rank.
@@ -166,6 +166,8 @@ typedef struct gsc_bounds {
     float world_min[3];  /* min over local AABB mins */
     float world_max[3];  /* max over local AABB maxs */
     uint32_t status_flags;
+    float home_x_max;    /* max over local AABB min.x: floor(world_min[0] / cell) .. floor(home_x_max / cell) is the
+                            home x-cell range of the local colliders once the global cell size is known */
 } gsc_bounds;
 
 #define GSC_HALO_RECORD_BYTES 96 /* 32 B volume record + 64 B OBB record */
@@ -174,6 +176,10 @@ typedef struct gsc_bounds {
 int gsc_phase_bounds(gsc_ctx *ctx, gsc_bounds *local);
 /* install the globally reduced bounds (max of longest_axis, min of world_min, max of world_max) */
 int gsc_set_global_bounds(gsc_ctx *ctx, const gsc_bounds *global);
+/* restrict this rank's grid to the home x-cells [x_lo, x_hi] (absolute cells; normally xmin_r - 1 .. xmax_r): the
+ * cell table then covers the slab, not the world.  Must contain every local collider's home cell (GSC_ERR_INVALID
+ * from gsc_phase_finish otherwise); ghosts outside it are ignored.  Valid for the current step only. */
+int gsc_set_x_window(gsc_ctx *ctx, int32_t x_lo, int32_t x_hi);
 /* min/max home x-cell (floor(aabb.min.x / cell), absolute) of the local colliders; empty => *x_min > *x_max */
 int gsc_local_x_range(gsc_ctx *ctx, int32_t *x_min, int32_t *x_max);
 /* pack into the caller's DEVICE buffer (16-byte aligned, cap_records * GSC_HALO_RECORD_BYTES) the local
