@@ -89,6 +89,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def profiled_traffic(cfg: int, n: int, stage: str):
+    """DRAM bytes per launch of `stage` from the committed ncu capture (profiles/), if it was taken on this
+    workload; None otherwise.  traffic well above the algorithmic bytes == wasted re-reads."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    try:
+        for name in sorted(os.listdir(pdir)):
+            if name.endswith("_traffic.json"):
+                d = json.load(open(os.path.join(pdir, name)))
+                if d["workload"]["config"] == cfg and d["workload"]["n"] == n and stage in d["stages"]:
+                    st = d["stages"][stage]
+                    best = {"bytes": st["dram_bytes"] / max(st["launches"], 1), "source": name}
+    except Exception:
+        return None
+    return best
+
+
 def make_scene(cfg: int, n: int):
     from gunship_rs_b200 import scenes
     return scenes.by_config(cfg, n)
@@ -267,8 +284,10 @@ def main():
     sb = stage_bytes(n, f_box, mean[3], int(mean[4]), mean[0], mean[1], mean[2], mean[5])
     dom = int(np.argmax(stage_ms))
     dom_name = STAGE_NAMES[dom]
-    launches_in_stage = {"sort": int(mean[4])}.get(dom_name, 1)
+    launches_in_stage = {"sort": int(mean[4]), "narrow": 4, "cell_table": 2}.get(dom_name, 1)
+    # per launch: algorithmic bytes of the stage / its launches, over the stage's CUDA-event time / its launches
     achieved = sb[dom_name] / (stage_ms[dom] * 1e-3) / 1e9
+    traffic = profiled_traffic(args.config, n, dom_name)
     stages = {STAGE_NAMES[i]: {"ms": round(float(stage_ms[i]), 4), "alg_bytes": int(sb[STAGE_NAMES[i]]),
                                "gbs": round(sb[STAGE_NAMES[i]] / max(stage_ms[i], 1e-9) / 1e6, 1)} for i in range(6)}
     total_bytes = sum(sb.values())
@@ -286,8 +305,9 @@ def main():
         "gpu_launches": 13 * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
-                     "launches_per_step": launches_in_stage,
+                     "frac": achieved / peak, "traffic": traffic["bytes"] if traffic else None,
+                     "traffic_source": traffic["source"] if traffic else None, "peak_kind": peak_kind,
+                     "alg_bytes_per_launch": sb[dom_name] / launches_in_stage, "launches_per_step": launches_in_stage,
                      "step_alg_bytes": int(total_bytes), "step_frac": total_bytes / (np.mean(dev_ms) * 1e-3) / 1e9 / peak},
         "stages": stages,
     }
