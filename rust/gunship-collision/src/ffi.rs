@@ -1,0 +1,81 @@
+//! `extern "C"` declarations -- one to one with include/gunship_collision.h (GSC_ABI_VERSION 1).
+#![allow(non_camel_case_types, dead_code)]
+use std::os::raw::{c_char, c_int, c_void};
+
+pub const GSC_OK: c_int = 0;
+pub const GSC_ERR_CAPACITY: c_int = 4;
+pub const GSC_SPHERE: u8 = 0;
+pub const GSC_BOX: u8 = 1;
+pub const GSC_MESH: u8 = 2;
+pub const GSC_FLAG_TIMING: u32 = 1;
+pub const GSC_NUM_STAGES: usize = 6;
+pub const GSC_HALO_RECORD_BYTES: usize = 96;
+
+pub enum gsc_ctx {}
+
+#[repr(C)]
+pub struct gsc_config {
+    pub device: i32,
+    pub max_colliders: u32,
+    pub max_pairs: u64,
+    pub max_candidates: u64,
+    pub max_cells: u64,
+    pub flags: u32,
+    pub reserved: u32,
+}
+
+#[repr(C)]
+pub struct gsc_step_out {
+    pub n_pairs: u64,
+    pub n_sphere_sphere: u64,
+    pub n_sphere_obb: u64,
+    pub n_obb_obb: u64,
+    pub n_cells: u64,
+    pub cell_size: f32,
+    pub n_wide: u32,
+    pub grid_origin: [i32; 3],
+    pub grid_dims: [i32; 3],
+    pub sort_passes: u32,
+    pub status_flags: u32,
+    pub stage_ms: [f32; GSC_NUM_STAGES],
+    pub step_ms: f32,
+    pub d_pairs: *const u32,
+}
+
+#[repr(C)]
+pub struct gsc_bounds {
+    pub longest_axis: f32,
+    pub world_min: [f32; 3],
+    pub world_max: [f32; 3],
+    pub status_flags: u32,
+    pub home_x_max: f32,
+}
+
+extern "C" {
+    pub fn gsc_create(cfg: *const gsc_config, out: *mut *mut gsc_ctx) -> c_int;
+    pub fn gsc_destroy(ctx: *mut gsc_ctx);
+    pub fn gsc_last_error(ctx: *const gsc_ctx) -> *const c_char;
+    pub fn gsc_abi_version() -> c_int;
+    pub fn gsc_upload_colliders(ctx: *mut gsc_ctx, n: u32, entity: *const u32, kind: *const u8, offset3: *const f32,
+                                size3: *const f32, global_index: *const u32) -> c_int;
+    pub fn gsc_update_transforms(ctx: *mut gsc_ctx, n: u32, pos3: *const f32, quat4: *const f32, scale3: *const f32) -> c_int;
+    pub fn gsc_bind_device_transforms(ctx: *mut gsc_ctx, n: u32, d_pos3: *const f32, d_quat4: *const f32,
+                                      d_scale3: *const f32) -> c_int;
+    pub fn gsc_step(ctx: *mut gsc_ctx, out: *mut gsc_step_out) -> c_int;
+    pub fn gsc_download_pairs(ctx: *mut gsc_ctx, dst: *mut u32, cap_pairs: u64, sorted: c_int, n_out: *mut u64) -> c_int;
+    pub fn gsc_debug_download(ctx: *mut gsc_ctx, what: c_int, dst: *mut c_void, dst_bytes: usize) -> c_int;
+    pub fn gsc_test_sphere_sphere(device: c_int, n: usize, a4: *const f32, b4: *const f32, out: *mut u8) -> c_int;
+    pub fn gsc_test_sphere_obb(device: c_int, n: usize, s4: *const f32, obb16: *const f32, out: *mut u8) -> c_int;
+    pub fn gsc_test_obb_obb(device: c_int, n: usize, a16: *const f32, b16: *const f32, out: *mut u8) -> c_int;
+    pub fn gsc_test_aabb_aabb(device: c_int, n: usize, a6: *const f32, b6: *const f32, out: *mut u8) -> c_int;
+    pub fn gsc_fnv1a_gridcell(device: c_int, n: usize, cells3: *const i16, out: *mut u64) -> c_int;
+    pub fn gsc_sort_pairs_u32(device: c_int, n: usize, keys: *mut u32, vals: *mut u32, key_bits: c_int) -> c_int;
+    pub fn gsc_phase_bounds(ctx: *mut gsc_ctx, local: *mut gsc_bounds) -> c_int;
+    pub fn gsc_set_global_bounds(ctx: *mut gsc_ctx, global: *const gsc_bounds) -> c_int;
+    pub fn gsc_set_x_window(ctx: *mut gsc_ctx, x_lo: i32, x_hi: i32) -> c_int;
+    pub fn gsc_local_x_range(ctx: *mut gsc_ctx, x_min: *mut i32, x_max: *mut i32) -> c_int;
+    pub fn gsc_halo_select(ctx: *mut gsc_ctx, x_lo: i32, x_hi: i32, d_records: *mut c_void, cap_records: u32,
+                           count: *mut u32) -> c_int;
+    pub fn gsc_halo_append(ctx: *mut gsc_ctx, count: u32, d_records: *const c_void) -> c_int;
+    pub fn gsc_phase_finish(ctx: *mut gsc_ctx, out: *mut gsc_step_out) -> c_int;
+}

@@ -1,0 +1,122 @@
+//! Drop-in for Gunship's `GridCollisionSystem` (src/component/collider/grid_collision.rs:110-285) that
+//! runs the collision step on a B200 through the C ABI of include/gunship_collision.h.
+//!
+//! What stays exactly as in the engine: `Collider`, `ColliderManager`, `BoundingVolumeManager`'s dense
+//! `entities` order, `CollisionSystem::update(&mut self, &Scene, f32)`, and the public field
+//! `collisions: HashSet<(Entity, Entity), FnvHashState>` that `CollisionCallbackManager::process_collisions`
+//! consumes (mod.rs:602, 678-708).  What changes: `bvh_update` + `GridCollisionSystem::update` become one
+//! `gsc_step`.  Errors: the engine panics on the same conditions (Cargo.toml `panic = "abort"`), so a
+//! non-zero status becomes `panic!`.
+//!
+//! NOT compiled in the authoring image (no Rust toolchain there) -- see INTEGRATION.md.
+mod ffi;
+
+use std::collections::HashSet;
+use std::ffi::CStr;
+use std::hash::BuildHasherDefault;
+use std::ptr;
+
+/// `Entity` is a `u32` id (src/old/ecs.rs:7-8).
+pub type Entity = u32;
+
+/// The engine passes its own `FnvHashState` (lib/hash); any `BuildHasher` works for the shim.
+pub type PairSet<S> = HashSet<(Entity, Entity), S>;
+
+/// Mirror of `enum Collider` (mod.rs:139-183) flattened for the FFI.
+#[derive(Debug, Clone, Copy, PartialEq)]
+pub enum Collider {
+    Sphere { offset: [f32; 3], radius: f32 },
+    Box { offset: [f32; 3], widths: [f32; 3] },
+    Mesh,
+}
+
+/// Derived transform of one entity (TransformManager position/rotation/scale_derived,
+/// component/transform.rs:441-459); rotation is the quaternion (x, y, z, w).
+#[derive(Debug, Clone, Copy)]
+pub struct DerivedTransform {
+    pub position: [f32; 3],
+    pub rotation: [f32; 4],
+    pub scale: [f32; 3],
+}
+
+pub struct GridCollisionSystem<S: std::hash::BuildHasher + Default = BuildHasherDefault<std::collections::hash_map::DefaultHasher>> {
+    ctx: *mut ffi::gsc_ctx,
+    n: u32,
+    pos: Vec<f32>,
+    quat: Vec<f32>,
+    scale: Vec<f32>,
+    pairs: Vec<u32>,
+    /// Same name, type shape and tuple order as grid_collision.rs:119: (later volume, earlier volume).
+    pub collisions: PairSet<S>,
+    pub cell_size: f32,
+}
+
+fn check(ctx: *const ffi::gsc_ctx, rc: i32) {
+    if rc != ffi::GSC_OK {
+        let msg = unsafe { CStr::from_ptr(ffi::gsc_last_error(ctx)) }.to_string_lossy().into_owned();
+        panic!("gunship_collision: status {}: {}", rc, msg); // the reference panics here too
+    }
+}
+
+impl<S: std::hash::BuildHasher + Default> GridCollisionSystem<S> {
+    /// `GridCollisionSystem::new()` (grid_collision.rs:122-216); `max_colliders` replaces the engine's
+    /// MAX_COMPONENTS cap (struct_component_manager.rs:9).
+    pub fn new(device: i32, max_colliders: u32) -> Self {
+        let cfg = ffi::gsc_config { device, max_colliders, max_pairs: 0, max_candidates: 0, max_cells: 0, flags: 0, reserved: 0 };
+        let mut ctx = ptr::null_mut();
+        let rc = unsafe { ffi::gsc_create(&cfg, &mut ctx) };
+        check(ptr::null(), rc);
+        GridCollisionSystem { ctx, n: 0, pos: vec![], quat: vec![], scale: vec![], pairs: vec![],
+                              collisions: HashSet::with_hasher(S::default()), cell_size: 0.0 }
+    }
+
+    /// Called when the collider set changes (`ColliderManager::assign` / `destroy`, mod.rs:221-223, 282-285):
+    /// `entities` and `colliders` in `BoundingVolumeManager.components` order -- that order orients every tuple.
+    pub fn set_colliders(&mut self, entities: &[Entity], colliders: &[Collider]) {
+        assert_eq!(entities.len(), colliders.len());
+        let n = entities.len();
+        let (mut kind, mut off, mut size) = (Vec::with_capacity(n), Vec::with_capacity(3 * n), Vec::with_capacity(3 * n));
+        for c in colliders {
+            match *c {
+                Collider::Sphere { offset, radius } => { kind.push(ffi::GSC_SPHERE); off.extend_from_slice(&offset); size.extend_from_slice(&[radius, 0.0, 0.0]); }
+                Collider::Box { offset, widths } => { kind.push(ffi::GSC_BOX); off.extend_from_slice(&offset); size.extend_from_slice(&widths); }
+                Collider::Mesh => { kind.push(ffi::GSC_MESH); off.extend_from_slice(&[0.0; 3]); size.extend_from_slice(&[0.0; 3]); } // -> GSC_ERR_KIND, as unimplemented!()
+            }
+        }
+        let rc = unsafe { ffi::gsc_upload_colliders(self.ctx, n as u32, entities.as_ptr(), kind.as_ptr(), off.as_ptr(), size.as_ptr(), ptr::null()) };
+        check(self.ctx, rc);
+        self.n = n as u32;
+    }
+
+    /// `bvh_update` + `GridCollisionSystem::update(&mut self, &BoundingVolumeManager)` (grid_collision.rs:218):
+    /// fills `self.collisions`.  `transforms[i]` belongs to `entities[i]` of `set_colliders`.
+    pub fn update(&mut self, transforms: &[DerivedTransform]) {
+        assert_eq!(transforms.len(), self.n as usize);
+        self.pos.clear(); self.quat.clear(); self.scale.clear();
+        for t in transforms {
+            self.pos.extend_from_slice(&t.position);
+            self.quat.extend_from_slice(&t.rotation);
+            self.scale.extend_from_slice(&t.scale);
+        }
+        let mut out: ffi::gsc_step_out = unsafe { std::mem::zeroed() };
+        unsafe {
+            check(self.ctx, ffi::gsc_update_transforms(self.ctx, self.n, self.pos.as_ptr(), self.quat.as_ptr(), self.scale.as_ptr()));
+            check(self.ctx, ffi::gsc_step(self.ctx, &mut out));
+        }
+        self.cell_size = out.cell_size;
+        self.pairs.resize(2 * out.n_pairs as usize, 0);
+        let mut n = 0u64;
+        let rc = unsafe { ffi::gsc_download_pairs(self.ctx, self.pairs.as_mut_ptr(), out.n_pairs, 0, &mut n) };
+        check(self.ctx, rc);
+        self.collisions.clear(); // grid_collision.rs:221
+        for p in self.pairs.chunks(2) {
+            self.collisions.insert((p[0], p[1]));
+        }
+    }
+}
+
+impl<S: std::hash::BuildHasher + Default> Drop for GridCollisionSystem<S> {
+    fn drop(&mut self) {
+        unsafe { ffi::gsc_destroy(self.ctx) }
+    }
+}

@@ -1,0 +1,83 @@
+"""N>1 host logic on CPU: world_size-2 (and 3) gloo process groups drive gunship_rs_b200.slabs.SlabDriver with
+the CPU stand-in backend; the union of the ranks' pair lists must be the oracle's single-process pair set."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, cfg, n, frames, ownership, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from gunship_rs_b200 import scenes, slabs
+    from slab_cpu_backend import CpuSlabBackend
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    s = scenes.by_config(cfg, n)
+    if ownership == "slabs":
+        owner = slabs.partition_x_slabs(s.pos[:, 0], world)
+    elif ownership == "scattered":
+        owner = (np.arange(s.n) % world).astype(np.int32)
+    else:  # one rank owns nothing
+        owner = np.zeros(s.n, dtype=np.int32)
+    mine = np.nonzero(owner == rank)[0]
+    be = CpuSlabBackend(s.entity[mine], s.kind[mine], s.offset[mine], s.size[mine], mine)
+    drv = slabs.SlabDriver(be)
+    for f in frames:
+        pos, quat = s.frame(f)
+        be.set_frame(pos[mine], quat[mine], s.scale[mine])
+        out = drv.step()
+        np.save(os.path.join(out_dir, f"p_{f}_{rank}.npy"), out.pairs)
+        np.save(os.path.join(out_dir, f"h_{f}_{rank}.npy"), np.array([drv.last_halo_in, drv.last_halo_out, len(mine)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,cfg,n,ownership", [(2, 4, 4000, "slabs"), (2, 3, 3000, "scattered"), (3, 2, 4000, "slabs"),
+                                                   (2, 1, 1000, "empty")])
+def test_union_of_rank_pairs_is_the_single_process_set(tmp_path, world, cfg, n, ownership):
+    import torch.multiprocessing as mp
+    import oracle_lib as O
+    from gunship_rs_b200 import scenes
+    frames = (0, 2)
+    mp.spawn(_worker, args=(world, _free_port(), cfg, n, frames, ownership, str(tmp_path)), nprocs=world, join=True)
+    s = scenes.by_config(cfg, n)
+    oracle = O.OracleSystem()
+    for f in frames:
+        pos, quat = s.frame(f)
+        want = oracle.step(s, pos, quat)
+        parts = [np.load(tmp_path / f"p_{f}_{r}.npy") for r in range(world)]
+        got = np.sort(np.concatenate(parts))
+        assert len(got) == len(want) and np.array_equal(got, want)   # complete and duplicate free
+        halo = [np.load(tmp_path / f"h_{f}_{r}.npy") for r in range(world)]
+        assert sum(h[0] for h in halo) == sum(h[1] for h in halo)     # everything sent was received
+        if ownership == "slabs":
+            assert all(h[0] < 0.6 * max(h[2], 1) for h in halo)       # the halo is a boundary layer, not the world
+            assert halo[-1][0] > 0
+        if ownership == "empty":
+            assert len(parts[1]) == 0 and halo[1][0] == 0
+    oracle.close()
+
+
+def test_partition_x_slabs_is_balanced_and_ordered():
+    from gunship_rs_b200 import slabs
+    x = np.random.default_rng(0).normal(size=10001).astype(np.float32)
+    for world in (1, 2, 3, 8):
+        owner = slabs.partition_x_slabs(x, world)
+        counts = np.bincount(owner, minlength=world)
+        assert counts.max() - counts.min() <= 1
+        for r in range(world - 1):
+            assert x[owner == r].max() <= x[owner == r + 1].min()
+    assert slabs.needed_range(5, 9) == (4, 9)
