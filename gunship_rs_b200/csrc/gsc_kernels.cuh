@@ -76,6 +76,7 @@ struct GridParams {
     int32_t dims[3];
     uint32_t num_cells;  // dims product; also the key given to wide volumes
     int32_t valid;
+    float qorg[3], qscale[3];  // 16-bit conservative box quantisation of k_pairs: t = (v - qorg) * qscale in [0, 65535]
 };
 
 // Per-step device control block.  Zeroed at the start of every step.
@@ -261,7 +262,7 @@ __global__ void k_grid_setup(FrameBlock *fb, unsigned long long max_cells, uint3
     g.valid = 0;
     g.num_cells = 0;
     g.cell_size = ord2f(fb->bounds[0]);
-    for (int a = 0; a < 3; ++a) { g.origin[a] = 0; g.dims[a] = 0; }
+    for (int a = 0; a < 3; ++a) { g.origin[a] = 0; g.dims[a] = 0; g.qorg[a] = 0.0f; g.qscale[a] = 0.0f; }
     fb->sort.num_passes = 0;
     uint32_t st = 0;
     if (n_total == 0 || fb->bounds[0] == 0) {  // nothing to do (no colliders): valid stays 0, not an error
@@ -273,8 +274,12 @@ __global__ void k_grid_setup(FrameBlock *fb, unsigned long long max_cells, uint3
     if (st == 0) {
         unsigned long long cells = 1;
         for (int a = 0; a < 3; ++a) {
-            float lo = cell_coord_f(ord2f(~fb->bounds[1 + a]), g.cell_size);
-            float hi = cell_coord_f(ord2f(fb->bounds[4 + a]), g.cell_size);
+            const float wmin = ord2f(~fb->bounds[1 + a]), wmax = ord2f(fb->bounds[4 + a]);
+            const float ext = wmax - wmin;
+            g.qorg[a] = wmin;
+            g.qscale[a] = ext > 0.0f ? 65535.0f / ext : 0.0f;  // flat world on this axis: everything quantises to [0, 1]
+            float lo = cell_coord_f(wmin, g.cell_size);
+            float hi = cell_coord_f(wmax, g.cell_size);
             if (a == 0 && has_window) {  // only the slab's columns get cells; home cells outside are dropped by k_cell_keys
                 lo = fmaxf(lo, (float)x_lo);
                 hi = fminf(fmaxf(hi, lo), fmaxf((float)x_hi, lo));
@@ -360,9 +365,24 @@ k_cell_keys(uint32_t n_total, const float4 *__restrict__ rec, uint32_t *__restri
 // the next cell along y / z (cell(max) > cell(min)), which is what lets k_pairs prune rows exactly.
 constexpr uint32_t kMetaReachY = 4u, kMetaReachZ = 8u;
 
+// and, for the filter loop of k_pairs, a 16 B conservatively quantised copy per volume:
+//   q[p] = (qmax.x << 16 | qmin.x, qmax.y << 16 | qmin.y, qmax.z << 16 | qmin.z, gidx << 4 | meta flags)
+// qmin = floor(t) - 1, qmax = ceil(t) + 1 with t = (v - world_min) * 65535 / world_extent, clamped to
+// [0, 65535]: the f32 rounding error of t is < 0.01 quanta, so exact overlap always implies quantised overlap
+// (never a false negative); the exact test runs on the survivors only.
 struct SortedVolumes {
     float4 *v;
+    uint4 *q;
 };
+
+GSC_DEV uint32_t quant_lo(float v, float org, float scale)
+{
+    return (uint32_t)fminf(fmaxf(floorf((v - org) * scale) - 1.0f, 0.0f), 65535.0f);
+}
+GSC_DEV uint32_t quant_hi(float v, float org, float scale)
+{
+    return (uint32_t)fminf(fmaxf(ceilf((v - org) * scale) + 1.0f, 0.0f), 65535.0f);
+}
 
 // ---- stage 3: cell start table + cell-order permutation of the volume records ---------------------
 // start[c] = first sorted position whose key >= c, for c in [0, num_cells]; thread p fills the gap
@@ -392,12 +412,18 @@ k_cell_table_permute(uint32_t n_total, const uint32_t *__restrict__ keys_a, cons
     }
     if (p < n_total) {
         const uint32_t i = vals[p];
-        const Volume v = volume_decode(__ldg(rec + 2 * (size_t)i), __ldg(rec + 2 * (size_t)i + 1));
+        const Volume v = volume_decode(ldg_gather(rec + 2 * (size_t)i), ldg_gather(rec + 2 * (size_t)i + 1));
         uint32_t meta = v.meta;
         if (cell_coord_f(v.mx[1], g.cell_size) > cell_coord_f(v.mn[1], g.cell_size)) meta |= kMetaReachY;
         if (cell_coord_f(v.mx[2], g.cell_size) > cell_coord_f(v.mn[2], g.cell_size)) meta |= kMetaReachZ;
         sv.v[2 * (size_t)p] = make_float4(v.mn[0], v.mn[1], v.mn[2], v.mx[0]);
         sv.v[2 * (size_t)p + 1] = make_float4(v.mx[1], v.mx[2], __uint_as_float(v.gidx), __uint_as_float(meta));
+        uint4 qv;
+        qv.x = (quant_hi(v.mx[0], g.qorg[0], g.qscale[0]) << 16) | quant_lo(v.mn[0], g.qorg[0], g.qscale[0]);
+        qv.y = (quant_hi(v.mx[1], g.qorg[1], g.qscale[1]) << 16) | quant_lo(v.mn[1], g.qorg[1], g.qscale[1]);
+        qv.z = (quant_hi(v.mx[2], g.qorg[2], g.qscale[2]) << 16) | quant_lo(v.mn[2], g.qorg[2], g.qscale[2]);
+        qv.w = (v.gidx << 4) | (meta & 15u);
+        sv.q[p] = qv;
     }
     const int64_t len = hi - lo + 1;
     if (len > kGapLong) {  // a huge run of empty cells (space between clusters / slabs): hand it to k_fill_gaps
@@ -456,11 +482,11 @@ k_fill_gaps(uint32_t *__restrict__ cell_start, const uint4 *__restrict__ gaps, c
 // index and append them -- one atomicAdd per class and CTA -- to the three global candidate lists.  The
 // shape tests run as separate, perfectly balanced kernels over those lists (stage 5).  Shared memory is
 // kept small on purpose: the candidate boxes are read through L1, which needs the carve-out.
-constexpr int kPairThreads = 256;
+constexpr int kPairThreads = 64;
 constexpr int kPairWarps = kPairThreads / 32;
 constexpr int kPairRows = 5;
 constexpr int kPairPriv = 8;    // private survivor slots per lane; a lane that fills them drains early
-constexpr int kPairCap = 1024;  // survivors staged per CTA (4 per volume); denser CTAs spill one by one
+constexpr int kPairCap = 256;   // survivors staged per CTA (4 per volume); denser CTAs spill one by one
 
 struct PairOut {
     uint2 *cand_ss;
@@ -494,7 +520,9 @@ GSC_DEV int pair_classify(uint32_t a_gidx, uint32_t a_meta, uint32_t b_gidx, uin
 // slow path of a full CTA list: classify and append one pair straight to the global lists
 __device__ __noinline__ void pair_spill(uint32_t p, uint32_t q, const float4 *__restrict__ sv, PairOut out, FrameBlock *fb)
 {
-    const float4 a1 = __ldg(sv + 2 * (size_t)p + 1), b1 = __ldg(sv + 2 * (size_t)q + 1);
+    const float4 a0 = __ldg(sv + 2 * (size_t)p), a1 = __ldg(sv + 2 * (size_t)p + 1);
+    const float4 b0 = __ldg(sv + 2 * (size_t)q), b1 = __ldg(sv + 2 * (size_t)q + 1);
+    if (a0.x > b0.w || b0.x > a0.w || a0.y > b1.x || b0.y > a1.x || a0.z > b1.y || b0.z > a1.y) return;  // exact AABB test
     uint2 item;
     const int cls = pair_classify(__float_as_uint(a1.z), __float_as_uint(a1.w), __float_as_uint(b1.z), __float_as_uint(b1.w), &item);
     unsigned long long *ctr = cls == 0 ? &fb->n_ss : (cls == 1 ? &fb->n_so : &fb->n_oo);
@@ -515,7 +543,7 @@ __device__ __noinline__ void pair_drain_lane(PairShared &sh, uint32_t p, uint32_
     }
 }
 
-__global__ void __launch_bounds__(kPairThreads, 5)
+__global__ void __launch_bounds__(kPairThreads, 20)
 k_pairs(uint32_t n_total, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ keys_b,
         SortedVolumes sv, const uint32_t *__restrict__ cell_start, PairOut out, FrameBlock *__restrict__ fb)
 {
@@ -528,23 +556,23 @@ k_pairs(uint32_t n_total, const uint32_t *__restrict__ keys_a, const uint32_t *_
     __syncthreads();
 
     const uint32_t p = blockIdx.x * kPairThreads + tid;
-    float amn0 = 0.f, amn1 = 0.f, amn2 = 0.f, amx0 = 0.f, amx1 = 0.f, amx2 = 0.f;
-    uint32_t a_gidx = 0, qsame = 0;
+    // A's quantised box: lo = qmin << 16 (compared with B's whole word), hi = qmax (compared with B's low half)
+    uint32_t alo0 = 0, alo1 = 0, alo2 = 0, ahi0 = 0, ahi1 = 0, ahi2 = 0, a_w3 = 0, qsame = 0;
     uint32_t lo[kPairRows], hi[kPairRows];
 #pragma unroll
     for (int r = 0; r < kPairRows; ++r) lo[r] = hi[r] = 0;
     if (p < n_total) {
-        const float4 a0 = __ldg(sv.v + 2 * (size_t)p), a1 = __ldg(sv.v + 2 * (size_t)p + 1);
+        const uint4 aq = __ldg(sv.q + p);
         const uint32_t key = keys[p];
-        const uint32_t a_meta = __float_as_uint(a1.w);
-        a_gidx = __float_as_uint(a1.z);
-        amn0 = a0.x; amn1 = a0.y; amn2 = a0.z;
-        amx0 = a0.w; amx1 = a1.x; amx2 = a1.y;
+        alo0 = aq.x << 16; ahi0 = aq.x >> 16;
+        alo1 = aq.y << 16; ahi1 = aq.y >> 16;
+        alo2 = aq.z << 16; ahi2 = aq.z >> 16;
+        a_w3 = aq.w;
         // ghosts only serve as the earlier volume; wide volumes (key == num_cells) go to k_wide_pairs
-        const bool active = !(a_meta & kMetaGhost) && key < g.num_cells;
+        const bool active = !(a_w3 & kMetaGhost) && key < g.num_cells;
         const uint32_t dz = (uint32_t)g.dims[2], dydz = (uint32_t)g.dims[1] * dz;
-        const uint32_t zhi = (a_meta & kMetaReachZ) ? 2u : 1u;  // end = start[kk + zhi]
-        const bool ry = a_meta & kMetaReachY;
+        const uint32_t zhi = (a_w3 & kMetaReachZ) ? 2u : 1u;  // end = start[kk + zhi]
+        const bool ry = a_w3 & kMetaReachY;
 #pragma unroll
         for (int r = 0; r < kPairRows; ++r) {
             // row base key kk = key + dx * dims.y * dims.z + dy * dims.z  (apron => always a valid cell)
@@ -563,40 +591,62 @@ k_pairs(uint32_t n_total, const uint32_t *__restrict__ keys_a, const uint32_t *_
     const uint32_t pa0 = (uint32_t)__cvta_generic_to_shared(&sh.priv[tid]);
     constexpr uint32_t kSlotStride = kPairThreads * 4u;
     uint32_t pa = pa0;
-    auto test = [&](uint32_t q, const float4 b0, const float4 b1, bool own) {
-        // AABB::test_aabb (bounding_volume.rs:338-343, 411-419), inclusive
-        const bool sep = amn0 > b0.w || b0.x > amx0 || amn1 > b1.x || b0.y > amx1 || amn2 > b1.y || b0.z > amx2;
-        const bool take = !own || (q < qsame) || (__float_as_uint(b1.z) < a_gidx);
+    // quantised AABB::test_aabb (bounding_volume.rs:338-343, 411-419; inclusive): separated on an axis iff
+    // B.qmax < A.qmin  <=>  whole word (B.qmax << 16 | B.qmin) < A.qmin << 16,  or  B.qmin > A.qmax
+    auto test = [&](uint32_t q, uint32_t w0, uint32_t w1, uint32_t w2, bool take) {
+        const bool sep = w0 < alo0 || (w0 & 0xffffu) > ahi0 || w1 < alo1 || (w1 & 0xffffu) > ahi1 || w2 < alo2 ||
+                         (w2 & 0xffffu) > ahi2;
         if (!sep && take) {
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(pa), "r"(q) : "memory");
             pa += kSlotStride;
         }
     };
+    auto drain_if_full = [&]() {
+        if (pa - pa0 >= (kPairPriv - 1) * kSlotStride) {  // fewer than two free slots left
+            pair_drain_lane(sh, p, (pa - pa0) / kSlotStride, tid, sv.v, out, fb);
+            pa = pa0;
+        }
+    };
 #pragma unroll
-    for (int r = 0; r < kPairRows; ++r) {
+    for (int r = 0; r < kPairRows - 1; ++r) {  // neighbour rows: 12 B per candidate
         const uint32_t qe = hi[r];
         uint32_t q = lo[r];
-        const bool own = r == kPairRows - 1;
 #pragma unroll 1
-        for (; q + 1 < qe; q += 2) {  // two candidates per trip: both loads in flight before either test
-            const float4 *v = sv.v + 2 * (size_t)q;
-            const float4 b0 = __ldg(v), b1 = __ldg(v + 1), c0 = __ldg(v + 2), c1 = __ldg(v + 3);
-            test(q, b0, b1, own);
-            test(q + 1, c0, c1, own);
-            if (pa - pa0 >= (kPairPriv - 1) * kSlotStride) {  // fewer than two free slots left
-                pair_drain_lane(sh, p, (pa - pa0) / kSlotStride, tid, sv.v, out, fb);
-                pa = pa0;
-            }
+        for (; q + 1 < qe; q += 2) {  // two candidates per trip: all loads in flight before either test
+            const uint4 *v = sv.q + q;
+            const uint2 b01 = __ldg(reinterpret_cast<const uint2 *>(v));
+            const uint32_t b2 = __ldg(reinterpret_cast<const uint32_t *>(v) + 2);
+            const uint2 c01 = __ldg(reinterpret_cast<const uint2 *>(v + 1));
+            const uint32_t c2 = __ldg(reinterpret_cast<const uint32_t *>(v + 1) + 2);
+            test(q, b01.x, b01.y, b2, true);
+            test(q + 1, c01.x, c01.y, c2, true);
+            drain_if_full();
         }
         if (q < qe) {
-            const float4 *v = sv.v + 2 * (size_t)q;
-            test(q, __ldg(v), __ldg(v + 1), own);
-            if (pa - pa0 >= (kPairPriv - 1) * kSlotStride) {
-                pair_drain_lane(sh, p, (pa - pa0) / kSlotStride, tid, sv.v, out, fb);
-                pa = pa0;
-            }
+            const uint4 *v = sv.q + q;
+            const uint2 b01 = __ldg(reinterpret_cast<const uint2 *>(v));
+            const uint32_t b2 = __ldg(reinterpret_cast<const uint32_t *>(v) + 2);
+            test(q, b01.x, b01.y, b2, true);
+            drain_if_full();
         }
         __syncwarp();  // reconverge before the next run: lanes must walk each run together
+    }
+    {  // own row (cells z-1, z): 16 B per candidate, same-cell pairs go to the larger global index
+        const uint32_t qe = hi[kPairRows - 1];
+        uint32_t q = lo[kPairRows - 1];
+#pragma unroll 1
+        for (; q + 1 < qe; q += 2) {
+            const uint4 b = __ldg(sv.q + q), c = __ldg(sv.q + q + 1);
+            test(q, b.x, b.y, b.z, q < qsame || b.w < a_w3);
+            test(q + 1, c.x, c.y, c.z, q + 1 < qsame || c.w < a_w3);
+            drain_if_full();
+        }
+        if (q < qe) {
+            const uint4 b = __ldg(sv.q + q);
+            test(q, b.x, b.y, b.z, q < qsame || b.w < a_w3);
+            drain_if_full();
+        }
+        __syncwarp();
     }
 
     // ---- compact the private slots into the CTA list: warp scan + one shared atomic per warp ----
@@ -628,8 +678,12 @@ k_pairs(uint32_t n_total, const uint32_t *__restrict__ keys_a, const uint32_t *_
         uint2 item = make_uint2(0, 0);
         if (i < have) {
             const uint2 e = sh.list[i];
-            const float4 a1 = __ldg(sv.v + 2 * (size_t)e.x + 1), c1 = __ldg(sv.v + 2 * (size_t)e.y + 1);
-            cls = pair_classify(__float_as_uint(a1.z), __float_as_uint(a1.w), __float_as_uint(c1.z), __float_as_uint(c1.w), &item);
+            const float4 a0 = __ldg(sv.v + 2 * (size_t)e.x), a1 = __ldg(sv.v + 2 * (size_t)e.x + 1);
+            const float4 c0 = __ldg(sv.v + 2 * (size_t)e.y), c1 = __ldg(sv.v + 2 * (size_t)e.y + 1);
+            // the exact AABB::test_aabb (bounding_volume.rs:338-343, 411-419), inclusive
+            const bool sep = a0.x > c0.w || c0.x > a0.w || a0.y > c1.x || c0.y > a1.x || a0.z > c1.y || c0.z > a1.y;
+            if (!sep)
+                cls = pair_classify(__float_as_uint(a1.z), __float_as_uint(a1.w), __float_as_uint(c1.z), __float_as_uint(c1.w), &item);
         }
         uint32_t m[3], rank = 0;
 #pragma unroll

@@ -18,6 +18,16 @@ GSC_DEV float mul(float a, float b) { return __fmul_rn(a, b); }
 GSC_DEV float add(float a, float b) { return __fadd_rn(a, b); }
 GSC_DEV float sub(float a, float b) { return __fsub_rn(a, b); }
 
+// Random-access 16 B load for gathers of 32 B / 64 B records: read-only path with the smallest L2 prefetch
+// size PTX offers.  By default a missing sector makes L2 fetch its whole 128 B line from HBM (ncu: 3.8
+// sectors per request on the cell-order gather), which quadruples the DRAM bytes of a 32 B gather.
+GSC_DEV float4 ldg_gather(const float4 *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L2::64B.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
 // vector.rs:190-196  Dot: x*x' + y*y' + z*z'
 GSC_DEV float dot3(float ax, float ay, float az, float bx, float by, float bz)
 {

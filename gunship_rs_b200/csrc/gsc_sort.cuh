@@ -85,7 +85,11 @@ __global__ void __launch_bounds__(256) k_radix_histogram(const uint32_t *__restr
 // One radix pass.  grid = ceil(n / kSortTile) CTAs of kSortThreads threads.
 //   keys_in/vals_in -> keys_out/vals_out; vals_in == nullptr means "value = position" (first pass).
 //   ctl->num_passes is data dependent: passes beyond it exit at once and the ping-pong simply stops.
-__global__ void __launch_bounds__(kSortThreads)
+// Register budget: 64 (4 CTAs = 32 warps per SM).  Values are loaded only after the keys have been
+// ranked and staged, so keys and values are never live together.
+constexpr int kLookBatch = 8;  // predecessors inspected per look-back round trip (independent loads)
+
+__global__ void __launch_bounds__(kSortThreads, 4)
 k_onesweep_pass(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                 uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n, int pass,
                 const SortControl *__restrict__ ctl, const uint32_t *__restrict__ hist /*[kMaxPasses][256]*/,
@@ -95,8 +99,8 @@ k_onesweep_pass(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
     constexpr int WARPS = kSortThreads / 32;
     constexpr int WTILE = 32 * kSortIpt;
     __shared__ uint32_t s_hist[WARPS][kRadix];
-    __shared__ uint32_t s_data[kSortTile];
-    __shared__ uint32_t s_binstart[kRadix];
+    __shared__ uint32_t s_keys[kSortTile];
+    __shared__ uint32_t s_vals[kSortTile];
     __shared__ uint32_t s_goff[kRadix];
     __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_tile;
@@ -112,26 +116,16 @@ k_onesweep_pass(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
     const uint32_t tile_base = tile * (uint32_t)kSortTile;
     const uint32_t warp_base = tile_base + warp * WTILE + lane;
 
-    uint32_t key[kSortIpt], val[kSortIpt];
+    uint32_t key[kSortIpt];
 #pragma unroll
     for (int j = 0; j < kSortIpt; ++j) {
         const uint32_t idx = warp_base + j * 32;
         key[j] = idx < n ? keys_in[idx] : 0xffffffffu;
     }
-    if (vals_in) {
-#pragma unroll
-        for (int j = 0; j < kSortIpt; ++j) {
-            const uint32_t idx = warp_base + j * 32;
-            val[j] = idx < n ? vals_in[idx] : 0u;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < kSortIpt; ++j) val[j] = warp_base + j * 32;
-    }
 
     // ---- stable ranking inside the warp: order is (j, lane) == original order ----
     const uint32_t lt_mask = (1u << lane) - 1u;
-    uint32_t rank[kSortIpt];
+    uint16_t rank[kSortIpt];
 #pragma unroll
     for (int j = 0; j < kSortIpt; ++j) {
         const uint32_t d = (key[j] >> shift) & 255u;
@@ -141,7 +135,7 @@ k_onesweep_pass(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
         __syncwarp();
         if (r == 0) s_hist[warp][d] = before + __popc(peers);
         __syncwarp();
-        rank[j] = before + r;
+        rank[j] = (uint16_t)(before + r);
     }
     __syncthreads();
 
@@ -164,48 +158,68 @@ k_onesweep_pass(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
     const uint32_t digit_base = block_excl_scan256(hist[pass * kRadix + tid], s_warp, nullptr);
     const uint32_t bin_start = block_excl_scan256(tile_count, s_warp, nullptr);
 
+    // ---- decoupled look-back, kLookBatch predecessors per round trip ----
     uint32_t excl = 0;
     if (tile != 0) {
         int prev = (int)tile - 1;
-        for (;;) {
-            const uint32_t v = lb[(size_t)prev * kRadix + tid];
-            if ((v & ~kLbMask) == 0) continue;  // predecessor has not published yet
-            excl += v & kLbMask;
-            if (v & kLbIncl) break;
-            --prev;
+        bool done = false;
+        while (!done) {
+            uint32_t v[kLookBatch];
+#pragma unroll
+            for (int j = 0; j < kLookBatch; ++j)
+                v[j] = (prev - j >= 0) ? (uint32_t)lb[(size_t)(prev - j) * kRadix + tid] : (uint32_t)(1u << 31);  // before tile 0: empty inclusive prefix
+            int used = 0;
+#pragma unroll
+            for (int j = 0; j < kLookBatch; ++j) {
+                if (done || used != j) continue;
+                if ((v[j] & ~kLbMask) == 0) continue;  // not published yet: retry from this one
+                excl += v[j] & kLbMask;
+                ++used;
+                if (v[j] & kLbIncl) done = true;
+            }
+            prev -= used;
         }
         lb[(size_t)tile * kRadix + tid] = (excl + tile_count) | kLbIncl;
     }
-    s_binstart[tid] = bin_start;
-    s_goff[tid] = digit_base + excl - bin_start;  // wraps; added back to the tile-local position below
+    // position of digit run d in the output minus its position in the tile
+    s_goff[tid] = digit_base + excl - bin_start;
+    // per-warp offsets become absolute tile positions
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) s_hist[w][tid] += bin_start;
     __syncthreads();
 
     // ---- stage the tile digit-sorted in shared memory, then write digit runs contiguously ----
 #pragma unroll
     for (int j = 0; j < kSortIpt; ++j) {
         const uint32_t d = (key[j] >> shift) & 255u;
-        rank[j] += s_binstart[d] + s_hist[warp][d];
-        s_data[rank[j]] = key[j];
+        const uint32_t pos = (uint32_t)rank[j] + s_hist[warp][d];
+        rank[j] = (uint16_t)pos;
+        s_keys[pos] = key[j];
     }
+    if (vals_in) {
+#pragma unroll
+        for (int j = 0; j < kSortIpt; ++j) {
+            const uint32_t idx = warp_base + j * 32;
+            key[j] = idx < n ? vals_in[idx] : 0u;  // key[] now holds the values
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kSortIpt; ++j) key[j] = warp_base + j * 32;
+    }
+#pragma unroll
+    for (int j = 0; j < kSortIpt; ++j) s_vals[rank[j]] = key[j];
     __syncthreads();
     const uint32_t remaining = n - tile_base;
     const uint32_t valid = remaining < (uint32_t)kSortTile ? remaining : (uint32_t)kSortTile;
-    uint32_t dst[kSortIpt];
 #pragma unroll
     for (int j = 0; j < kSortIpt; ++j) {
         const uint32_t i = tid + j * kSortThreads;
-        const uint32_t k = s_data[i];
-        dst[j] = s_goff[(k >> shift) & 255u] + i;
-        if (i < valid) keys_out[dst[j]] = k;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < kSortIpt; ++j) s_data[rank[j]] = val[j];
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < kSortIpt; ++j) {
-        const uint32_t i = tid + j * kSortThreads;
-        if (i < valid) vals_out[dst[j]] = s_data[i];
+        if (i < valid) {
+            const uint32_t k = s_keys[i];
+            const uint32_t dst = s_goff[(k >> shift) & 255u] + i;
+            keys_out[dst] = k;
+            vals_out[dst] = s_vals[i];
+        }
     }
 }
 
