@@ -16,6 +16,8 @@ GSC_SPHERE, GSC_BOX, GSC_MESH = 0, 1, 2
 GSC_FLAG_TIMING, GSC_FLAG_GRAPH = 1, 2
 GSC_NUM_STAGES = 6
 GSC_HALO_RECORD_BYTES = 96
+GSC_MAX_PEERS = 16
+GSC_IPC_EXPORT_BYTES = 256
 STAGE_NAMES = ("bvh_update", "cell_keys", "sort", "cell_table", "pairs", "narrow")
 (GSC_DBG_AABB, GSC_DBG_SORTED_KEYS, GSC_DBG_SORTED_IDX, GSC_DBG_CELL_START, GSC_DBG_OBB) = range(5)
 
@@ -56,7 +58,8 @@ EXPORTS = (
     "gsc_update_transforms", "gsc_bind_device_transforms", "gsc_step", "gsc_download_pairs", "gsc_debug_download",
     "gsc_test_sphere_sphere", "gsc_test_sphere_obb", "gsc_test_obb_obb", "gsc_test_aabb_aabb", "gsc_fnv1a_gridcell",
     "gsc_sort_pairs_u32", "gsc_phase_bounds", "gsc_set_global_bounds", "gsc_local_x_range", "gsc_halo_select",
-    "gsc_halo_append", "gsc_phase_finish", "gsc_set_x_window",
+    "gsc_halo_append", "gsc_phase_finish", "gsc_set_x_window", "gsc_ipc_export", "gsc_ipc_open_peer", "gsc_halo_push",
+    "gsc_halo_sync", "gsc_halo_commit",
 )
 
 _lib = None
@@ -97,6 +100,11 @@ def load():
     L.gsc_halo_append.argtypes = [vp, C.c_uint32, vp]
     L.gsc_phase_finish.argtypes = [vp, C.POINTER(GscStepOut)]
     L.gsc_set_x_window.argtypes = [vp, C.c_int32, C.c_int32]
+    L.gsc_ipc_export.argtypes = [vp, vp, C.c_size_t]
+    L.gsc_ipc_open_peer.argtypes = [vp, C.c_uint32, vp, C.c_size_t]
+    L.gsc_halo_push.argtypes = [vp, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32]
+    L.gsc_halo_sync.argtypes = [vp]
+    L.gsc_halo_commit.argtypes = [vp, C.POINTER(C.c_uint32)]
     for name in EXPORTS:
         fn = getattr(L, name)  # raises AttributeError if the .so does not export it
         if name not in ("gsc_destroy", "gsc_last_error"):

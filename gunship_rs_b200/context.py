@@ -142,6 +142,27 @@ class CollisionContext:
     def halo_append(self, count: int, d_records: int):
         self._check(self._lib.gsc_halo_append(self._h, count, d_records or None))
 
+    # halo push over peer memory (GPUs of one box)
+    def ipc_export(self) -> bytes:
+        buf = C.create_string_buffer(N.GSC_IPC_EXPORT_BYTES)
+        self._check(self._lib.gsc_ipc_export(self._h, buf, N.GSC_IPC_EXPORT_BYTES))
+        return buf.raw
+
+    def ipc_open_peer(self, peer: int, blob: bytes):
+        buf = C.create_string_buffer(blob, N.GSC_IPC_EXPORT_BYTES)
+        self._check(self._lib.gsc_ipc_open_peer(self._h, peer, buf, N.GSC_IPC_EXPORT_BYTES))
+
+    def halo_push(self, peer: int, x_lo: int, x_hi: int, peer_n_local: int):
+        self._check(self._lib.gsc_halo_push(self._h, peer, x_lo, x_hi, peer_n_local))
+
+    def halo_sync(self):
+        self._check(self._lib.gsc_halo_sync(self._h))
+
+    def halo_commit(self) -> int:
+        n = C.c_uint32(0)
+        self._check(self._lib.gsc_halo_commit(self._h, C.byref(n)))
+        return int(n.value)
+
     def phase_finish(self) -> N.GscStepOut:
         out = N.GscStepOut()
         rc = self._lib.gsc_phase_finish(self._h, C.byref(out))

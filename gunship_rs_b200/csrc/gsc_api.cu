@@ -7,6 +7,7 @@
 #include "../../include/gunship_collision.h"
 
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdarg>
@@ -68,6 +69,14 @@ struct gsc_ctx {
     float4 *d_halo_rec = nullptr, *d_halo_obb = nullptr;
     uint32_t *d_halo_count = nullptr;
     uint32_t halo_cap = 0;
+
+    // peer contexts opened over CUDA IPC (multi-GPU halo push)
+    struct Peer {
+        float4 *rec = nullptr, *obb = nullptr;
+        FrameBlock *fb = nullptr;
+        uint32_t cap = 0;
+        bool self = false;
+    } peers[GSC_MAX_PEERS];
 
     uint64_t max_pairs = 0, max_cands = 0, max_cells = 0;
     uint64_t last_pairs = 0;
@@ -245,6 +254,12 @@ void gsc_destroy(gsc_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto &p : c->peers)
+        if (p.rec && !p.self) {
+            cudaIpcCloseMemHandle(p.rec);
+            cudaIpcCloseMemHandle(p.obb);
+            cudaIpcCloseMemHandle(p.fb);
+        }
     void *bufs[] = { c->d_entity, c->d_gidx, c->d_kind, c->d_offset, c->d_size, c->d_pos, c->d_quat, c->d_scale, c->d_rec,
                      c->d_rec_sorted, c->d_qrec_sorted, c->d_obb, c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1], c->d_cell_start,
                      c->d_wide, c->d_gaps, c->d_pairs, c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->d_pairs_sorted, c->d_fb, c->d_lookback,
@@ -476,6 +491,95 @@ int gsc_set_global_bounds(gsc_ctx *c, const gsc_bounds *g)
     CU(c, cudaGetLastError());
     CU(c, cudaStreamSynchronize(c->stream));  // enc lives on this stack frame
     c->global_bounds_set = true;
+    return GSC_OK;
+}
+
+// ---- halo push over peer memory ------------------------------------------------------------------------
+struct IpcBlob {  // what gsc_ipc_export hands to the other ranks (GSC_IPC_EXPORT_BYTES)
+    cudaIpcMemHandle_t rec, obb, fb;
+    uint32_t cap;
+    uint32_t device;
+    uint64_t ctx_tag;  // address of the exporting context: lets a rank recognise its own blob
+    uint32_t pad[12];
+};
+static_assert(sizeof(IpcBlob) == GSC_IPC_EXPORT_BYTES, "IpcBlob size");
+
+int gsc_ipc_export(gsc_ctx *c, void *blob, size_t blob_bytes)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!blob || blob_bytes < sizeof(IpcBlob)) return fail(c, GSC_ERR_INVALID, "gsc_ipc_export: need %zu bytes", sizeof(IpcBlob));
+    IpcBlob b;
+    memset(&b, 0, sizeof b);
+    CU(c, cudaIpcGetMemHandle(&b.rec, c->d_rec));
+    CU(c, cudaIpcGetMemHandle(&b.obb, c->d_obb));
+    CU(c, cudaIpcGetMemHandle(&b.fb, c->d_fb));
+    b.cap = c->cap;
+    b.device = (uint32_t)c->device;
+    b.ctx_tag = (uint64_t)(uintptr_t)c ^ ((uint64_t)getpid() << 40);
+    memcpy(blob, &b, sizeof b);
+    return GSC_OK;
+}
+
+int gsc_ipc_open_peer(gsc_ctx *c, uint32_t peer, const void *blob, size_t blob_bytes)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (peer >= GSC_MAX_PEERS || !blob || blob_bytes < sizeof(IpcBlob)) return fail(c, GSC_ERR_INVALID, "gsc_ipc_open_peer: bad argument");
+    IpcBlob b;
+    memcpy(&b, blob, sizeof b);
+    gsc_ctx::Peer &p = c->peers[peer];
+    if (p.rec && !p.self) {  // re-open: drop the old mapping
+        cudaIpcCloseMemHandle(p.rec);
+        cudaIpcCloseMemHandle(p.obb);
+        cudaIpcCloseMemHandle(p.fb);
+    }
+    p = gsc_ctx::Peer();
+    if (b.ctx_tag == ((uint64_t)(uintptr_t)c ^ ((uint64_t)getpid() << 40))) {  // my own export
+        p.rec = c->d_rec;
+        p.obb = c->d_obb;
+        p.fb = c->d_fb;
+        p.cap = c->cap;
+        p.self = true;
+        return GSC_OK;
+    }
+    CU(c, cudaIpcOpenMemHandle((void **)&p.rec, b.rec, cudaIpcMemLazyEnablePeerAccess));
+    CU(c, cudaIpcOpenMemHandle((void **)&p.obb, b.obb, cudaIpcMemLazyEnablePeerAccess));
+    CU(c, cudaIpcOpenMemHandle((void **)&p.fb, b.fb, cudaIpcMemLazyEnablePeerAccess));
+    p.cap = b.cap;
+    return GSC_OK;
+}
+
+int gsc_halo_push(gsc_ctx *c, uint32_t peer, int32_t x_lo, int32_t x_hi, uint32_t peer_n_local)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (peer >= GSC_MAX_PEERS || !c->peers[peer].rec || c->peers[peer].self)
+        return fail(c, GSC_ERR_INVALID, "gsc_halo_push: peer %u was not opened with gsc_ipc_open_peer", peer);
+    if (!c->global_bounds_set) return fail(c, GSC_ERR_INVALID, "gsc_halo_push: call gsc_set_global_bounds first");
+    const gsc_ctx::Peer &p = c->peers[peer];
+    if (c->n_local && x_lo <= x_hi)
+        k_halo_push<<<kGridStrideBlocks, 256, 0, c->stream>>>(c->n_local, c->d_rec, c->d_obb, x_lo, x_hi, p.rec, p.obb, p.fb,
+                                                            peer_n_local, p.cap, c->d_fb);
+    CU(c, cudaGetLastError());
+    return GSC_OK;  // asynchronous: gsc_halo_sync waits for it
+}
+
+int gsc_halo_sync(gsc_ctx *c)
+{
+    if (int rc = check_ctx(c)) return rc;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return GSC_OK;
+}
+
+int gsc_halo_commit(gsc_ctx *c, uint32_t *n_ghost)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!c->bounds_done) return fail(c, GSC_ERR_INVALID, "gsc_halo_commit: call gsc_phase_bounds first");
+    uint32_t pushed = 0;
+    CU(c, cudaMemcpyAsync(&pushed, &c->d_fb->n_ghost_in, sizeof pushed, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (n_ghost) *n_ghost = pushed;
+    if ((uint64_t)c->n_local + c->n_ghost + pushed > c->cap)
+        return fail(c, GSC_ERR_CAPACITY, "gsc_halo_commit: %u local + %u pushed ghosts > max_colliders %u", c->n_local, pushed, c->cap);
+    c->n_ghost += pushed;
     return GSC_OK;
 }
 

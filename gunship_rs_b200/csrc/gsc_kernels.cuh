@@ -87,8 +87,8 @@ struct FrameBlock {
     unsigned long long n_pairs, n_ss, n_so, n_oo;
     uint32_t tile_counter[kMaxPasses];
     uint32_t xrange[2];  // ~(min home x + 32768), (max home x + 32768) of local volumes
-    uint32_t n_gaps;  // long empty key gaps queued for k_fill_gaps
-    uint32_t pad[1];
+    uint32_t n_gaps;      // long empty key gaps queued for k_fill_gaps
+    uint32_t n_ghost_in;  // ghosts written into this context by peer GPUs this step (k_halo_push, system-scope atomic)
     GridParams grid;
     SortControl sort;
     uint32_t hist[kMaxPasses][kRadix];
@@ -936,6 +936,48 @@ k_halo_select(uint32_t n_local, const float4 *__restrict__ rec, const float4 *__
             if (__float_as_uint(r1.w) & kMetaBox) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) d[2 + k] = __ldg(obb + 4 * (size_t)i + k);
+            }
+        }
+    }
+}
+
+// Fused select + transfer over peer memory (NVLink / NVSwitch): the local volumes whose home x-cell lies in
+// [x_lo, x_hi] are written straight into the PEER context's record arrays behind its local volumes, as ghosts
+// with their new local index; the slot comes from a system-scope atomic on the peer's FrameBlock, one per warp.
+// No staging buffer, no count exchange, no append kernel on the receiving side.
+__global__ void __launch_bounds__(256)
+k_halo_push(uint32_t n_local, const float4 *__restrict__ rec, const float4 *__restrict__ obb, int x_lo, int x_hi,
+            float4 *__restrict__ peer_rec, float4 *__restrict__ peer_obb, FrameBlock *peer_fb, uint32_t peer_first,
+            uint32_t peer_cap, const FrameBlock *__restrict__ fb)
+{
+    const GridParams g = fb->grid;
+    if (!g.valid) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_round = (n_local + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        bool sel = false;
+        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+        if (i < n_local) {
+            r0 = __ldg(rec + 2 * (size_t)i);
+            r1 = __ldg(rec + 2 * (size_t)i + 1);
+            const Volume v = volume_decode(r0, r1);
+            const int x = (int)cell_coord_f(v.mn[0], g.cell_size);
+            sel = x >= x_lo && x <= x_hi;
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, sel);
+        if (m == 0) continue;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd_system(&peer_fb->n_ghost_in, (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t at = peer_first + base + __popc(m & ((1u << lane) - 1u));
+        if (sel && at < peer_cap) {
+            const uint32_t box = __float_as_uint(r1.w) & kMetaBox;
+            r1.w = __uint_as_float((at << 4) | box | kMetaGhost);
+            peer_rec[2 * (size_t)at] = r0;
+            peer_rec[2 * (size_t)at + 1] = r1;
+            if (box) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) peer_obb[4 * (size_t)at + k] = __ldg(obb + 4 * (size_t)i + k);
             }
         }
     }

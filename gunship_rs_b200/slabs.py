@@ -20,6 +20,7 @@ The device work is behind a small backend interface so the same driver runs on t
 """
 from __future__ import annotations
 
+import os
 import time
 
 import numpy as np
@@ -53,7 +54,7 @@ def needed_range(x_min: int, x_max: int):
 class SlabDriver:
     """One collision step across `world` ranks.  `backend` does the device work of this rank:
 
-    phase_bounds() -> (longest_axis, world_min[3], world_max[3], status_flags, home_x_max)
+    phase_bounds() -> (longest_axis, world_min[3], world_max[3], status_flags, home_x_max, n_local)
     set_global_bounds(longest_axis, world_min, world_max, status_flags)
     set_x_window(x_lo, x_hi)                                home x-cells this rank's grid must cover
     halo_select(x_lo, x_hi) -> (count, tensor)              uint8 tensor, count * RECORD_BYTES valid bytes
@@ -72,18 +73,37 @@ class SlabDriver:
         self.world = dist.get_world_size(group)
         self.last_halo_in = 0
         self.last_halo_out = 0
+        self.push = False
+
+    def enable_peer_push(self):
+        """GPUs of one box: open every other rank's record arrays over CUDA IPC so that the halo is written
+        straight into the neighbour's memory by the selecting kernel (gsc_halo_push) -- no staging buffers, no
+        count exchange, no send/recv.  Collective: every rank of the group must call it."""
+        import torch
+        dist, be = self.dist, self.backend
+        dev = be.tensor_device
+        mine = torch.frombuffer(bytearray(be.ipc_export()), dtype=torch.uint8).to(dev)
+        blobs = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(blobs, mine, group=self.group)
+        for s_, b in enumerate(blobs):
+            if s_ != self.rank:
+                be.ipc_open_peer(s_, bytes(b.cpu().numpy().tobytes()))
+        self.push = True
 
     def step(self):
         import torch
         dist, be = self.dist, self.backend
         dev = be.tensor_device
-        longest, wmin, wmax, status, home_x_max = be.phase_bounds()
+        longest, wmin, wmax, status, home_x_max, n_local = be.phase_bounds()
         # ONE all-gather carries everything the ranks must agree on: the global cell size (max longest axis) and
         # world box (they place the grid), and every rank's home x-range in world units
-        mine = torch.tensor([longest, *wmin, *wmax, home_x_max, float(status)], dtype=torch.float32, device=dev)
-        allb = [torch.zeros(9, dtype=torch.float32, device=dev) for _ in range(self.world)]
+        # (f64 carries the f32 values exactly, and the collider counts the peer push needs)
+        mine = torch.tensor([longest, *wmin, *wmax, home_x_max, float(status), float(n_local)], dtype=torch.float64, device=dev)
+        allb = [torch.zeros(10, dtype=torch.float64, device=dev) for _ in range(self.world)]
         dist.all_gather(allb, mine, group=self.group)
-        allb = torch.stack(allb).cpu().numpy()                       # [world, 9] float32
+        allb = torch.stack(allb).cpu().numpy()                       # [world, 10]
+        peer_n_local = allb[:, 9].astype(np.int64)
+        allb = allb.astype(np.float32)
         cell = np.float32(allb[:, 0].max())
         g_min = allb[:, 1:4].min(axis=0)
         g_max = allb[:, 4:7].max(axis=0)
@@ -100,6 +120,24 @@ class SlabDriver:
         x_min, x_max = ranges[self.rank]
         if x_min <= x_max:
             be.set_x_window(*needed_range(x_min, x_max))
+
+        if self.push:
+            # fused select + transfer: my volumes in rank s's needed range go straight into its arrays
+            pushed_to = 0
+            if x_min <= x_max:
+                for s, (smin, smax) in enumerate(ranges):
+                    if s == self.rank or smin > smax:
+                        continue
+                    lo, hi = needed_range(smin, smax)
+                    lo, hi = max(lo, x_min), min(hi, x_max)
+                    if lo <= hi:
+                        be.halo_push(s, lo, hi, int(peer_n_local[s]))
+                        pushed_to += 1
+            be.halo_sync()                       # my pushes have landed ...
+            dist.barrier(group=self.group)       # ... and so have everyone else's
+            self.last_halo_in = be.halo_commit()
+            self.last_halo_out = pushed_to
+            return be.phase_finish()
 
         # what each other rank needs from me
         send = {}
@@ -160,7 +198,8 @@ class GpuSlabBackend:
 
     def phase_bounds(self):
         b = self.ctx.phase_bounds()
-        return float(b.longest_axis), list(b.world_min), list(b.world_max), int(b.status_flags), float(b.home_x_max)
+        return (float(b.longest_axis), list(b.world_min), list(b.world_max), int(b.status_flags), float(b.home_x_max),
+                self.ctx.n)
 
     def set_global_bounds(self, longest, wmin, wmax, status):
         b = N.GscBounds()
@@ -209,6 +248,22 @@ class GpuSlabBackend:
     def sync(self):
         self.torch.cuda.synchronize(self.cuda)
 
+    # peer push (CUDA IPC)
+    def ipc_export(self):
+        return self.ctx.ipc_export()
+
+    def ipc_open_peer(self, peer, blob):
+        self.ctx.ipc_open_peer(peer, blob)
+
+    def halo_push(self, peer, x_lo, x_hi, peer_n_local):
+        self.ctx.halo_push(peer, x_lo, x_hi, peer_n_local)
+
+    def halo_sync(self):
+        self.ctx.halo_sync()
+
+    def halo_commit(self):
+        return self.ctx.halo_commit()
+
     def phase_finish(self):
         return self.ctx.phase_finish()
 
@@ -253,6 +308,8 @@ def bench_multi_gpu(args, n, rank, world, local_rank, metric, unit, workload_nam
     ctx.upload_colliders(scene.entity[mine], scene.kind[mine], scene.offset[mine], scene.size[mine],
                          global_index=mine.astype(np.uint32))
     driver = SlabDriver(GpuSlabBackend(ctx, local_rank))
+    if os.environ.get("GSC_HALO", "push") == "push":
+        driver.enable_peer_push()  # halo written straight into the neighbour's HBM over NVLink
     f_box = float((scene.kind == 1).mean())
 
     def step_resident(i):
@@ -334,7 +391,9 @@ def bench_multi_gpu(args, n, rank, world, local_rank, metric, unit, workload_nam
             "ms_per_step": 1e3 * span / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.config, n), "frames_cycled": nframes,
-                       "partition": f"{world} count-balanced x-slabs, one-cell halo (+x direction) over NCCL",
+                       "partition": f"{world} count-balanced x-slabs, one-cell halo (+x direction), " +
+                                    ("pushed into peer HBM over NVLink (CUDA IPC), NCCL for the bounds all-gather and the barrier"
+                                     if driver.push else "NCCL send/recv"),
                        "l2": "inputs larger than L2 (no flush needed)" if n_local * 100 > 126e6 else "per-rank inputs near L2 size",
                        "box_fraction": round(f_box, 3), "contact_pairs_per_step": int(sums[0]),
                        "halo_colliders_per_step": int(sums[5])},

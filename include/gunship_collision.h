@@ -188,6 +188,22 @@ int gsc_halo_select(gsc_ctx *ctx, int32_t x_lo, int32_t x_hi, void *d_records, u
 /* append `count` ghost colliders (records produced by gsc_halo_select on another rank, DEVICE memory);
  * ghosts take part as the earlier volume of a pair only */
 int gsc_halo_append(gsc_ctx *ctx, uint32_t count, const void *d_records);
+/* -- the same exchange fused with the transfer, for GPUs of one box (NVLink / NVSwitch peer memory) --
+ * Setup (once): every rank calls gsc_ipc_export, the blobs are all-gathered, every rank opens every other
+ * rank's blob with gsc_ipc_open_peer(peer = rank).  Per step, instead of select / send / recv / append:
+ *   gsc_halo_push(peer s, xmin_s - 1, xmax_s, n_local of s)   select + write straight into rank s's arrays
+ *   gsc_halo_sync -> [barrier across ranks] -> gsc_halo_commit   adopt what the peers pushed into me
+ * The receiving context must not start its next gsc_phase_bounds before all pushes of this step are done
+ * (the barrier), and pushes must not start before every rank's gsc_phase_bounds of this step has returned
+ * (the bounds all-gather orders that). */
+#define GSC_MAX_PEERS 16
+#define GSC_IPC_EXPORT_BYTES 256
+int gsc_ipc_export(gsc_ctx *ctx, void *blob, size_t blob_bytes);
+int gsc_ipc_open_peer(gsc_ctx *ctx, uint32_t peer, const void *blob, size_t blob_bytes);
+int gsc_halo_push(gsc_ctx *ctx, uint32_t peer, int32_t x_lo, int32_t x_hi, uint32_t peer_n_local);
+int gsc_halo_sync(gsc_ctx *ctx);
+int gsc_halo_commit(gsc_ctx *ctx, uint32_t *n_ghost);
+
 /* stages 1..5 on local + ghost colliders */
 int gsc_phase_finish(gsc_ctx *ctx, gsc_step_out *out);
 

@@ -54,10 +54,10 @@ class CpuSlabBackend:
         self.window = None
         if len(self.local) == 0:
             inf = float("inf")
-            return 0.0, [inf] * 3, [-inf] * 3, 0, -inf
+            return 0.0, [inf] * 3, [-inf] * 3, 0, -inf, 0
         a = self.local["aabb"]
         return (float(self.oracle.longest_axis), a[:, :3].min(axis=0).tolist(), a[:, 3:].max(axis=0).tolist(), 0,
-                float(a[:, 0].max()))
+                float(a[:, 0].max()), len(self.local))
 
     def set_global_bounds(self, longest, wmin, wmax, status):
         self.cell = np.float32(longest)

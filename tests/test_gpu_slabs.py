@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, cfg, n, frames, out_dir, ownership):
+def _worker(rank, world, port, cfg, n, frames, out_dir, ownership, push):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -38,6 +38,8 @@ def _worker(rank, world, port, cfg, n, frames, out_dir, ownership):
     with G.CollisionContext(s.n, device=dev) as ctx:
         ctx.upload_colliders(s.entity[mine], s.kind[mine], s.offset[mine], s.size[mine], global_index=mine.astype(np.uint32))
         drv = slabs.SlabDriver(slabs.GpuSlabBackend(ctx, dev, host_staging=True))
+        if push:
+            drv.enable_peer_push()   # CUDA IPC: ghosts written straight into the other rank's arrays
         for f in frames:
             pos, quat = s.frame(f)
             ctx.update_transforms(pos[mine], quat[mine], s.scale[mine])
@@ -49,14 +51,15 @@ def _worker(rank, world, port, cfg, n, frames, out_dir, ownership):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("cfg,n,ownership", [(4, 60000, "slabs"), (3, 30000, "slabs"), (2, 30000, "scattered")])
-def test_two_ranks_report_the_single_context_pair_set(tmp_path, cfg, n, ownership):
+@pytest.mark.parametrize("cfg,n,ownership,push", [(4, 60000, "slabs", False), (3, 30000, "slabs", False), (2, 30000, "scattered", False),
+                                                  (4, 60000, "slabs", True), (3, 30000, "scattered", True)])
+def test_two_ranks_report_the_single_context_pair_set(tmp_path, cfg, n, ownership, push):
     import torch.multiprocessing as mp
     import oracle_lib as O
     from gunship_rs_b200 import scenes
     frames = (0, 2)
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), cfg, n, frames, str(tmp_path), ownership), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), cfg, n, frames, str(tmp_path), ownership, push), nprocs=world, join=True)
     s = scenes.by_config(cfg, n)
     oracle = O.OracleSystem()
     for f in frames:
@@ -67,7 +70,7 @@ def test_two_ranks_report_the_single_context_pair_set(tmp_path, cfg, n, ownershi
         assert len(got) == len(want) and np.array_equal(got, want)         # union == oracle, no duplicates
         assert all(len(p) > 0 for p in parts)
         halo = [np.load(tmp_path / f"halo_{ownership}_{f}_{r}.npy") for r in range(world)]
-        if ownership == "slabs":
+        if ownership == "slabs" and not push:
             # the halo flows in +x: rank 1 receives the boundary layer (two cell columns), rank 0 only the
             # foreign volumes of the one cell column the cut runs through
             assert 0 < halo[1][0] < 0.35 * halo[1][2] and halo[0][0] < halo[1][0]
