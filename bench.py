@@ -154,6 +154,27 @@ def run_reference(args, scene, frames):
     return scene.n * len(times) / total, 1e3 * total / len(times), cores
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line on the real stdout (libraries such as NCCL print banners to fd 1: everything else this
+    process writes there is diverted to stderr by guard_stdout)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
+def guard_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -166,6 +187,7 @@ def main():
     ap.add_argument("--cpu-sample-n", type=int, default=0, help="collider count of the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    guard_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -190,7 +212,7 @@ def main():
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                                  "sample": f"{args.steps} steps over {n_ref} colliders (same generator, density and mix)"},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -202,7 +224,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         from gunship_rs_b200 import slabs
         return slabs.bench_multi_gpu(args, n, rank, world, local_rank, METRIC, UNIT, workload_name, measured_peak_gbs,
-                                     ClockSampler, stage_bytes)
+                                     ClockSampler, stage_bytes, emit)
 
     from gunship_rs_b200 import context as G
     scene = make_scene(args.config, n)
@@ -332,7 +354,7 @@ def main():
         line["cpu_baseline"] = {"value": n_cpu / best, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"3 steps (first discarded) over {n_cpu} colliders of the same generator",
                                 "ms_per_step": 1e3 * best}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 

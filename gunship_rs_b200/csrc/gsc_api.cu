@@ -63,6 +63,7 @@ struct gsc_ctx {
     uint2 *d_pairs_sorted = nullptr;
     FrameBlock *d_fb = nullptr;
     FrameBlock *h_fb = nullptr;  // pinned
+    uint32_t *h_enc = nullptr;   // pinned staging of gsc_set_global_bounds
     uint32_t *d_lookback = nullptr;
     uint32_t lookback_tiles = 0;
     // halo staging
@@ -234,6 +235,7 @@ int gsc_create(const gsc_config *cfg, gsc_ctx **out)
     CR(dmalloc(&c->d_lookback, (size_t)kMaxPasses * c->lookback_tiles * kRadix));
     CR(dmalloc(&c->d_halo_count, 1));
     CR(cudaHostAlloc((void **)&c->h_fb, sizeof(FrameBlock), cudaHostAllocDefault));
+    CR(cudaHostAlloc((void **)&c->h_enc, 8 * sizeof(uint32_t), cudaHostAllocDefault));
     for (auto &ev : c->ev) CR(cudaEventCreate(&ev));
     CR(cudaEventCreate(&c->ev_begin));
     CR(cudaEventCreate(&c->ev_end));
@@ -267,6 +269,7 @@ void gsc_destroy(gsc_ctx *c)
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (c->h_fb) cudaFreeHost(c->h_fb);
+    if (c->h_enc) cudaFreeHost(c->h_enc);
     for (auto &ev : c->ev)
         if (ev) cudaEventDestroy(ev);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
@@ -478,18 +481,18 @@ int gsc_set_global_bounds(gsc_ctx *c, const gsc_bounds *g)
 {
     if (int rc = check_ctx(c)) return rc;
     if (!g || !c->bounds_done) return fail(c, GSC_ERR_INVALID, "gsc_set_global_bounds: call gsc_phase_bounds first");
-    uint32_t enc[7] = { 0 };
+    uint32_t *enc = c->h_enc;  // pinned, owned by the context: no sync needed before returning
     enc[0] = host_f2ord(g->longest_axis);
     for (int a = 0; a < 3; ++a) {
         enc[1 + a] = ~host_f2ord(g->world_min[a]);
         enc[4 + a] = host_f2ord(g->world_max[a]);
     }
-    CU(c, cudaMemcpyAsync(c->d_fb, enc, sizeof enc, cudaMemcpyHostToDevice, c->stream));
-    if (g->status_flags) CU(c, cudaMemcpyAsync(&c->d_fb->status, &g->status_flags, 4, cudaMemcpyHostToDevice, c->stream));
-    // place the (global) grid now: gsc_local_x_range / gsc_halo_select need the cell size
+    enc[7] = g->status_flags;
+    CU(c, cudaMemcpyAsync(c->d_fb, enc, 7 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    if (g->status_flags) CU(c, cudaMemcpyAsync(&c->d_fb->status, enc + 7, 4, cudaMemcpyHostToDevice, c->stream));
+    // place the (global) grid now: gsc_local_x_range / gsc_halo_select / gsc_halo_push need the cell size
     k_grid_setup<<<1, 32, 0, c->stream>>>(c->d_fb, c->max_cells, c->cap, 0, 0, 0);
     CU(c, cudaGetLastError());
-    CU(c, cudaStreamSynchronize(c->stream));  // enc lives on this stack frame
     c->global_bounds_set = true;
     return GSC_OK;
 }

@@ -943,43 +943,65 @@ k_halo_select(uint32_t n_local, const float4 *__restrict__ rec, const float4 *__
 
 // Fused select + transfer over peer memory (NVLink / NVSwitch): the local volumes whose home x-cell lies in
 // [x_lo, x_hi] are written straight into the PEER context's record arrays behind its local volumes, as ghosts
-// with their new local index; the slot comes from a system-scope atomic on the peer's FrameBlock, one per warp.
+// with their new local index.  Each CTA first collects the indices it selects in shared memory, then reserves
+// its slice of the peer's ghost region with ONE system-scope atomic on the peer's FrameBlock (remote atomics
+// cost microseconds: one per warp made this kernel 5x slower), then streams the records across.
 // No staging buffer, no count exchange, no append kernel on the receiving side.
-__global__ void __launch_bounds__(256)
+constexpr int kPushThreads = 256;
+constexpr int kPushList = 3072;  // selected indices staged per CTA and round
+
+__global__ void __launch_bounds__(kPushThreads)
 k_halo_push(uint32_t n_local, const float4 *__restrict__ rec, const float4 *__restrict__ obb, int x_lo, int x_hi,
             float4 *__restrict__ peer_rec, float4 *__restrict__ peer_obb, FrameBlock *peer_fb, uint32_t peer_first,
             uint32_t peer_cap, const FrameBlock *__restrict__ fb)
 {
+    __shared__ uint32_t s_list[kPushList];
+    __shared__ uint32_t s_count, s_base;
     const GridParams g = fb->grid;
     if (!g.valid) return;
     const int lane = threadIdx.x & 31;
-    const uint32_t n_round = (n_local + 31u) & ~31u;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
-        bool sel = false;
-        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-        if (i < n_local) {
-            r0 = __ldg(rec + 2 * (size_t)i);
-            r1 = __ldg(rec + 2 * (size_t)i + 1);
-            const Volume v = volume_decode(r0, r1);
-            const int x = (int)cell_coord_f(v.mn[0], g.cell_size);
-            sel = x >= x_lo && x <= x_hi;
+    // contiguous share of the records per CTA, walked in rounds that cannot overflow the list
+    const uint32_t per_cta = (n_local + gridDim.x - 1) / gridDim.x;
+    const uint32_t begin = min(n_local, blockIdx.x * per_cta), end = min(n_local, begin + per_cta);
+    for (uint32_t r0 = begin; r0 < end; r0 += kPushList) {
+        const uint32_t r1 = min(end, r0 + (uint32_t)kPushList);
+        if (threadIdx.x == 0) s_count = 0;
+        __syncthreads();
+        for (uint32_t i = r0 + threadIdx.x; i < ((r1 - r0 + 31u) & ~31u) + r0; i += kPushThreads) {
+            bool sel = false;
+            if (i < r1) {
+                const Volume v = volume_decode(__ldg(rec + 2 * (size_t)i), __ldg(rec + 2 * (size_t)i + 1));
+                const int x = (int)cell_coord_f(v.mn[0], g.cell_size);
+                sel = x >= x_lo && x <= x_hi;
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, sel);
+            if (m == 0) continue;
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&s_count, (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (sel) s_list[base + __popc(m & ((1u << lane) - 1u))] = i;
         }
-        const uint32_t m = __ballot_sync(0xffffffffu, sel);
-        if (m == 0) continue;
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd_system(&peer_fb->n_ghost_in, (uint32_t)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        const uint32_t at = peer_first + base + __popc(m & ((1u << lane) - 1u));
-        if (sel && at < peer_cap) {
-            const uint32_t box = __float_as_uint(r1.w) & kMetaBox;
-            r1.w = __uint_as_float((at << 4) | box | kMetaGhost);
-            peer_rec[2 * (size_t)at] = r0;
-            peer_rec[2 * (size_t)at + 1] = r1;
+        __syncthreads();
+        const uint32_t cnt = s_count;
+        if (cnt == 0) continue;  // uniform
+        if (threadIdx.x == 0) s_base = atomicAdd_system(&peer_fb->n_ghost_in, cnt);
+        __syncthreads();
+        const uint32_t first = peer_first + s_base;
+        for (uint32_t k = threadIdx.x; k < cnt; k += kPushThreads) {
+            const uint32_t i = s_list[k], at = first + k;
+            if (at >= peer_cap) continue;
+            const float4 r0v = __ldg(rec + 2 * (size_t)i);
+            float4 r1v = __ldg(rec + 2 * (size_t)i + 1);
+            const uint32_t box = __float_as_uint(r1v.w) & kMetaBox;
+            r1v.w = __uint_as_float((at << 4) | box | kMetaGhost);
+            peer_rec[2 * (size_t)at] = r0v;
+            peer_rec[2 * (size_t)at + 1] = r1v;
             if (box) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) peer_obb[4 * (size_t)at + k] = __ldg(obb + 4 * (size_t)i + k);
+                for (int q = 0; q < 4; ++q) peer_obb[4 * (size_t)at + q] = __ldg(obb + 4 * (size_t)i + q);
             }
         }
+        __syncthreads();
     }
 }
 

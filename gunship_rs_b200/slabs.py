@@ -21,6 +21,7 @@ The device work is behind a small backend interface so the same driver runs on t
 from __future__ import annotations
 
 import os
+import sys
 import time
 
 import numpy as np
@@ -51,6 +52,49 @@ def needed_range(x_min: int, x_max: int):
     return x_min - 1, x_max
 
 
+class ShmControl:
+    """Host-side all-gather / barrier between the ranks of ONE box over a shared-memory file (/dev/shm).
+
+    The per-step control data is ten numbers per rank and is already on the host when it is needed
+    (gsc_phase_bounds returns it), so routing it through a device collective would cost two extra copies and a
+    kernel launch per step; a cache-line spin on shared memory costs a few microseconds.  Two banks alternate
+    so that a fast rank can never overwrite a row a slow rank has not read yet (to finish gather k+1 every rank
+    must have published k+1, i.e. finished reading k)."""
+
+    SLOTS = 16
+
+    def __init__(self, dist, group, rank, world):
+        import uuid
+        self.rank, self.world, self.seq = rank, world, 0
+        box = [f"/dev/shm/gsc_ctl_{uuid.uuid4().hex}" if rank == 0 else None]
+        shape = (2, world, self.SLOTS + 1)
+        if rank == 0:
+            self.mem = np.memmap(box[0], dtype=np.float64, mode="w+", shape=shape)
+            self.mem[:] = 0.0
+            self.mem.flush()
+        dist.broadcast_object_list(box, src=0 if group is None else dist.get_global_rank(group, 0), group=group)
+        if rank != 0:
+            self.mem = np.memmap(box[0], dtype=np.float64, mode="r+", shape=shape)
+        dist.barrier(group=group)
+        if rank == 0:
+            os.unlink(box[0])  # stays alive while mapped; nothing is left behind
+
+    def all_gather(self, values):
+        self.seq += 1
+        bank = self.mem[self.seq & 1]
+        n = len(values)
+        if n:
+            bank[self.rank, 1:1 + n] = values
+        bank[self.rank, 0] = self.seq          # publish after the payload (x86 store order)
+        seqs = bank[:, 0]
+        while (seqs < self.seq).any():
+            pass
+        return np.array(bank[:, 1:1 + n])
+
+    def barrier(self):
+        self.all_gather(())
+
+
 class SlabDriver:
     """One collision step across `world` ranks.  `backend` does the device work of this rank:
 
@@ -74,6 +118,8 @@ class SlabDriver:
         self.last_halo_in = 0
         self.last_halo_out = 0
         self.push = False
+        self.shm = None
+        self.trace = {} if os.environ.get("GSC_SLAB_TRACE") else None  # host seconds per phase, summed over steps
 
     def enable_peer_push(self):
         """GPUs of one box: open every other rank's record arrays over CUDA IPC so that the halo is written
@@ -89,19 +135,33 @@ class SlabDriver:
             if s_ != self.rank:
                 be.ipc_open_peer(s_, bytes(b.cpu().numpy().tobytes()))
         self.push = True
+        if os.environ.get("GSC_CONTROL", "shm") == "shm":
+            self.shm = ShmControl(dist, self.group, self.rank, self.world)  # same box: host control plane
+
+    def _t(self, name, t0):
+        if self.trace is not None:
+            self.trace[name] = self.trace.get(name, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
 
     def step(self):
         import torch
         dist, be = self.dist, self.backend
         dev = be.tensor_device
+        t0 = time.perf_counter()
         longest, wmin, wmax, status, home_x_max, n_local = be.phase_bounds()
+        t0 = self._t("phase_bounds", t0)
         # ONE all-gather carries everything the ranks must agree on: the global cell size (max longest axis) and
         # world box (they place the grid), and every rank's home x-range in world units
         # (f64 carries the f32 values exactly, and the collider counts the peer push needs)
-        mine = torch.tensor([longest, *wmin, *wmax, home_x_max, float(status), float(n_local)], dtype=torch.float64, device=dev)
-        allb = [torch.zeros(10, dtype=torch.float64, device=dev) for _ in range(self.world)]
-        dist.all_gather(allb, mine, group=self.group)
-        allb = torch.stack(allb).cpu().numpy()                       # [world, 10]
+        mine = [longest, *wmin, *wmax, home_x_max, float(status), float(n_local)]
+        if self.shm is not None:
+            allb = self.shm.all_gather(mine)                             # [world, 10]
+        else:
+            t = torch.tensor(mine, dtype=torch.float64, device=dev)
+            allb = [torch.zeros(10, dtype=torch.float64, device=dev) for _ in range(self.world)]
+            dist.all_gather(allb, t, group=self.group)
+            allb = torch.stack(allb).cpu().numpy()
+        t0 = self._t("bounds_all_gather", t0)
         peer_n_local = allb[:, 9].astype(np.int64)
         allb = allb.astype(np.float32)
         cell = np.float32(allb[:, 0].max())
@@ -121,6 +181,7 @@ class SlabDriver:
         if x_min <= x_max:
             be.set_x_window(*needed_range(x_min, x_max))
 
+        t0 = self._t("host_ranges_set_bounds", t0)
         if self.push:
             # fused select + transfer: my volumes in rank s's needed range go straight into its arrays
             pushed_to = 0
@@ -133,11 +194,20 @@ class SlabDriver:
                     if lo <= hi:
                         be.halo_push(s, lo, hi, int(peer_n_local[s]))
                         pushed_to += 1
+            t0 = self._t("push_launch", t0)
             be.halo_sync()                       # my pushes have landed ...
-            dist.barrier(group=self.group)       # ... and so have everyone else's
+            t0 = self._t("push_sync", t0)
+            if self.shm is not None:             # ... and so have everyone else's
+                self.shm.barrier()
+            else:
+                dist.barrier(group=self.group)
+            t0 = self._t("barrier", t0)
             self.last_halo_in = be.halo_commit()
             self.last_halo_out = pushed_to
-            return be.phase_finish()
+            t0 = self._t("commit", t0)
+            out = be.phase_finish()
+            self._t("phase_finish", t0)
+            return out
 
         # what each other rank needs from me
         send = {}
@@ -273,9 +343,7 @@ class GpuSlabBackend:
 # ------------------------------------------------------------------------------------------------------
 
 def bench_multi_gpu(args, n, rank, world, local_rank, metric, unit, workload_name, measured_peak_gbs, ClockSampler,
-                    stage_bytes):
-    import json
-
+                    stage_bytes, emit):
     import torch
     import torch.distributed as dist
 
@@ -406,7 +474,10 @@ def bench_multi_gpu(args, n, rank, world, local_rank, metric, unit, workload_nam
                          "note": "per-rank launch: mean bytes per rank over the slowest rank's stage time"},
             "stages": {N.STAGE_NAMES[i]: {"ms_max_over_ranks": round(float(stage_ms[i]), 4)} for i in range(6)},
         }
-        print(json.dumps(line))
+        emit(line)
+    if driver.trace is not None and rank == 0:
+        total_steps = 2 * (args.warmup + args.steps)
+        print("slab trace (us/step, rank 0):", {k: round(1e6 * v / total_steps, 1) for k, v in driver.trace.items()}, file=sys.stderr)
     ctx.close()
     dist.barrier()
     dist.destroy_process_group()
