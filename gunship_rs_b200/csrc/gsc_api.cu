@@ -491,7 +491,7 @@ int gsc_set_global_bounds(gsc_ctx *c, const gsc_bounds *g)
     CU(c, cudaMemcpyAsync(c->d_fb, enc, 7 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     if (g->status_flags) CU(c, cudaMemcpyAsync(&c->d_fb->status, enc + 7, 4, cudaMemcpyHostToDevice, c->stream));
     // place the (global) grid now: gsc_local_x_range / gsc_halo_select / gsc_halo_push need the cell size
-    k_grid_setup<<<1, 32, 0, c->stream>>>(c->d_fb, c->max_cells, c->cap, 0, 0, 0);
+    k_grid_setup<<<1, 32, 0, c->stream>>>(c->d_fb, ~0ull, c->cap, 0, 0, 0);
     CU(c, cudaGetLastError());
     c->global_bounds_set = true;
     return GSC_OK;

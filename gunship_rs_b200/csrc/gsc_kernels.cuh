@@ -292,7 +292,11 @@ __global__ void k_grid_setup(FrameBlock *fb, unsigned long long max_cells, uint3
             cells *= (unsigned long long)g.dims[a];
         }
         if (st == 0) {
-            if (cells > max_cells || cells >= (1ull << 31)) st |= kStCells;
+            if (max_cells == ~0ull) {
+                // probe (gsc_set_global_bounds): only the cell size / quantisation are needed yet; the real
+                // table is sized when the slab window is known
+                g.valid = 1;
+            } else if (cells > max_cells || cells >= (1ull << 31)) st |= kStCells;
             else {
                 g.num_cells = (uint32_t)cells;
                 g.valid = 1;
