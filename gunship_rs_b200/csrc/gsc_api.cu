@@ -64,8 +64,7 @@ struct gsc_ctx {
     FrameBlock *d_fb = nullptr;
     FrameBlock *h_fb = nullptr;  // pinned
     uint32_t *h_enc = nullptr;   // pinned staging of gsc_set_global_bounds
-    uint32_t *d_lookback = nullptr;
-    uint32_t lookback_tiles = 0;
+    uint32_t *d_sort_scratch = nullptr;
     // halo staging
     float4 *d_halo_rec = nullptr, *d_halo_obb = nullptr;
     uint32_t *d_halo_count = nullptr;
@@ -134,19 +133,24 @@ __global__ void k_decode_aabb(uint32_t n, const float4 *rec, float *out6)
 inline uint32_t tiles_for(uint32_t n) { return (n + kSortTile - 1) / kSortTile; }
 
 // Runs the radix passes on `n` (key, value) pairs.  Passes beyond ctl->num_passes exit on the device.
+// scratch = [kRadix * tiles] tile histogram + [kRadix] digit totals
 void launch_sort(cudaStream_t s, uint32_t n, uint32_t *keys[2], uint32_t *vals[2], bool first_vals_identity,
-                 int max_passes, const SortControl *ctl, const uint32_t *hist, uint32_t *lookback,
-                 uint32_t *tile_counter)
+                 int max_passes, const SortControl *ctl, uint32_t *scratch)
 {
     const uint32_t tiles = tiles_for(n);
     if (tiles == 0) return;
+    uint32_t *tile_hist = scratch, *digit_total = scratch + (size_t)kRadix * tiles;
     for (int pass = 0; pass < max_passes; ++pass) {
         const int in = pass & 1, out = in ^ 1;
         const uint32_t *vin = (pass == 0 && first_vals_identity) ? nullptr : vals[in];
-        k_onesweep_pass<<<tiles, kSortThreads, 0, s>>>(keys[in], vin, keys[out], vals[out], n, pass, ctl, hist, lookback,
-                                                      tile_counter, tiles);
+        k_radix_upsweep<<<tiles, kSortThreads, 0, s>>>(keys[in], n, pass, ctl, tile_hist, tiles);
+        k_radix_scan<<<kRadix, 256, 0, s>>>(tile_hist, tiles, pass, ctl, digit_total);
+        k_radix_downsweep<<<tiles, kSortThreads, 0, s>>>(keys[in], vin, keys[out], vals[out], n, pass, ctl, tile_hist,
+                                                        digit_total, tiles);
     }
 }
+
+inline size_t sort_scratch_words(uint32_t n) { return (size_t)kRadix * tiles_for(n) + kRadix; }
 
 int check_ctx(gsc_ctx *c)
 {
@@ -195,7 +199,6 @@ int gsc_create(const gsc_config *cfg, gsc_ctx **out)
     c->max_cells = cfg->max_cells ? cfg->max_cells : 16ull * c->cap + (1ull << 20);
     c->max_cells = std::min<uint64_t>(c->max_cells, (1ull << 31) - 2);
     const size_t M = c->cap;
-    c->lookback_tiles = tiles_for(c->cap);
 #define CR(expr)                                                                                     \
     do {                                                                                             \
         cudaError_t e2_ = (expr);                                                                    \
@@ -232,7 +235,7 @@ int gsc_create(const gsc_config *cfg, gsc_ctx **out)
     CR(dmalloc(&c->d_cand_so, c->max_cands));
     CR(dmalloc(&c->d_cand_oo, c->max_cands));
     CR(dmalloc(&c->d_fb, 1));
-    CR(dmalloc(&c->d_lookback, (size_t)kMaxPasses * c->lookback_tiles * kRadix));
+    CR(dmalloc(&c->d_sort_scratch, sort_scratch_words(c->cap)));
     CR(dmalloc(&c->d_halo_count, 1));
     CR(cudaHostAlloc((void **)&c->h_fb, sizeof(FrameBlock), cudaHostAllocDefault));
     CR(cudaHostAlloc((void **)&c->h_enc, 8 * sizeof(uint32_t), cudaHostAllocDefault));
@@ -264,7 +267,7 @@ void gsc_destroy(gsc_ctx *c)
         }
     void *bufs[] = { c->d_entity, c->d_gidx, c->d_kind, c->d_offset, c->d_size, c->d_pos, c->d_quat, c->d_scale, c->d_rec,
                      c->d_rec_sorted, c->d_qrec_sorted, c->d_obb, c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1], c->d_cell_start,
-                     c->d_wide, c->d_gaps, c->d_pairs, c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->d_pairs_sorted, c->d_fb, c->d_lookback,
+                     c->d_wide, c->d_gaps, c->d_pairs, c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->d_pairs_sorted, c->d_fb, c->d_sort_scratch,
                      c->d_halo_rec, c->d_halo_obb, c->d_halo_count };
     for (void *b : bufs)
         if (b) cudaFree(b);
@@ -369,14 +372,12 @@ static int stage_finish(gsc_ctx *c, gsc_step_out *out)
     const bool timing = c->cfg.flags & GSC_FLAG_TIMING;
     const uint32_t n_total = c->n_local + c->n_ghost;
     FrameBlock *fb = c->d_fb;
-    CU(c, cudaMemsetAsync(c->d_lookback, 0, (size_t)kMaxPasses * tiles_for(n_total) * kRadix * sizeof(uint32_t), s));
     k_grid_setup<<<1, 32, 0, s>>>(fb, c->max_cells, n_total, c->have_window ? 1 : 0, c->win_lo, c->win_hi);
     if (n_total) {
         const uint32_t kb = std::min<uint32_t>((n_total + kKeyThreads - 1) / kKeyThreads, kGridStrideBlocks);
         k_cell_keys<<<kb, kKeyThreads, 0, s>>>(n_total, c->d_rec, c->d_keys[0], c->d_wide, fb);
         if (timing) CU(c, cudaEventRecord(c->ev[2], s));
-        launch_sort(s, n_total, c->d_keys, c->d_vals, true, kMaxPasses, &fb->sort, &fb->hist[0][0], c->d_lookback,
-                    fb->tile_counter);
+        launch_sort(s, n_total, c->d_keys, c->d_vals, true, kMaxPasses, &fb->sort, c->d_sort_scratch);
         if (timing) CU(c, cudaEventRecord(c->ev[3], s));
         const uint32_t tb = (n_total + 1 + kTableThreads - 1) / kTableThreads;
         SortedVolumes sv{ c->d_rec_sorted, c->d_qrec_sorted };
@@ -688,18 +689,13 @@ int sort_standalone(gsc_ctx *c, cudaStream_t s, uint32_t n, uint32_t *keys[2], u
     *which = passes & 1;
     if (n == 0 || passes == 0) { *which = 0; return GSC_OK; }
     const uint32_t tiles = tiles_for(n);
-    uint32_t *scratch = nullptr;  // [hist 4*256][tile_counter 4][ctl 1][pad 3][lookback 4*tiles*256]
-    const size_t words = (size_t)kMaxPasses * kRadix + 8 + (size_t)kMaxPasses * tiles * kRadix;
+    uint32_t *scratch = nullptr;  // [ctl 4 words][tile histogram + digit totals]
+    const size_t words = 4 + sort_scratch_words(n);
     CU(c, cudaMalloc((void **)&scratch, words * 4));
-    CU(c, cudaMemsetAsync(scratch, 0, words * 4, s));
-    uint32_t *hist = scratch, *tile_counter = scratch + kMaxPasses * kRadix;
-    SortControl *ctl = reinterpret_cast<SortControl *>(tile_counter + 4);
-    uint32_t *lookback = tile_counter + 8;
-    SortControl h{ passes };
+    SortControl *ctl = reinterpret_cast<SortControl *>(scratch);
+    SortControl h{ passes, key_bits };
     CU(c, cudaMemcpyAsync(ctl, &h, sizeof h, cudaMemcpyHostToDevice, s));
-    const uint32_t hb = std::min<uint32_t>((n + 255) / 256, kGridStrideBlocks);
-    k_radix_histogram<<<hb, 256, 0, s>>>(keys[0], n, passes, hist);
-    launch_sort(s, n, keys, vals, identity, passes, ctl, hist, lookback, tile_counter);
+    launch_sort(s, n, keys, vals, identity, passes, ctl, scratch + 4);
     CU(c, cudaGetLastError());
     CU(c, cudaStreamSynchronize(s));
     cudaFree(scratch);

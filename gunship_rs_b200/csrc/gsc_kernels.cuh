@@ -4,7 +4,7 @@
 //   bvh_update (bounding_volume.rs:345-409)                      -> k_bvh_update
 //   longest_axis / cell size, grid extent                        -> k_grid_setup
 //   WorkUnit::world_to_grid (grid_collision.rs:329-335)          -> k_cell_keys (+ digit histograms)
-//   HashMap<GridCell, Vec<..>> grouping (grid_collision.rs:434)  -> k_onesweep_pass (gsc_sort.cuh)
+//   HashMap<GridCell, Vec<..>> grouping (grid_collision.rs:434)  -> k_radix_upsweep/scan/downsweep (gsc_sort.cuh)
 //   cell lookup                                                  -> k_cell_table_permute
 //   test_cell candidate generation + HashMap dedupe (:439-441,
 //   :497-511) + BoundVolume::test (bounding_volume.rs:124-132)   -> k_pairs, k_narrow_sphere_obb,
@@ -85,13 +85,11 @@ struct FrameBlock {
     uint32_t status;
     uint32_t n_wide;
     unsigned long long n_pairs, n_ss, n_so, n_oo;
-    uint32_t tile_counter[kMaxPasses];
     uint32_t xrange[2];  // ~(min home x + 32768), (max home x + 32768) of local volumes
     uint32_t n_gaps;      // long empty key gaps queued for k_fill_gaps
     uint32_t n_ghost_in;  // ghosts written into this context by peer GPUs this step (k_halo_push, system-scope atomic)
     GridParams grid;
     SortControl sort;
-    uint32_t hist[kMaxPasses][kRadix];
 };
 
 // ---- block-aggregated stream compaction ------------------------------------------------------
@@ -264,6 +262,7 @@ __global__ void k_grid_setup(FrameBlock *fb, unsigned long long max_cells, uint3
     g.cell_size = ord2f(fb->bounds[0]);
     for (int a = 0; a < 3; ++a) { g.origin[a] = 0; g.dims[a] = 0; g.qorg[a] = 0.0f; g.qscale[a] = 0.0f; }
     fb->sort.num_passes = 0;
+    fb->sort.key_bits = 0;
     uint32_t st = 0;
     if (n_total == 0 || fb->bounds[0] == 0) {  // nothing to do (no colliders): valid stays 0, not an error
         fb->grid = g;
@@ -303,6 +302,7 @@ __global__ void k_grid_setup(FrameBlock *fb, unsigned long long max_cells, uint3
                 int bits = 0;
                 while ((1ull << bits) <= cells) ++bits;  // keys take values 0..cells (cells == wide)
                 fb->sort.num_passes = radix_passes(bits);
+                fb->sort.key_bits = bits;
             }
         }
     }
@@ -322,7 +322,7 @@ GSC_DEV bool home_cell(const Volume &v, const GridParams &g, int c_mn[3], int c_
     return wide;
 }
 
-// ---- stage 1: cell keys + digit histograms of every radix pass ------------------------------------
+// ---- stage 1: cell keys -----------------------------------------------------------------------------
 // key = (x * dims.y + y) * dims.z + z of the home cell: x is the major axis, so x-slabs of the
 // multi-GPU partition are contiguous key ranges and cells of one (x,y) row are contiguous in z.
 constexpr int kKeyThreads = 256;
@@ -331,12 +331,8 @@ __global__ void __launch_bounds__(kKeyThreads)
 k_cell_keys(uint32_t n_total, const float4 *__restrict__ rec, uint32_t *__restrict__ keys,
             uint32_t *__restrict__ wide_list, FrameBlock *__restrict__ fb)
 {
-    __shared__ uint32_t s_hist[kMaxPasses][kRadix];
     const GridParams g = fb->grid;
     if (!g.valid) return;
-    const int passes = fb->sort.num_passes;
-    for (int i = threadIdx.x; i < kMaxPasses * kRadix; i += kKeyThreads) (&s_hist[0][0])[i] = 0;
-    __syncthreads();
     for (uint32_t i = blockIdx.x * kKeyThreads + threadIdx.x; i < n_total; i += gridDim.x * kKeyThreads) {
         const Volume v = volume_decode(__ldg(rec + 2 * (size_t)i), __ldg(rec + 2 * (size_t)i + 1));
         int c0[3], c1[3];
@@ -354,12 +350,6 @@ k_cell_keys(uint32_t n_total, const float4 *__restrict__ rec, uint32_t *__restri
             key = ((uint32_t)c0[0] * (uint32_t)g.dims[1] + (uint32_t)c0[1]) * (uint32_t)g.dims[2] + (uint32_t)c0[2];
         }
         keys[i] = key;
-        for (int p = 0; p < passes; ++p) atomicAdd(&s_hist[p][(key >> (8 * p)) & 255u], 1u);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < passes * kRadix; i += kKeyThreads) {
-        const uint32_t c = (&s_hist[0][0])[i];
-        if (c) atomicAdd(&fb->hist[0][0] + i, c);
     }
 }
 

@@ -3,17 +3,12 @@
 // Replaces the reference's per-thread `HashMap<GridCell, Vec<*const BoundVolume>>` grouping
 // (grid_collision.rs:107, 434-444): colliders are grouped by cell by SORTING (key, index) pairs.
 //
-// One-sweep design, 8-bit digits: every pass reads each (key, value) once and writes it once.
-//   * digit histograms of ALL passes are accumulated by the producer of the keys (k_cell_keys) or by
-//     k_radix_histogram, so a pass needs no counting sweep of its own;
-//   * a pass kernel takes a tile of THREADS*IPT items per CTA, ranks them with warp-level
-//     __match_any_sync multisplit (stable), publishes its per-digit tile counts and resolves the
-//     exclusive prefix over earlier tiles with decoupled look-back (flag bits in the same word as the
-//     count, so no fences), stages the tile digit-sorted in shared memory and writes each digit run
-//     contiguously;
-//   * tile ids come from an atomic ticket, so a tile's predecessors are always resident or done.
-// HBM bytes per pass: 16 B per pair (8 read + 8 written); the first pass synthesises the index and
-// reads only 4 B.
+// LSD, 8-bit digits, three kernels per pass (upsweep / scan / downsweep, see below):
+//   * the downsweep takes a tile of THREADS*IPT items per CTA, ranks them with warp-level
+//     __match_any_sync multisplit (stable), adds the scanned tile/digit offsets, stages the tile
+//     digit-sorted in shared memory and writes each digit run contiguously.
+// HBM bytes per pass: 20 B per pair (4 upsweep + 8 read + 8 written); the first pass synthesises the
+// index and reads only 4 + 4 B.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,10 +22,6 @@ constexpr int kSortThreads = 256;
 constexpr int kSortIpt = 16;
 constexpr int kSortTile = kSortThreads * kSortIpt;
 
-constexpr uint32_t kLbAgg = 1u << 30;   // tile aggregate available
-constexpr uint32_t kLbIncl = 1u << 31;  // inclusive prefix available
-constexpr uint32_t kLbMask = (1u << 30) - 1;
-
 // number of 8-bit passes for keys < 2^key_bits
 __host__ __device__ inline int radix_passes(int key_bits) { return key_bits <= 0 ? 0 : (key_bits + kRadixBits - 1) / kRadixBits; }
 
@@ -38,6 +29,7 @@ __host__ __device__ inline int radix_passes(int key_bits) { return key_bits <= 0
 // so that the number of passes (a function of the data-dependent grid size) needs no host round trip.
 struct SortControl {
     int num_passes;
+    int key_bits;  // significant key bits: the last pass ranks on fewer than 8
 };
 
 // exclusive scan of one value per thread over the first 256 threads of a CTA (all threads call)
@@ -64,57 +56,118 @@ __device__ __forceinline__ uint32_t block_excl_scan256(uint32_t v, uint32_t *s_w
     return base + inc - v;
 }
 
-// Standalone histogram of all passes (used when the keys were not produced by k_cell_keys).
-__global__ void __launch_bounds__(256) k_radix_histogram(const uint32_t *__restrict__ keys, uint32_t n, int passes,
-                                                         uint32_t *__restrict__ hist /*[kMaxPasses][256]*/)
+// ---- one radix pass = upsweep (per-tile digit counts) -> scan (over tiles, per digit) -> downsweep ----
+// A decoupled look-back ("onesweep") pass was measured first: on B200 the sort is instruction-issue bound, not
+// bandwidth bound (44 GB/s of HBM per SM), and the look-back's polling loops were half of all issued
+// instructions.  The extra 4 B/item read of the upsweep costs ~12 us per pass at 16M; the polling cost 70.
+//   tile_hist[d * num_tiles + t] : count of digit d in tile t, then its exclusive prefix over tiles
+//   digit_total[d]               : count of digit d in the whole array
+//   ctl->num_passes is data dependent: passes beyond it exit at once and the ping-pong simply stops.
+
+__global__ void __launch_bounds__(kSortThreads)
+k_radix_upsweep(const uint32_t *__restrict__ keys_in, uint32_t n, int pass, const SortControl *__restrict__ ctl,
+                uint32_t *__restrict__ tile_hist, uint32_t num_tiles)
 {
-    __shared__ uint32_t s_hist[kMaxPasses][kRadix];
-    for (int i = threadIdx.x; i < kMaxPasses * kRadix; i += blockDim.x) (&s_hist[0][0])[i] = 0;
+    constexpr int WARPS = kSortThreads / 32;
+    __shared__ uint32_t s_hist[WARPS][kRadix];
+    if (pass >= ctl->num_passes) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int shift = pass * kRadixBits;
+#pragma unroll
+    for (int i = 0; i < WARPS * kRadix / (4 * kSortThreads); ++i)
+        reinterpret_cast<uint4 *>(&s_hist[0][0])[tid + i * kSortThreads] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t k = keys[i];
-        for (int p = 0; p < passes; ++p) atomicAdd(&s_hist[p][(k >> (8 * p)) & 255u], 1u);
+    const uint32_t tile = blockIdx.x, tile_base = tile * (uint32_t)kSortTile;
+    const uint32_t warp_base = tile_base + warp * (32 * kSortIpt) + lane;
+    uint32_t key[kSortIpt];
+#pragma unroll
+    for (int j = 0; j < kSortIpt; ++j) {
+        const uint32_t idx = warp_base + j * 32;
+        key[j] = idx < n ? keys_in[idx] : 0xffffffffu;
     }
+    // plain shared atomics on the warp's private counters (MATCH.ANY-based aggregation was measured 5x slower:
+    // the instruction serialises over the distinct values in the warp)
+#pragma unroll
+    for (int j = 0; j < kSortIpt; ++j) atomicAdd(&s_hist[warp][(key[j] >> shift) & 255u], 1u);
     __syncthreads();
-    for (int i = threadIdx.x; i < passes * kRadix; i += blockDim.x) {
-        const uint32_t c = (&s_hist[0][0])[i];
-        if (c) atomicAdd(&hist[i], c);
-    }
+    uint32_t c = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) c += s_hist[w][tid];
+    tile_hist[(size_t)tid * num_tiles + tile] = c;  // (padding of the last tile lands in digit 255 of that tile: harmless)
 }
 
-// One radix pass.  grid = ceil(n / kSortTile) CTAs of kSortThreads threads.
-//   keys_in/vals_in -> keys_out/vals_out; vals_in == nullptr means "value = position" (first pass).
-//   ctl->num_passes is data dependent: passes beyond it exit at once and the ping-pong simply stops.
-// Register budget: 64 (4 CTAs = 32 warps per SM).  Values are loaded only after the keys have been
-// ranked and staged, so keys and values are never live together.
-constexpr int kLookBatch = 8;  // predecessors inspected per look-back round trip (independent loads)
+// grid = kRadix CTAs: CTA d turns the counts of digit d into exclusive prefixes over the tiles.
+// The row is pulled through shared memory so that global accesses are coalesced 16 B per thread.
+constexpr int kScanChunk = 4096;  // tiles per round (16 KB of shared memory)
 
+__global__ void __launch_bounds__(256)
+k_radix_scan(uint32_t *__restrict__ tile_hist, uint32_t num_tiles, int pass, const SortControl *__restrict__ ctl,
+             uint32_t *__restrict__ digit_total)
+{
+    __shared__ uint32_t s_row[kScanChunk];
+    __shared__ uint32_t s_warp[8];
+    if (pass >= ctl->num_passes) return;
+    uint32_t *row = tile_hist + (size_t)blockIdx.x * num_tiles;
+    const int tid = threadIdx.x;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < num_tiles; base += kScanChunk) {
+        const uint32_t cnt = min((uint32_t)kScanChunk, num_tiles - base);
+        for (uint32_t i = tid; i < kScanChunk; i += 256) s_row[i] = i < cnt ? row[base + i] : 0u;
+        __syncthreads();
+        // thread t owns 16 consecutive entries
+        uint32_t v[kScanChunk / 256], sum = 0;
+#pragma unroll
+        for (int k = 0; k < kScanChunk / 256; ++k) {
+            v[k] = s_row[tid * (kScanChunk / 256) + k];
+            sum += v[k];
+        }
+        uint32_t total = 0;
+        uint32_t run = carry + block_excl_scan256(sum, s_warp, &total);
+#pragma unroll
+        for (int k = 0; k < kScanChunk / 256; ++k) {
+            s_row[tid * (kScanChunk / 256) + k] = run;
+            run += v[k];
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < cnt; i += 256) row[base + i] = s_row[i];
+        carry += total;
+        __syncthreads();
+    }
+    if (tid == 0) digit_total[blockIdx.x] = carry;
+}
+
+// grid = num_tiles CTAs of kSortThreads threads, 64 registers (4 CTAs = 32 warps per SM).
+//   keys_in/vals_in -> keys_out/vals_out; vals_in == nullptr means "value = position" (first pass).
+// ncu (round 1): this kernel is bound by the shared-memory / MIO pipe (mio_throttle + short_scoreboard), not by
+// HBM: every shared-memory instruction below is there because it has to be.
 __global__ void __launch_bounds__(kSortThreads, 4)
-k_onesweep_pass(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-                uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n, int pass,
-                const SortControl *__restrict__ ctl, const uint32_t *__restrict__ hist /*[kMaxPasses][256]*/,
-                uint32_t *lookback /*[kMaxPasses][tiles][256]*/, uint32_t *tile_counter /*[kMaxPasses]*/,
-                uint32_t num_tiles)
+k_radix_downsweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                  uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n, int pass,
+                  const SortControl *__restrict__ ctl, const uint32_t *__restrict__ tile_hist,
+                  const uint32_t *__restrict__ digit_total, uint32_t num_tiles)
 {
     constexpr int WARPS = kSortThreads / 32;
     constexpr int WTILE = 32 * kSortIpt;
-    __shared__ uint32_t s_hist[WARPS][kRadix];
+    __shared__ __align__(16) uint32_t s_hist[WARPS][kRadix];  // per-warp digit counts, then offsets within the digit
     __shared__ uint32_t s_keys[kSortTile];
     __shared__ uint32_t s_vals[kSortTile];
-    __shared__ uint32_t s_goff[kRadix];
+    __shared__ uint32_t s_bin[kRadix];   // first tile position of each digit
+    __shared__ uint32_t s_goff[kRadix];  // output position of digit run d minus its tile position
     __shared__ uint32_t s_warp[8];
-    __shared__ uint32_t s_tile;
 
     if (pass >= ctl->num_passes) return;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int shift = pass * kRadixBits;
-    if (tid == 0) s_tile = atomicAdd(&tile_counter[pass], 1u);
-    for (int i = tid; i < WARPS * kRadix; i += kSortThreads) (&s_hist[0][0])[i] = 0;
-    __syncthreads();
-    const uint32_t tile = s_tile;
+#pragma unroll
+    for (int i = 0; i < WARPS * kRadix / (4 * kSortThreads); ++i)
+        reinterpret_cast<uint4 *>(&s_hist[0][0])[tid + i * kSortThreads] = make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t tile = blockIdx.x;
     const uint32_t tile_base = tile * (uint32_t)kSortTile;
     const uint32_t warp_base = tile_base + warp * WTILE + lane;
+    // this tile's output offsets: issued now, consumed after the ranking
+    const uint32_t tile_excl = tile_hist[(size_t)tid * num_tiles + tile];
+    const uint32_t dtotal = digit_total[tid];
 
     uint32_t key[kSortIpt];
 #pragma unroll
@@ -122,14 +175,26 @@ k_onesweep_pass(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
         const uint32_t idx = warp_base + j * 32;
         key[j] = idx < n ? keys_in[idx] : 0xffffffffu;
     }
+    __syncthreads();
 
     // ---- stable ranking inside the warp: order is (j, lane) == original order ----
+    // peers = lanes holding the same digit, from one ballot per significant digit bit (MATCH.ANY serialises over
+    // the distinct values of the warp and was measured ~50 cycles per instruction and SM)
+    const int digit_bits = min(kRadixBits, ctl->key_bits - shift);
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint16_t rank[kSortIpt];
 #pragma unroll
     for (int j = 0; j < kSortIpt; ++j) {
         const uint32_t d = (key[j] >> shift) & 255u;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        uint32_t peers = 0xffffffffu;
+#pragma unroll
+        for (int b = 0; b < kRadixBits; ++b) {
+            if (b < digit_bits) {  // warp-uniform
+                const bool bit = (d >> b) & 1u;
+                const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+                peers &= bit ? bal : ~bal;
+            }
+        }
         const uint32_t before = s_hist[warp][d];
         const uint32_t r = __popc(peers & lt_mask);
         __syncwarp();
@@ -139,60 +204,25 @@ k_onesweep_pass(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
     }
     __syncthreads();
 
-    // ---- per digit (thread t owns digit t): warp counts -> warp offsets, tile count ----
+    // ---- per digit (thread t owns digit t): warp counts -> offsets within the digit, tile count ----
     uint32_t tile_count = 0;
-    {
-        uint32_t run = 0;
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-            const uint32_t c = s_hist[w][tid];
-            s_hist[w][tid] = run;
-            run += c;
-        }
-        tile_count = run;
+    for (int w = 0; w < WARPS; ++w) {
+        const uint32_t cnt = s_hist[w][tid];
+        s_hist[w][tid] = tile_count;
+        tile_count += cnt;
     }
-    volatile uint32_t *lb = lookback + (size_t)pass * num_tiles * kRadix;
-    // publish the aggregate as early as possible so later tiles can look back through us
-    lb[(size_t)tile * kRadix + tid] = tile_count | (tile == 0 ? kLbIncl : kLbAgg);
-
-    const uint32_t digit_base = block_excl_scan256(hist[pass * kRadix + tid], s_warp, nullptr);
+    const uint32_t digit_base = block_excl_scan256(dtotal, s_warp, nullptr);
     const uint32_t bin_start = block_excl_scan256(tile_count, s_warp, nullptr);
-
-    // ---- decoupled look-back, kLookBatch predecessors per round trip ----
-    uint32_t excl = 0;
-    if (tile != 0) {
-        int prev = (int)tile - 1;
-        bool done = false;
-        while (!done) {
-            uint32_t v[kLookBatch];
-#pragma unroll
-            for (int j = 0; j < kLookBatch; ++j)
-                v[j] = (prev - j >= 0) ? (uint32_t)lb[(size_t)(prev - j) * kRadix + tid] : (uint32_t)(1u << 31);  // before tile 0: empty inclusive prefix
-            int used = 0;
-#pragma unroll
-            for (int j = 0; j < kLookBatch; ++j) {
-                if (done || used != j) continue;
-                if ((v[j] & ~kLbMask) == 0) continue;  // not published yet: retry from this one
-                excl += v[j] & kLbMask;
-                ++used;
-                if (v[j] & kLbIncl) done = true;
-            }
-            prev -= used;
-        }
-        lb[(size_t)tile * kRadix + tid] = (excl + tile_count) | kLbIncl;
-    }
-    // position of digit run d in the output minus its position in the tile
-    s_goff[tid] = digit_base + excl - bin_start;
-    // per-warp offsets become absolute tile positions
-#pragma unroll
-    for (int w = 0; w < WARPS; ++w) s_hist[w][tid] += bin_start;
+    s_bin[tid] = bin_start;
+    s_goff[tid] = digit_base + tile_excl - bin_start;
     __syncthreads();
 
-    // ---- stage the tile digit-sorted in shared memory, then write digit runs contiguously ----
+    // ---- stage the tile digit-sorted in shared memory ----
 #pragma unroll
     for (int j = 0; j < kSortIpt; ++j) {
         const uint32_t d = (key[j] >> shift) & 255u;
-        const uint32_t pos = (uint32_t)rank[j] + s_hist[warp][d];
+        const uint32_t pos = (uint32_t)rank[j] + s_hist[warp][d] + s_bin[d];
         rank[j] = (uint16_t)pos;
         s_keys[pos] = key[j];
     }
@@ -209,6 +239,8 @@ k_onesweep_pass(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
 #pragma unroll
     for (int j = 0; j < kSortIpt; ++j) s_vals[rank[j]] = key[j];
     __syncthreads();
+
+    // ---- write digit runs contiguously ----
     const uint32_t remaining = n - tile_base;
     const uint32_t valid = remaining < (uint32_t)kSortTile ? remaining : (uint32_t)kSortTile;
 #pragma unroll
