@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libgunship_collision.so")
 
 GSC_OK, GSC_ERR_INVALID, GSC_ERR_CUDA, GSC_ERR_NCCL, GSC_ERR_CAPACITY, GSC_ERR_RANGE, GSC_ERR_KIND = range(7)
 GSC_SPHERE, GSC_BOX, GSC_MESH = 0, 1, 2
-GSC_FLAG_TIMING, GSC_FLAG_GRAPH = 1, 2
+GSC_FLAG_TIMING, GSC_FLAG_GRAPH, GSC_FLAG_CONTACTS = 1, 2, 4
 GSC_NUM_STAGES = 6
 GSC_HALO_RECORD_BYTES = 96
 GSC_MAX_PEERS = 16
@@ -44,7 +44,7 @@ class GscStepOut(C.Structure):
                 ("n_cells", C.c_uint64), ("cell_size", C.c_float), ("n_wide", C.c_uint32),
                 ("grid_origin", C.c_int32 * 3), ("grid_dims", C.c_int32 * 3), ("sort_passes", C.c_uint32),
                 ("status_flags", C.c_uint32), ("stage_ms", C.c_float * GSC_NUM_STAGES), ("step_ms", C.c_float),
-                ("d_pairs", C.c_void_p)]
+                ("d_pairs", C.c_void_p), ("d_contacts", C.c_void_p)]
 
 
 class GscBounds(C.Structure):
@@ -59,7 +59,8 @@ EXPORTS = (
     "gsc_test_sphere_sphere", "gsc_test_sphere_obb", "gsc_test_obb_obb", "gsc_test_aabb_aabb", "gsc_fnv1a_gridcell",
     "gsc_sort_pairs_u32", "gsc_phase_bounds", "gsc_set_global_bounds", "gsc_local_x_range", "gsc_halo_select",
     "gsc_halo_append", "gsc_phase_finish", "gsc_set_x_window", "gsc_ipc_export", "gsc_ipc_open_peer", "gsc_halo_push",
-    "gsc_halo_sync", "gsc_halo_commit",
+    "gsc_halo_sync", "gsc_halo_commit", "gsc_download_contacts", "gsc_contact_sphere_sphere", "gsc_contact_sphere_obb",
+    "gsc_contact_obb_obb",
 )
 
 _lib = None
@@ -87,6 +88,10 @@ def load():
     L.gsc_step.argtypes = [vp, C.POINTER(GscStepOut)]
     L.gsc_download_pairs.argtypes = [vp, u32p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
     L.gsc_debug_download.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.gsc_download_contacts.argtypes = [vp, f32p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
+    L.gsc_contact_sphere_sphere.argtypes = [C.c_int, C.c_size_t, f32p, f32p, f32p]
+    L.gsc_contact_sphere_obb.argtypes = [C.c_int, C.c_size_t, f32p, f32p, u8p, f32p]
+    L.gsc_contact_obb_obb.argtypes = [C.c_int, C.c_size_t, f32p, f32p, f32p]
     L.gsc_test_sphere_sphere.argtypes = [C.c_int, C.c_size_t, f32p, f32p, u8p]
     L.gsc_test_sphere_obb.argtypes = [C.c_int, C.c_size_t, f32p, f32p, u8p]
     L.gsc_test_obb_obb.argtypes = [C.c_int, C.c_size_t, f32p, f32p, u8p]

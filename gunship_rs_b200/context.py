@@ -22,10 +22,10 @@ class CollisionContext:
     """gsc_ctx: device buffers + the per-frame step for up to `max_colliders` colliders on one GPU."""
 
     def __init__(self, max_colliders: int, device: int = 0, max_pairs: int = 0, max_candidates: int = 0,
-                 max_cells: int = 0, timing: bool = False):
+                 max_cells: int = 0, timing: bool = False, contacts: bool = False):
         self._lib = N.load()
         cfg = N.GscConfig(device, max_colliders, max_pairs, max_candidates, max_cells,
-                          N.GSC_FLAG_TIMING if timing else 0, 0)
+                          (N.GSC_FLAG_TIMING if timing else 0) | (N.GSC_FLAG_CONTACTS if contacts else 0), 0)
         h = C.c_void_p()
         rc = self._lib.gsc_create(C.byref(cfg), C.byref(h))
         if rc != N.GSC_OK:
@@ -91,6 +91,15 @@ class CollisionContext:
         out = np.zeros((int(n.value), 2), dtype=np.uint32)
         if n.value:
             self._check(self._lib.gsc_download_pairs(self._h, _ptr(out), n.value, 1 if sorted else 0, C.byref(n)))
+        return out
+
+    def contacts(self, sorted: bool = True) -> np.ndarray:
+        """(n,4) float32: (normal.xyz, depth) per pair, same order as pairs(sorted) -- needs contacts=True."""
+        n = C.c_uint64(0)
+        self._check(self._lib.gsc_download_pairs(self._h, None, 0, 0, C.byref(n)))
+        out = np.zeros((int(n.value), 4), dtype=np.float32)
+        if n.value:
+            self._check(self._lib.gsc_download_contacts(self._h, _ptr(out), n.value, 1 if sorted else 0, C.byref(n)))
         return out
 
     def pairs_packed(self, sorted: bool = True) -> np.ndarray:
@@ -198,6 +207,37 @@ def test_sphere_obb(s4, obb16, device=0):
 
 def test_obb_obb(a16, b16, device=0):
     return _batch("gsc_test_obb_obb", a16, b16, np.float32, np.uint8, device)
+
+
+def contact_sphere_sphere(hi4, lo4, device=0):
+    L = N.load()
+    a, b = np.ascontiguousarray(hi4, dtype=np.float32), np.ascontiguousarray(lo4, dtype=np.float32)
+    out = np.zeros((a.shape[0], 4), dtype=np.float32)
+    rc = L.gsc_contact_sphere_sphere(device, a.shape[0], _ptr(a), _ptr(b), _ptr(out))
+    if rc != N.GSC_OK:
+        raise GscError(rc, L.gsc_last_error(None).decode())
+    return out
+
+
+def contact_sphere_obb(s4, obb16, sphere_is_hi, device=0):
+    L = N.load()
+    a, b = np.ascontiguousarray(s4, dtype=np.float32), np.ascontiguousarray(obb16, dtype=np.float32)
+    f = np.ascontiguousarray(sphere_is_hi, dtype=np.uint8)
+    out = np.zeros((a.shape[0], 4), dtype=np.float32)
+    rc = L.gsc_contact_sphere_obb(device, a.shape[0], _ptr(a), _ptr(b), _ptr(f), _ptr(out))
+    if rc != N.GSC_OK:
+        raise GscError(rc, L.gsc_last_error(None).decode())
+    return out
+
+
+def contact_obb_obb(hi16, lo16, device=0):
+    L = N.load()
+    a, b = np.ascontiguousarray(hi16, dtype=np.float32), np.ascontiguousarray(lo16, dtype=np.float32)
+    out = np.zeros((a.shape[0], 4), dtype=np.float32)
+    rc = L.gsc_contact_obb_obb(device, a.shape[0], _ptr(a), _ptr(b), _ptr(out))
+    if rc != N.GSC_OK:
+        raise GscError(rc, L.gsc_last_error(None).decode())
+    return out
 
 
 def test_aabb_aabb(a6, b6, device=0):

@@ -61,6 +61,9 @@ struct gsc_ctx {
     int32_t win_lo = 0, win_hi = 0;
     uint2 *d_pairs = nullptr, *d_cand_ss = nullptr, *d_cand_so = nullptr, *d_cand_oo = nullptr;
     uint2 *d_pairs_sorted = nullptr;
+    float4 *d_contacts = nullptr, *d_contacts_sorted = nullptr;  // GSC_FLAG_CONTACTS
+    uint32_t *d_perm = nullptr;  // permutation that sorts the pairs of the last step
+    bool perm_valid = false;
     FrameBlock *d_fb = nullptr;
     FrameBlock *h_fb = nullptr;  // pinned
     uint32_t *h_enc = nullptr;   // pinned staging of gsc_set_global_bounds
@@ -231,6 +234,7 @@ int gsc_create(const gsc_config *cfg, gsc_ctx **out)
     CR(dmalloc(&c->d_wide, M));
     CR(dmalloc(&c->d_gaps, (size_t)kGapCap));
     CR(dmalloc(&c->d_pairs, c->max_pairs));
+    if (cfg->flags & GSC_FLAG_CONTACTS) CR(dmalloc(&c->d_contacts, c->max_pairs));
     CR(dmalloc(&c->d_cand_ss, c->max_cands));
     CR(dmalloc(&c->d_cand_so, c->max_cands));
     CR(dmalloc(&c->d_cand_oo, c->max_cands));
@@ -267,7 +271,7 @@ void gsc_destroy(gsc_ctx *c)
         }
     void *bufs[] = { c->d_entity, c->d_gidx, c->d_kind, c->d_offset, c->d_size, c->d_pos, c->d_quat, c->d_scale, c->d_rec,
                      c->d_rec_sorted, c->d_qrec_sorted, c->d_obb, c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1], c->d_cell_start,
-                     c->d_wide, c->d_gaps, c->d_pairs, c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->d_pairs_sorted, c->d_fb, c->d_sort_scratch,
+                     c->d_wide, c->d_gaps, c->d_pairs, c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->d_pairs_sorted, c->d_contacts, c->d_contacts_sorted, c->d_perm, c->d_fb, c->d_sort_scratch,
                      c->d_halo_rec, c->d_halo_obb, c->d_halo_count };
     for (void *b : bufs)
         if (b) cudaFree(b);
@@ -390,13 +394,13 @@ static int stage_finish(gsc_ctx *c, gsc_step_out *out)
         k_pairs<<<pb, kPairThreads, 0, s>>>(n_total, c->d_keys[0], c->d_keys[1], sv, c->d_cell_start, po, fb);
         if (timing) CU(c, cudaEventRecord(c->ev[5], s));
         k_narrow_sphere_sphere<<<kGridStrideBlocks, kNarrowThreads, 0, s>>>(c->d_cand_ss, c->max_cands, c->d_rec, c->d_pairs,
-                                                                          c->max_pairs, fb);
+                                                                          c->d_contacts, c->max_pairs, fb);
         k_narrow_sphere_obb<<<kGridStrideBlocks, kNarrowThreads, 0, s>>>(c->d_cand_so, c->max_cands, c->d_rec, c->d_obb,
-                                                                       c->d_pairs, c->max_pairs, fb);
+                                                                       c->d_pairs, c->d_contacts, c->max_pairs, fb);
         k_narrow_obb_obb<<<kGridStrideBlocks, kNarrowThreads, 0, s>>>(c->d_cand_oo, c->max_cands, c->d_obb, c->d_pairs,
-                                                                    c->max_pairs, fb);
+                                                                    c->d_contacts, c->max_pairs, fb);
         k_wide_pairs<<<kGridStrideBlocks, kNarrowThreads, 0, s>>>(c->n_local, c->d_wide, c->d_rec, c->d_obb, c->d_pairs,
-                                                                c->max_pairs, fb);
+                                                                c->d_contacts, c->max_pairs, fb);
         if (timing) CU(c, cudaEventRecord(c->ev[6], s));
     } else if (timing) {
         for (int i = 2; i <= GSC_NUM_STAGES; ++i) CU(c, cudaEventRecord(c->ev[i], s));
@@ -406,6 +410,7 @@ static int stage_finish(gsc_ctx *c, gsc_step_out *out)
     CU(c, cudaEventRecord(c->ev_end, s));
     CU(c, cudaStreamSynchronize(s));
     c->bounds_done = false;
+    c->perm_valid = false;
 
     const FrameBlock &h = *c->h_fb;
     c->last_pairs = std::min<uint64_t>(h.n_pairs, c->max_pairs);
@@ -425,6 +430,7 @@ static int stage_finish(gsc_ctx *c, gsc_step_out *out)
         out->sort_passes = (uint32_t)h.sort.num_passes;
         out->status_flags = h.status;
         out->d_pairs = reinterpret_cast<const uint32_t *>(c->d_pairs);
+        out->d_contacts = reinterpret_cast<const float *>(c->d_contacts);
         cudaEventElapsedTime(&out->step_ms, c->ev_begin, c->ev_end);
         if (timing)
             for (int i = 0; i < GSC_NUM_STAGES; ++i) cudaEventElapsedTime(&out->stage_ms[i], c->ev[i], c->ev[i + 1]);
@@ -680,6 +686,11 @@ __global__ void k_gather_pairs(const uint2 *pairs, const uint32_t *perm, uint32_
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = pairs[perm[i]];
 }
+__global__ void k_gather_contacts(const float4 *contacts, const uint32_t *perm, uint32_t n, float4 *out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = contacts[perm[i]];
+}
 
 // standalone sort of n (key,value) pairs with full control over its scratch; result lands in buffer index *which
 int sort_standalone(gsc_ctx *c, cudaStream_t s, uint32_t n, uint32_t *keys[2], uint32_t *vals[2], bool identity, int key_bits,
@@ -705,6 +716,40 @@ int sort_standalone(gsc_ctx *c, cudaStream_t s, uint32_t n, uint32_t *keys[2], u
 
 extern "C" {
 
+// permutation that orders the pairs of the last step ascending by (first << 32 | second); cached per step
+static int ensure_sorted_perm(gsc_ctx *c)
+{
+    if (c->perm_valid) return GSC_OK;
+    const uint64_t n = c->last_pairs;
+    if (n >= (1ull << 30)) return fail(c, GSC_ERR_CAPACITY, "sorted download supports < 2^30 pairs");
+    cudaStream_t s = c->stream;
+    // LSD over the 64-bit tuple with the 32-bit sort: second entity first, then (stable) the first
+    const uint32_t m = (uint32_t)n;
+    uint32_t *k[2] = { nullptr, nullptr }, *v[2] = { nullptr, nullptr };
+    for (int i = 0; i < 2; ++i) {
+        CU(c, dmalloc(&k[i], m));
+        CU(c, dmalloc(&v[i], m));
+    }
+    if (!c->d_perm) CU(c, dmalloc(&c->d_perm, c->max_pairs));
+    const uint32_t blocks = (m + 255) / 256;
+    int w1 = 0, w2 = 0;
+    k_extract_field<<<blocks, 256, 0, s>>>(c->d_pairs, nullptr, m, 1, k[0]);
+    int rc = sort_standalone(c, s, m, k, v, true, 32, &w1);
+    if (rc == GSC_OK) {
+        if (w1 != 0) { std::swap(k[0], k[1]); std::swap(v[0], v[1]); }
+        k_extract_field<<<blocks, 256, 0, s>>>(c->d_pairs, v[0], m, 0, k[0]);
+        rc = sort_standalone(c, s, m, k, v, false, 32, &w2);
+    }
+    if (rc == GSC_OK) {
+        cudaError_t e = cudaMemcpyAsync(c->d_perm, v[w2], (size_t)m * 4, cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = fail(c, GSC_ERR_CUDA, "sorted download: %s", cudaGetErrorString(e));
+    }
+    for (int i = 0; i < 2; ++i) { cudaFree(k[i]); cudaFree(v[i]); }
+    if (rc == GSC_OK) c->perm_valid = true;
+    return rc;
+}
+
 int gsc_download_pairs(gsc_ctx *c, uint32_t *dst, uint64_t cap_pairs, int sorted, uint64_t *n_out)
 {
     if (int rc = check_ctx(c)) return rc;
@@ -715,34 +760,33 @@ int gsc_download_pairs(gsc_ctx *c, uint32_t *dst, uint64_t cap_pairs, int sorted
     cudaStream_t s = c->stream;
     const uint2 *src = c->d_pairs;
     if (sorted) {
-        if (n >= (1ull << 30)) return fail(c, GSC_ERR_CAPACITY, "sorted download supports < 2^30 pairs");
-        // LSD over the 64-bit tuple with the 32-bit sort: second entity first, then (stable) the first
-        const uint32_t m = (uint32_t)n;
-        uint32_t *k[2] = { nullptr, nullptr }, *v[2] = { nullptr, nullptr };
-        for (int i = 0; i < 2; ++i) {
-            CU(c, dmalloc(&k[i], m));
-            CU(c, dmalloc(&v[i], m));
-        }
+        if (int rc = ensure_sorted_perm(c)) return rc;
         if (!c->d_pairs_sorted) CU(c, dmalloc(&c->d_pairs_sorted, c->max_pairs));
-        const uint32_t blocks = (m + 255) / 256;
-        int w1 = 0, w2 = 0;
-        k_extract_field<<<blocks, 256, 0, s>>>(c->d_pairs, nullptr, m, 1, k[0]);
-        int rc = sort_standalone(c, s, m, k, v, true, 32, &w1);
-        if (rc == GSC_OK) {
-            if (w1 != 0) { std::swap(k[0], k[1]); std::swap(v[0], v[1]); }
-            k_extract_field<<<blocks, 256, 0, s>>>(c->d_pairs, v[0], m, 0, k[0]);
-            rc = sort_standalone(c, s, m, k, v, false, 32, &w2);
-        }
-        if (rc == GSC_OK) {
-            k_gather_pairs<<<blocks, 256, 0, s>>>(c->d_pairs, v[w2], m, c->d_pairs_sorted);
-            cudaError_t e = cudaStreamSynchronize(s);
-            if (e != cudaSuccess) rc = fail(c, GSC_ERR_CUDA, "sorted download: %s", cudaGetErrorString(e));
-        }
-        for (int i = 0; i < 2; ++i) { cudaFree(k[i]); cudaFree(v[i]); }
-        if (rc) return rc;
+        k_gather_pairs<<<((uint32_t)n + 255) / 256, 256, 0, s>>>(c->d_pairs, c->d_perm, (uint32_t)n, c->d_pairs_sorted);
         src = c->d_pairs_sorted;
     }
     CU(c, cudaMemcpyAsync(dst, src, n * sizeof(uint2), cudaMemcpyDeviceToHost, s));
+    CU(c, cudaStreamSynchronize(s));
+    return GSC_OK;
+}
+
+int gsc_download_contacts(gsc_ctx *c, float *dst, uint64_t cap_pairs, int sorted, uint64_t *n_out)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!c->d_contacts) return fail(c, GSC_ERR_INVALID, "gsc_download_contacts: the context was created without GSC_FLAG_CONTACTS");
+    const uint64_t n = c->last_pairs;
+    if (n_out) *n_out = n;
+    if (n == 0 || (!dst && cap_pairs == 0)) return GSC_OK;
+    if (!dst || cap_pairs < n) return fail(c, GSC_ERR_CAPACITY, "gsc_download_contacts: need room for %llu contacts", (unsigned long long)n);
+    cudaStream_t s = c->stream;
+    const float4 *src = c->d_contacts;
+    if (sorted) {
+        if (int rc = ensure_sorted_perm(c)) return rc;
+        if (!c->d_contacts_sorted) CU(c, dmalloc(&c->d_contacts_sorted, c->max_pairs));
+        k_gather_contacts<<<((uint32_t)n + 255) / 256, 256, 0, s>>>(c->d_contacts, c->d_perm, (uint32_t)n, c->d_contacts_sorted);
+        src = c->d_contacts_sorted;
+    }
+    CU(c, cudaMemcpyAsync(dst, src, n * sizeof(float4), cudaMemcpyDeviceToHost, s));
     CU(c, cudaStreamSynchronize(s));
     return GSC_OK;
 }
@@ -845,6 +889,32 @@ int gsc_fnv1a_gridcell(int device, size_t n, const int16_t *cells3, uint64_t *ou
 {
     return run_batch(device, n, cells3, 6, nullptr, 0, out, 8, [&](void *a, void *, void *o, unsigned g) {
         k_batch_fnv1a<<<g, 256>>>(n, (const int16_t *)a, (uint64_t *)o);
+    });
+}
+
+int gsc_contact_sphere_sphere(int device, size_t n, const float *hi4, const float *lo4, float *out4)
+{
+    return run_batch(device, n, hi4, 16, lo4, 16, out4, 16, [&](void *a, void *b, void *o, unsigned g) {
+        k_batch_contact_ss<<<g, 256>>>(n, (const float4 *)a, (const float4 *)b, (float4 *)o);
+    });
+}
+int gsc_contact_obb_obb(int device, size_t n, const float *hi16, const float *lo16, float *out4)
+{
+    return run_batch(device, n, hi16, 64, lo16, 64, out4, 16, [&](void *a, void *b, void *o, unsigned g) {
+        k_batch_contact_oo<<<g, 256>>>(n, (const float *)a, (const float *)b, (float4 *)o);
+    });
+}
+int gsc_contact_sphere_obb(int device, size_t n, const float *s4, const float *obb16, const uint8_t *sphere_is_hi, float *out4)
+{
+    if (n == 0) return GSC_OK;
+    if (!sphere_is_hi) return fail(nullptr, GSC_ERR_INVALID, "batch: null array");
+    BT(cudaSetDevice(device));
+    Scratch flag;
+    BT(cudaMalloc(&flag.p[0], n));
+    BT(cudaMemcpy(flag.p[0], sphere_is_hi, n, cudaMemcpyHostToDevice));
+    const uint8_t *d_flag = (const uint8_t *)flag.p[0];
+    return run_batch(device, n, s4, 16, obb16, 64, out4, 16, [&](void *a, void *b, void *o, unsigned g) {
+        k_batch_contact_so<<<g, 256>>>(n, (const float4 *)a, (const float *)b, d_flag, (float4 *)o);
     });
 }
 

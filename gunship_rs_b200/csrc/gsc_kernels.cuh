@@ -99,6 +99,7 @@ struct FrameBlock {
 template <int WARPS, int CAP>
 struct EmitBuf {
     uint2 items[WARPS][CAP];
+    float4 extra[WARPS][CAP];  // contact (normal.xyz, depth) travelling with the pair (GSC_FLAG_CONTACTS)
     uint32_t count[WARPS];
     unsigned long long base;
 };
@@ -109,9 +110,10 @@ GSC_DEV void emit_init(EmitBuf<WARPS, CAP> &b)
     if (threadIdx.x < WARPS) b.count[threadIdx.x] = 0;
 }
 
+// `out_extra` == nullptr: pairs only
 template <int WARPS, int CAP>
-GSC_DEV void emit(EmitBuf<WARPS, CAP> &b, bool pred, uint2 item, uint2 *__restrict__ out,
-                  unsigned long long *counter, unsigned long long cap)
+GSC_DEV void emit(EmitBuf<WARPS, CAP> &b, bool pred, uint2 item, float4 extra, uint2 *__restrict__ out,
+                  float4 *__restrict__ out_extra, unsigned long long *counter, unsigned long long cap)
 {
     const uint32_t mask = __ballot_sync(0xffffffffu, pred);
     if (mask == 0) return;
@@ -123,19 +125,26 @@ GSC_DEV void emit(EmitBuf<WARPS, CAP> &b, bool pred, uint2 item, uint2 *__restri
         if (lane == 0) base = atomicAdd(counter, (unsigned long long)have);
         base = __shfl_sync(0xffffffffu, base, 0);
         for (uint32_t i = lane; i < have; i += 32)
-            if (base + i < cap) out[base + i] = b.items[warp][i];
+            if (base + i < cap) {
+                out[base + i] = b.items[warp][i];
+                if (out_extra) out_extra[base + i] = b.extra[warp][i];
+            }
         have = 0;
         __syncwarp();
     }
-    if (pred) b.items[warp][have + __popc(mask & ((1u << lane) - 1u))] = item;
+    if (pred) {
+        const uint32_t at = have + __popc(mask & ((1u << lane) - 1u));
+        b.items[warp][at] = item;
+        if (out_extra) b.extra[warp][at] = extra;
+    }
     __syncwarp();
     if (lane == 0) b.count[warp] = have + cnt;
     __syncwarp();
 }
 
 template <int WARPS, int CAP>
-GSC_DEV void emit_finish(EmitBuf<WARPS, CAP> &b, uint2 *__restrict__ out, unsigned long long *counter,
-                         unsigned long long cap)
+GSC_DEV void emit_finish(EmitBuf<WARPS, CAP> &b, uint2 *__restrict__ out, float4 *__restrict__ out_extra,
+                         unsigned long long *counter, unsigned long long cap)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -149,7 +158,10 @@ GSC_DEV void emit_finish(EmitBuf<WARPS, CAP> &b, uint2 *__restrict__ out, unsign
     for (int w = 0; w < warp; ++w) base += b.count[w];
     const uint32_t have = b.count[warp];
     for (uint32_t i = lane; i < have; i += 32)
-        if (base + i < cap) out[base + i] = b.items[warp][i];
+        if (base + i < cap) {
+            out[base + i] = b.items[warp][i];
+            if (out_extra) out_extra[base + i] = b.extra[warp][i];
+        }
 }
 
 // ---- stage 0: bvh_update -----------------------------------------------------------------------
@@ -479,6 +491,7 @@ k_fill_gaps(uint32_t *__restrict__ cell_start, const uint4 *__restrict__ gaps, c
 constexpr int kPairThreads = 64;
 constexpr int kPairWarps = kPairThreads / 32;
 constexpr int kPairRows = 5;
+constexpr int kPairTrip = 4;    // candidates per loop trip
 constexpr int kPairPriv = 8;    // private survivor slots per lane; a lane that fills them drains early
 constexpr int kPairCap = 256;   // survivors staged per CTA (4 per volume); denser CTAs spill one by one
 
@@ -596,51 +609,31 @@ k_pairs(uint32_t n_total, const uint32_t *__restrict__ keys_a, const uint32_t *_
         }
     };
     auto drain_if_full = [&]() {
-        if (pa - pa0 >= (kPairPriv - 1) * kSlotStride) {  // fewer than two free slots left
+        if (pa - pa0 > (kPairPriv - kPairTrip) * kSlotStride) {  // fewer than one trip of free slots left
             pair_drain_lane(sh, p, (pa - pa0) / kSlotStride, tid, sv.v, out, fb);
             pa = pa0;
         }
     };
+    // kPairTrip candidates per trip, all their loads in flight before the first test.  Runs are short (4.4
+    // candidates on average), so a trip usually covers the whole run: indices past the end are clamped for the
+    // load and masked out of the test.
 #pragma unroll
-    for (int r = 0; r < kPairRows - 1; ++r) {  // neighbour rows: 12 B per candidate
+    for (int r = 0; r < kPairRows; ++r) {
+        const bool own = r == kPairRows - 1;  // own row (cells z-1, z): same-cell pairs go to the larger global index
         const uint32_t qe = hi[r];
-        uint32_t q = lo[r];
 #pragma unroll 1
-        for (; q + 1 < qe; q += 2) {  // two candidates per trip: all loads in flight before either test
-            const uint4 *v = sv.q + q;
-            const uint2 b01 = __ldg(reinterpret_cast<const uint2 *>(v));
-            const uint32_t b2 = __ldg(reinterpret_cast<const uint32_t *>(v) + 2);
-            const uint2 c01 = __ldg(reinterpret_cast<const uint2 *>(v + 1));
-            const uint32_t c2 = __ldg(reinterpret_cast<const uint32_t *>(v + 1) + 2);
-            test(q, b01.x, b01.y, b2, true);
-            test(q + 1, c01.x, c01.y, c2, true);
-            drain_if_full();
-        }
-        if (q < qe) {
-            const uint4 *v = sv.q + q;
-            const uint2 b01 = __ldg(reinterpret_cast<const uint2 *>(v));
-            const uint32_t b2 = __ldg(reinterpret_cast<const uint32_t *>(v) + 2);
-            test(q, b01.x, b01.y, b2, true);
+        for (uint32_t q = lo[r]; q < qe; q += kPairTrip) {
+            uint4 b[kPairTrip];
+#pragma unroll
+            for (int k = 0; k < kPairTrip; ++k) b[k] = __ldg(sv.q + min(q + k, qe - 1));
+#pragma unroll
+            for (int k = 0; k < kPairTrip; ++k) {
+                const uint32_t qk = q + k;
+                test(qk, b[k].x, b[k].y, b[k].z, qk < qe && (!own || qk < qsame || b[k].w < a_w3));
+            }
             drain_if_full();
         }
         __syncwarp();  // reconverge before the next run: lanes must walk each run together
-    }
-    {  // own row (cells z-1, z): 16 B per candidate, same-cell pairs go to the larger global index
-        const uint32_t qe = hi[kPairRows - 1];
-        uint32_t q = lo[kPairRows - 1];
-#pragma unroll 1
-        for (; q + 1 < qe; q += 2) {
-            const uint4 b = __ldg(sv.q + q), c = __ldg(sv.q + q + 1);
-            test(q, b.x, b.y, b.z, q < qsame || b.w < a_w3);
-            test(q + 1, c.x, c.y, c.z, q + 1 < qsame || c.w < a_w3);
-            drain_if_full();
-        }
-        if (q < qe) {
-            const uint4 b = __ldg(sv.q + q);
-            test(q, b.x, b.y, b.z, q < qsame || b.w < a_w3);
-            drain_if_full();
-        }
-        __syncwarp();
     }
 
     // ---- compact the private slots into the CTA list: warp scan + one shared atomic per warp ----
@@ -715,7 +708,8 @@ constexpr int kNarrowCap = 96;
 // Sphere::test_sphere (mod.rs:383-389): later.test_sphere(earlier); spheres come from the volume records
 __global__ void __launch_bounds__(kNarrowThreads)
 k_narrow_sphere_sphere(const uint2 *__restrict__ cand, unsigned long long cap_cands, const float4 *__restrict__ rec,
-                       uint2 *__restrict__ pairs, unsigned long long cap_pairs, FrameBlock *__restrict__ fb)
+                       uint2 *__restrict__ pairs, float4 *__restrict__ contacts, unsigned long long cap_pairs,
+                       FrameBlock *__restrict__ fb)
 {
     __shared__ EmitBuf<kNarrowWarps, kNarrowCap> s_out;
     emit_init(s_out);
@@ -726,6 +720,7 @@ k_narrow_sphere_sphere(const uint2 *__restrict__ cand, unsigned long long cap_ca
         const unsigned long long i = b + threadIdx.x;
         bool hit = false;
         uint2 item = make_uint2(0, 0);
+        float4 ct = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < n) {
             const uint2 c = cand[i];
             const float4 h0 = __ldg(rec + 2 * (size_t)c.x), l0 = __ldg(rec + 2 * (size_t)c.y);
@@ -733,18 +728,19 @@ k_narrow_sphere_sphere(const uint2 *__restrict__ cand, unsigned long long cap_ca
             if (hit) {
                 const float4 h1 = __ldg(rec + 2 * (size_t)c.x + 1), l1 = __ldg(rec + 2 * (size_t)c.y + 1);
                 item = make_uint2(__float_as_uint(h1.x), __float_as_uint(l1.x));
+                if (contacts) ct = contact_sphere_sphere(h0.x, h0.y, h0.z, h0.w, l0.x, l0.y, l0.z, l0.w);
             }
         }
-        emit(s_out, hit, item, pairs, &fb->n_pairs, cap_pairs);
+        emit(s_out, hit, item, ct, pairs, contacts, &fb->n_pairs, cap_pairs);
     }
-    emit_finish(s_out, pairs, &fb->n_pairs, cap_pairs);
+    emit_finish(s_out, pairs, contacts, &fb->n_pairs, cap_pairs);
 }
 
 // Sphere::test_obb (mod.rs:391-394) -- either order of the pair calls sphere.test_obb(obb) (mod.rs:378,407)
 __global__ void __launch_bounds__(kNarrowThreads)
 k_narrow_sphere_obb(const uint2 *__restrict__ cand, unsigned long long cap_cands, const float4 *__restrict__ rec,
-                    const float4 *__restrict__ obb, uint2 *__restrict__ pairs, unsigned long long cap_pairs,
-                    FrameBlock *__restrict__ fb)
+                    const float4 *__restrict__ obb, uint2 *__restrict__ pairs, float4 *__restrict__ contacts,
+                    unsigned long long cap_pairs, FrameBlock *__restrict__ fb)
 {
     __shared__ EmitBuf<kNarrowWarps, kNarrowCap> s_out;
     emit_init(s_out);
@@ -755,6 +751,7 @@ k_narrow_sphere_obb(const uint2 *__restrict__ cand, unsigned long long cap_cands
         const unsigned long long i = b + threadIdx.x;
         bool hit = false;
         uint2 item = make_uint2(0, 0);
+        float4 ct = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < n) {
             const uint2 c = cand[i];
             const bool hi_is_sphere = c.x >> 31;
@@ -766,16 +763,18 @@ k_narrow_sphere_obb(const uint2 *__restrict__ cand, unsigned long long cap_cands
             hit = test_sphere_obb(s0.x, s0.y, s0.z, s0.w, o);
             const uint32_t se = __float_as_uint(s1.x);
             item = hi_is_sphere ? make_uint2(se, oe) : make_uint2(oe, se);
+            if (hit && contacts) ct = contact_sphere_obb(s0.x, s0.y, s0.z, s0.w, o, hi_is_sphere);
         }
-        emit(s_out, hit, item, pairs, &fb->n_pairs, cap_pairs);
+        emit(s_out, hit, item, ct, pairs, contacts, &fb->n_pairs, cap_pairs);
     }
-    emit_finish(s_out, pairs, &fb->n_pairs, cap_pairs);
+    emit_finish(s_out, pairs, contacts, &fb->n_pairs, cap_pairs);
 }
 
 // OBB::test_obb (mod.rs:413-546) evaluated as later.test_obb(earlier) (grid_collision.rs:505, mod.rs:408)
 __global__ void __launch_bounds__(kNarrowThreads)
 k_narrow_obb_obb(const uint2 *__restrict__ cand, unsigned long long cap_cands, const float4 *__restrict__ obb,
-                 uint2 *__restrict__ pairs, unsigned long long cap_pairs, FrameBlock *__restrict__ fb)
+                 uint2 *__restrict__ pairs, float4 *__restrict__ contacts, unsigned long long cap_pairs,
+                 FrameBlock *__restrict__ fb)
 {
     __shared__ EmitBuf<kNarrowWarps, kNarrowCap> s_out;
     emit_init(s_out);
@@ -786,6 +785,7 @@ k_narrow_obb_obb(const uint2 *__restrict__ cand, unsigned long long cap_cands, c
         const unsigned long long i = b + threadIdx.x;
         bool hit = false;
         uint2 item = make_uint2(0, 0);
+        float4 ct = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < n) {
             const uint2 c = cand[i];
             uint32_t ea, eb;
@@ -793,35 +793,41 @@ k_narrow_obb_obb(const uint2 *__restrict__ cand, unsigned long long cap_cands, c
             const Obb bb = obb_load(obb + 4 * (size_t)c.y, &eb);
             hit = test_obb_obb(a, bb);
             item = make_uint2(ea, eb);
+            if (hit && contacts) ct = contact_obb_obb(a, bb);
         }
-        emit(s_out, hit, item, pairs, &fb->n_pairs, cap_pairs);
+        emit(s_out, hit, item, ct, pairs, contacts, &fb->n_pairs, cap_pairs);
     }
-    emit_finish(s_out, pairs, &fb->n_pairs, cap_pairs);
+    emit_finish(s_out, pairs, contacts, &fb->n_pairs, cap_pairs);
 }
 
 // full BoundVolume::test (bounding_volume.rs:124-132) between two arbitrary volumes, `hi` = later index
 GSC_DEV bool test_volume_full(const Volume &hi, const Volume &lo, const float4 *__restrict__ obb, uint32_t *e_hi,
-                              uint32_t *e_lo)
+                              uint32_t *e_lo, bool want_contact, float4 *ct)
 {
     if (!test_aabb(hi.mn, hi.mx, lo.mn, lo.mx)) return false;
     const bool hb = hi.meta & kMetaBox, lb = lo.meta & kMetaBox;
+    bool hit;
     if (!hb && !lb) {
         *e_hi = hi.entity; *e_lo = lo.entity;
-        return test_sphere_sphere(hi.cx, hi.cy, hi.cz, hi.r, lo.cx, lo.cy, lo.cz, lo.r);
-    }
-    if (hb && lb) {
+        hit = test_sphere_sphere(hi.cx, hi.cy, hi.cz, hi.r, lo.cx, lo.cy, lo.cz, lo.r);
+        if (hit && want_contact) *ct = contact_sphere_sphere(hi.cx, hi.cy, hi.cz, hi.r, lo.cx, lo.cy, lo.cz, lo.r);
+    } else if (hb && lb) {
         const Obb a = obb_load(obb + 4 * (size_t)(hi.meta >> 4), e_hi);
         const Obb b = obb_load(obb + 4 * (size_t)(lo.meta >> 4), e_lo);
-        return test_obb_obb(a, b);
-    }
-    if (hb) {
+        hit = test_obb_obb(a, b);
+        if (hit && want_contact) *ct = contact_obb_obb(a, b);
+    } else if (hb) {
         const Obb o = obb_load(obb + 4 * (size_t)(hi.meta >> 4), e_hi);
         *e_lo = lo.entity;
-        return test_sphere_obb(lo.cx, lo.cy, lo.cz, lo.r, o);
+        hit = test_sphere_obb(lo.cx, lo.cy, lo.cz, lo.r, o);
+        if (hit && want_contact) *ct = contact_sphere_obb(lo.cx, lo.cy, lo.cz, lo.r, o, false);
+    } else {
+        const Obb o = obb_load(obb + 4 * (size_t)(lo.meta >> 4), e_lo);
+        *e_hi = hi.entity;
+        hit = test_sphere_obb(hi.cx, hi.cy, hi.cz, hi.r, o);
+        if (hit && want_contact) *ct = contact_sphere_obb(hi.cx, hi.cy, hi.cz, hi.r, o, true);
     }
-    const Obb o = obb_load(obb + 4 * (size_t)(lo.meta >> 4), e_lo);
-    *e_hi = hi.entity;
-    return test_sphere_obb(hi.cx, hi.cy, hi.cz, hi.r, o);
+    return hit;
 }
 
 // Volumes that span 3 cells on an axis (possible only through rounding of p / cell_size): the
@@ -829,8 +835,8 @@ GSC_DEV bool test_volume_full(const Volume &hi, const Volume &lo, const float4 *
 // another volume iff the two share a corner cell.  Restated literally, wide x everything.
 __global__ void __launch_bounds__(kNarrowThreads)
 k_wide_pairs(uint32_t n_local, const uint32_t *__restrict__ wide_list, const float4 *__restrict__ rec,
-             const float4 *__restrict__ obb, uint2 *__restrict__ pairs, unsigned long long cap_pairs,
-             FrameBlock *__restrict__ fb)
+             const float4 *__restrict__ obb, uint2 *__restrict__ pairs, float4 *__restrict__ contacts,
+             unsigned long long cap_pairs, FrameBlock *__restrict__ fb)
 {
     __shared__ EmitBuf<kNarrowWarps, kNarrowCap> s_out;
     const GridParams g = fb->grid;
@@ -844,6 +850,7 @@ k_wide_pairs(uint32_t n_local, const uint32_t *__restrict__ wide_list, const flo
         const unsigned long long t = b + threadIdx.x;
         bool hit = false;
         uint2 item = make_uint2(0, 0);
+        float4 ct = make_float4(0.f, 0.f, 0.f, 0.f);
         if (t < total) {
             const uint32_t wi = wide_list[t / n_local];
             const uint32_t j = (uint32_t)(t % n_local);
@@ -861,14 +868,15 @@ k_wide_pairs(uint32_t n_local, const uint32_t *__restrict__ wide_list, const flo
                 if (take) {
                     const bool w_hi = W.gidx > J.gidx;
                     uint32_t eh = 0, el = 0;
-                    hit = w_hi ? test_volume_full(W, J, obb, &eh, &el) : test_volume_full(J, W, obb, &eh, &el);
+                    hit = w_hi ? test_volume_full(W, J, obb, &eh, &el, contacts != nullptr, &ct)
+                               : test_volume_full(J, W, obb, &eh, &el, contacts != nullptr, &ct);
                     item = make_uint2(eh, el);
                 }
             }
         }
-        emit(s_out, hit, item, pairs, &fb->n_pairs, cap_pairs);
+        emit(s_out, hit, item, ct, pairs, contacts, &fb->n_pairs, cap_pairs);
     }
-    emit_finish(s_out, pairs, &fb->n_pairs, cap_pairs);
+    emit_finish(s_out, pairs, contacts, &fb->n_pairs, cap_pairs);
 }
 
 // ---- multi-GPU slab support: home-x range, halo selection, ghost append ------------------------------
@@ -1047,6 +1055,26 @@ __global__ void k_batch_obb_obb(size_t n, const float *a16, const float *b16, ui
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     out[i] = test_obb_obb(obb_from16(a16 + 16 * i), obb_from16(b16 + 16 * i));
+}
+__global__ void k_batch_contact_ss(size_t n, const float4 *hi, const float4 *lo, float4 *out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 h = hi[i], l = lo[i];
+    out[i] = contact_sphere_sphere(h.x, h.y, h.z, h.w, l.x, l.y, l.z, l.w);
+}
+__global__ void k_batch_contact_so(size_t n, const float4 *s, const float *o16, const uint8_t *sphere_is_hi, float4 *out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = s[i];
+    out[i] = contact_sphere_obb(p.x, p.y, p.z, p.w, obb_from16(o16 + 16 * i), sphere_is_hi[i] != 0);
+}
+__global__ void k_batch_contact_oo(size_t n, const float *a16, const float *b16, float4 *out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = contact_obb_obb(obb_from16(a16 + 16 * i), obb_from16(b16 + 16 * i));
 }
 __global__ void k_batch_aabb_aabb(size_t n, const float *a6, const float *b6, uint8_t *out)
 {

@@ -216,6 +216,147 @@ GSC_DEV bool test_obb_obb(const Obb &a, const Obb &b)
     return true;
 }
 
+// ---- contacts (normal.xyz, depth) -------------------------------------------------------------------
+// NOT in the reference (it only plans them, mod.rs:110-113): this is the definition BASELINE.json's
+// north_star asks for, documented in include/gunship_collision.h.  `hi` is the later volume of the pair, `lo`
+// the earlier one; the unit normal points from lo to hi, depth is the overlap along it.  Same f32 operation
+// order as the checker in oracle/ (separate mul/add, IEEE sqrt and divide).
+GSC_DEV float4 contact_sphere_sphere(float hx, float hy, float hz, float hr, float lx, float ly, float lz, float lr)
+{
+    const float dx = sub(hx, lx), dy = sub(hy, ly), dz = sub(hz, lz);
+    const float dist = __fsqrt_rn(add(add(mul(dx, dx), mul(dy, dy)), mul(dz, dz)));
+    float4 c;
+    if (dist > 0.0f) { c.x = __fdiv_rn(dx, dist); c.y = __fdiv_rn(dy, dist); c.z = __fdiv_rn(dz, dist); }
+    else { c.x = 1.0f; c.y = 0.0f; c.z = 0.0f; }
+    c.w = sub(add(hr, lr), dist);
+    return c;
+}
+
+// from OBB::closest_point (mod.rs:549-568): outside, the normal is (centre - closest point) normalised; a centre
+// inside the box leaves through the face of least penetration
+GSC_DEV float4 contact_sphere_obb(float sx, float sy, float sz, float sr, const Obb &o, bool sphere_is_hi)
+{
+    const float dx = sub(sx, o.cx), dy = sub(sy, o.cy), dz = sub(sz, o.cz);
+    float rx = o.cx, ry = o.cy, rz = o.cz;
+    const float h[3] = { o.hx, o.hy, o.hz };
+    float proj[3];
+#pragma unroll
+    for (int axis = 0; axis < 3; ++axis) {
+        const float ax = o.m[0][axis], ay = o.m[1][axis], az = o.m[2][axis];
+        const float dist = dot3(dx, dy, dz, ax, ay, az);
+        proj[axis] = dist;
+        const float cl = fminf(fmaxf(dist, -h[axis]), h[axis]);
+        rx = add(rx, mul(ax, cl));
+        ry = add(ry, mul(ay, cl));
+        rz = add(rz, mul(az, cl));
+    }
+    const float vx = sub(sx, rx), vy = sub(sy, ry), vz = sub(sz, rz);
+    const float d2 = add(add(mul(vx, vx), mul(vy, vy)), mul(vz, vz));
+    // inside <=> no projection was clamped (d2 alone is not robust: the rebuilt point differs by rounding)
+    const bool inside = fabsf(proj[0]) <= h[0] && fabsf(proj[1]) <= h[1] && fabsf(proj[2]) <= h[2];
+    float4 c;
+    if (!inside && d2 > 0.0f) {
+        const float dd = __fsqrt_rn(d2);
+        c.x = __fdiv_rn(vx, dd); c.y = __fdiv_rn(vy, dd); c.z = __fdiv_rn(vz, dd);
+        c.w = sub(sr, dd);
+    } else {
+        int best = 0;
+        float pen = sub(h[0], fabsf(proj[0]));
+#pragma unroll
+        for (int i = 1; i < 3; ++i) {
+            const float p = sub(h[i], fabsf(proj[i]));
+            if (p < pen) { pen = p; best = i; }
+        }
+        const float pb = best == 0 ? proj[0] : (best == 1 ? proj[1] : proj[2]);
+        const float sgn = pb < 0.0f ? -1.0f : 1.0f;
+        c.x = mul(best == 0 ? o.m[0][0] : (best == 1 ? o.m[0][1] : o.m[0][2]), sgn);
+        c.y = mul(best == 0 ? o.m[1][0] : (best == 1 ? o.m[1][1] : o.m[1][2]), sgn);
+        c.z = mul(best == 0 ? o.m[2][0] : (best == 1 ? o.m[2][1] : o.m[2][2]), sgn);
+        c.w = add(sr, pen);
+    }
+    if (!sphere_is_hi) { c.x = -c.x; c.y = -c.y; c.z = -c.z; }
+    return c;
+}
+
+// least-penetration axis of the 15 SAT axes of OBB::test_obb (mod.rs:443-542), a = hi, b = lo.  Cross axes are
+// normalised by |A_i x B_j| = sqrt(1 - r_ij^2) and skipped when nearly parallel.
+GSC_DEV float4 contact_obb_obb(const Obb &a, const Obb &b)
+{
+    float r[3][3], ar[3][3];
+#pragma unroll
+    for (int row = 0; row < 3; ++row)
+#pragma unroll
+        for (int col = 0; col < 3; ++col) {
+            r[row][col] = dot3(a.m[0][row], a.m[1][row], a.m[2][row], b.m[0][col], b.m[1][col], b.m[2][col]);
+            ar[row][col] = add(fabsf(r[row][col]), kEpsilon);
+        }
+    const float tx = sub(b.cx, a.cx), ty = sub(b.cy, a.cy), tz = sub(b.cz, a.cz);
+    float t[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) t[i] = add(add(mul(a.m[0][i], tx), mul(a.m[1][i], ty)), mul(a.m[2][i], tz));
+    const float ah[3] = { a.hx, a.hy, a.hz };
+    const float bh[3] = { b.hx, b.hy, b.hz };
+    float best_pen = INFINITY, best_s = 0.0f, best_len = 1.0f;
+    int best_axis = 0;  // 0..2 A_i, 3..5 B_i, 6 + 3 i + j cross
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float rb = add(add(mul(bh[0], ar[i][0]), mul(bh[1], ar[i][1])), mul(bh[2], ar[i][2]));
+        const float pen = sub(add(ah[i], rb), fabsf(t[i]));
+        if (pen < best_pen) { best_pen = pen; best_s = t[i]; best_axis = i; }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float ra = add(add(mul(ah[0], ar[0][i]), mul(ah[1], ar[1][i])), mul(ah[2], ar[2][i]));
+        const float proj = add(add(mul(t[0], r[0][i]), mul(t[1], r[1][i])), mul(t[2], r[2][i]));
+        const float pen = sub(add(ra, bh[i]), fabsf(proj));
+        if (pen < best_pen) { best_pen = pen; best_s = proj; best_axis = 3 + i; }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        constexpr int nx[3] = { 1, 2, 0 }, pv[3] = { 2, 0, 1 };
+        const int i1 = nx[i], i2 = pv[i];
+        const int ilo = i1 < i2 ? i1 : i2, ihi = i1 < i2 ? i2 : i1;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int j1 = nx[j], j2 = pv[j];
+            const int jlo = j1 < j2 ? j1 : j2, jhi = j1 < j2 ? j2 : j1;
+            const float ra = add(mul(ah[ilo], ar[ihi][j]), mul(ah[ihi], ar[ilo][j]));
+            const float rb = add(mul(bh[jlo], ar[i][jhi]), mul(bh[jhi], ar[i][jlo]));
+            const float sv = sub(mul(t[i2], r[i1][j]), mul(t[i1], r[i2][j]));
+            const float len2 = sub(1.0f, mul(r[i][j], r[i][j]));
+            if (len2 > kEpsilon) {
+                const float len = __fsqrt_rn(len2);
+                const float pen = __fdiv_rn(sub(add(ra, rb), fabsf(sv)), len);
+                if (pen < best_pen) { best_pen = pen; best_s = sv; best_axis = 6 + 3 * i + j; best_len = len; }
+            }
+        }
+    }
+    float lx, ly, lz;
+    if (best_axis < 3) {
+        lx = best_axis == 0 ? a.m[0][0] : (best_axis == 1 ? a.m[0][1] : a.m[0][2]);
+        ly = best_axis == 0 ? a.m[1][0] : (best_axis == 1 ? a.m[1][1] : a.m[1][2]);
+        lz = best_axis == 0 ? a.m[2][0] : (best_axis == 1 ? a.m[2][1] : a.m[2][2]);
+    } else if (best_axis < 6) {
+        const int k = best_axis - 3;
+        lx = k == 0 ? b.m[0][0] : (k == 1 ? b.m[0][1] : b.m[0][2]);
+        ly = k == 0 ? b.m[1][0] : (k == 1 ? b.m[1][1] : b.m[1][2]);
+        lz = k == 0 ? b.m[2][0] : (k == 1 ? b.m[2][1] : b.m[2][2]);
+    } else {
+        const int i = (best_axis - 6) / 3, j = (best_axis - 6) % 3;
+        const float ux = i == 0 ? a.m[0][0] : (i == 1 ? a.m[0][1] : a.m[0][2]);
+        const float uy = i == 0 ? a.m[1][0] : (i == 1 ? a.m[1][1] : a.m[1][2]);
+        const float uz = i == 0 ? a.m[2][0] : (i == 1 ? a.m[2][1] : a.m[2][2]);
+        const float wx = j == 0 ? b.m[0][0] : (j == 1 ? b.m[0][1] : b.m[0][2]);
+        const float wy = j == 0 ? b.m[1][0] : (j == 1 ? b.m[1][1] : b.m[1][2]);
+        const float wz = j == 0 ? b.m[2][0] : (j == 1 ? b.m[2][1] : b.m[2][2]);
+        lx = __fdiv_rn(sub(mul(uy, wz), mul(uz, wy)), best_len);
+        ly = __fdiv_rn(sub(mul(uz, wx), mul(ux, wz)), best_len);
+        lz = __fdiv_rn(sub(mul(ux, wy), mul(uy, wx)), best_len);
+    }
+    if (best_s > 0.0f) { lx = -lx; ly = -ly; lz = -lz; }  // L pointed from a to b: the normal goes lo -> hi
+    return make_float4(lx, ly, lz, best_pen);
+}
+
 // grid_collision.rs:329-335  (p / cell_size).floor(), IEEE divide
 GSC_DEV float cell_coord_f(float p, float cell_size) { return floorf(__fdiv_rn(p, cell_size)); }
 

@@ -46,7 +46,8 @@ enum { GSC_SPHERE = 0, GSC_BOX = 1, GSC_MESH = 2 };
 /* gsc_config.flags */
 enum {
     GSC_FLAG_TIMING = 1u << 0, /* record per-stage CUDA-event times in gsc_step_out.stage_ms */
-    GSC_FLAG_GRAPH  = 1u << 1  /* replay the step as one CUDA graph (launch-bound small scenes) */
+    GSC_FLAG_GRAPH  = 1u << 1, /* reserved */
+    GSC_FLAG_CONTACTS = 1u << 2 /* also produce a contact (unit normal, depth) per pair -- see gsc_download_contacts */
 };
 
 /* stages of one step, in launch order (names follow the reference's Stopwatch scopes) */
@@ -87,6 +88,7 @@ typedef struct gsc_step_out {
     float    stage_ms[GSC_NUM_STAGES]; /* only with GSC_FLAG_TIMING */
     float    step_ms;        /* device time of the whole step (always) */
     const uint32_t *d_pairs; /* DEVICE pointer: n_pairs x (entity of higher index, entity of lower index) */
+    const float *d_contacts; /* DEVICE pointer: n_pairs x (normal.xyz, depth), same order; NULL without GSC_FLAG_CONTACTS */
 } gsc_step_out;
 
 /* ---- lifetime ---- */
@@ -122,6 +124,20 @@ int gsc_step(gsc_ctx *ctx, gsc_step_out *out);
  * cap_pairs == 0 only queries it. */
 int gsc_download_pairs(gsc_ctx *ctx, uint32_t *dst, uint64_t cap_pairs, int sorted, uint64_t *n_out);
 
+/* Contacts (GSC_FLAG_CONTACTS).  The reference computes boolean collisions only -- penetration depth and contact
+ * normal are planned there (mod.rs:110-113) but do not exist, so there is nothing to be bit-exact WITH: this is the
+ * definition this library adds (parity unpinned; checked against the same definition in oracle/ at 1e-5 relative).
+ * For the pair (hi, lo) = (later volume, earlier volume): `normal` is a unit vector pointing from lo to hi, `depth`
+ * the overlap along it (moving hi by depth * normal separates the two shapes along that axis).
+ *   sphere-sphere : normal = (c_hi - c_lo) / |c_hi - c_lo| ((1,0,0) if the centres coincide); depth = r_hi + r_lo - dist
+ *   sphere-box    : q = OBB::closest_point(centre) (mod.rs:549-568); outside: normal = +-(centre - q)/|centre - q|,
+ *                   depth = r - |centre - q|; centre inside the box (no projection clamped): the face of least
+ *                   penetration, depth = r + that
+ *   box-box       : the axis of least overlap among the 15 SAT axes of OBB::test_obb (mod.rs:443-542), cross axes
+ *                   normalised by |A_i x B_j| and skipped when nearly parallel; depth = that overlap
+ * dst[4*i .. 4*i+3] = (nx, ny, nz, depth) of pair i in the order of gsc_download_pairs(sorted). */
+int gsc_download_contacts(gsc_ctx *ctx, float *dst, uint64_t cap_pairs, int sorted, uint64_t *n_out);
+
 /* ---- stage-level read-back for parity tests (host buffers) ---- */
 enum {
     GSC_DBG_AABB        = 0, /* float[6n]: min xyz, max xyz per collider (AABB::from_collider) */
@@ -145,6 +161,10 @@ int gsc_test_obb_obb(int device, size_t n, const float *a16, const float *b16, u
 int gsc_test_aabb_aabb(int device, size_t n, const float *a6, const float *b6, uint8_t *out);
 /* FnvHasher over GridCell (lib/hash/src/fnv.rs:21-38, grid_collision.rs:523-528); cells as i16 xyz */
 int gsc_fnv1a_gridcell(int device, size_t n, const int16_t *cells3, uint64_t *out);
+/* contact definition above, batched: out4[4*i..] = (normal.xyz, depth); first argument is the later volume `hi` */
+int gsc_contact_sphere_sphere(int device, size_t n, const float *hi4, const float *lo4, float *out4);
+int gsc_contact_sphere_obb(int device, size_t n, const float *s4, const float *obb16, const uint8_t *sphere_is_hi, float *out4);
+int gsc_contact_obb_obb(int device, size_t n, const float *hi16, const float *lo16, float *out4);
 /* the radix sort used on (cell, collider) keys, exposed for testing: stable LSD over `key_bits` bits */
 int gsc_sort_pairs_u32(int device, size_t n, uint32_t *keys, uint32_t *vals, int key_bits);
 

@@ -330,6 +330,127 @@ int orc_test_volume(const orc_bound_volume *a, const orc_bound_volume *b)
 }
 
 /* ------------------------------------------------------------------------ */
+/* contacts (depth / normal) -- NOT in the reference (it only        */
+/* plans them, mod.rs:110-113).  PARITY UNPINNED: these functions define the    */
+/* outputs BASELINE.json's north_star asks for and are the checker of the CUDA  */
+/* implementation of the same definition (include/gunship_collision.h).         */
+/* Convention: `hi` is the later volume of the pair, `lo` the earlier one; the  */
+/* unit normal points from lo to hi, depth is the overlap along it.             */
+/* ------------------------------------------------------------------------ */
+
+void orc_contact_sphere_sphere(const orc_sphere *hi, const orc_sphere *lo, float out[4])
+{
+    const orc_vec3 d = p_sub(hi->center, lo->center);
+    const float dist = sqrtf(v_mag2(d));
+    if (dist > 0.0f) { out[0] = d.x / dist; out[1] = d.y / dist; out[2] = d.z / dist; }
+    else { out[0] = 1.0f; out[1] = 0.0f; out[2] = 0.0f; }
+    out[3] = (hi->radius + lo->radius) - dist;
+}
+
+/* from OBB::closest_point (mod.rs:549-568): outside, the normal is (centre - closest point) normalised; a
+ * centre inside the box leaves through the face of least penetration */
+void orc_contact_sphere_obb(const orc_sphere *s, const orc_obb *o, int sphere_is_hi, float out[4])
+{
+    const orc_vec3 d = p_sub(s->center, o->center);
+    orc_point res = o->center;
+    const float hw[3] = { o->half_widths.x, o->half_widths.y, o->half_widths.z };
+    float proj[3];
+    for (int axis = 0; axis < 3; ++axis) {
+        const orc_vec3 ax = m_col(&o->orientation, axis);
+        const float dist = v_dot(d, ax);
+        proj[axis] = dist;
+        const float c = f_clamp(dist, -hw[axis], hw[axis]);
+        orc_vec3 step = { ax.x * c, ax.y * c, ax.z * c };
+        res = p_add_v(res, step);
+    }
+    const orc_vec3 v = p_sub(s->center, res);
+    const float d2 = v_mag2(v);
+    /* inside <=> no projection was clamped (d2 alone is not robust: the rebuilt point differs by rounding) */
+    const int inside = fabsf(proj[0]) <= hw[0] && fabsf(proj[1]) <= hw[1] && fabsf(proj[2]) <= hw[2];
+    float n[3], depth;
+    if (!inside && d2 > 0.0f) {
+        const float dd = sqrtf(d2);
+        n[0] = v.x / dd; n[1] = v.y / dd; n[2] = v.z / dd;
+        depth = s->radius - dd;
+    } else {
+        int best = 0;
+        float pen = hw[0] - fabsf(proj[0]);
+        for (int i = 1; i < 3; ++i) {
+            const float p = hw[i] - fabsf(proj[i]);
+            if (p < pen) { pen = p; best = i; }
+        }
+        const float sgn = proj[best] < 0.0f ? -1.0f : 1.0f;
+        const orc_vec3 ax = m_col(&o->orientation, best);
+        n[0] = ax.x * sgn; n[1] = ax.y * sgn; n[2] = ax.z * sgn;
+        depth = s->radius + pen;
+    }
+    if (!sphere_is_hi) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
+    out[0] = n[0]; out[1] = n[1]; out[2] = n[2]; out[3] = depth;
+}
+
+/* least-penetration axis of the 15 SAT axes of OBB::test_obb (mod.rs:443-542), `a` = hi, `b` = lo.
+ * Cross axes are normalised by |A_i x B_j| = sqrt(1 - r_ij^2) and skipped when nearly parallel. */
+void orc_contact_obb_obb(const orc_obb *a, const orc_obb *b, float out[4])
+{
+    float r[3][3], abs_r[3][3];
+    for (int row = 0; row < 3; ++row)
+        for (int col = 0; col < 3; ++col)
+            r[row][col] = v_dot(m_col(&a->orientation, row), m_col(&b->orientation, col));
+    orc_vec3 tv = p_sub(b->center, a->center);
+    orc_mat3 at;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            at.m[i][j] = a->orientation.m[j][i];
+    tv = v_mul_m(tv, &at);
+    const float t[3] = { tv.x, tv.y, tv.z };
+    for (int row = 0; row < 3; ++row)
+        for (int col = 0; col < 3; ++col)
+            abs_r[row][col] = fabsf(r[row][col]) + ORC_EPSILON;
+    const float ah[3] = { a->half_widths.x, a->half_widths.y, a->half_widths.z };
+    const float bh[3] = { b->half_widths.x, b->half_widths.y, b->half_widths.z };
+
+    float best_pen = INFINITY, best_s = 0.0f, best_len = 1.0f;
+    int best_kind = 0, best_i = 0, best_j = 0;
+    for (int i = 0; i < 3; ++i) { /* L = A_i */
+        const float rb = bh[0] * abs_r[i][0] + bh[1] * abs_r[i][1] + bh[2] * abs_r[i][2];
+        const float pen = (ah[i] + rb) - fabsf(t[i]);
+        if (pen < best_pen) { best_pen = pen; best_s = t[i]; best_kind = 0; best_i = i; }
+    }
+    for (int i = 0; i < 3; ++i) { /* L = B_i */
+        const float ra = ah[0] * abs_r[0][i] + ah[1] * abs_r[1][i] + ah[2] * abs_r[2][i];
+        const float proj = t[0] * r[0][i] + t[1] * r[1][i] + t[2] * r[2][i];
+        const float pen = (ra + bh[i]) - fabsf(proj);
+        if (pen < best_pen) { best_pen = pen; best_s = proj; best_kind = 1; best_i = i; }
+    }
+    for (int i = 0; i < 3; ++i) { /* L = A_i x B_j, same expressions as mod.rs:463-542 */
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+        for (int j = 0; j < 3; ++j) {
+            const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+            const float ra = ah[i1 < i2 ? i1 : i2] * abs_r[i1 < i2 ? i2 : i1][j] + ah[i1 < i2 ? i2 : i1] * abs_r[i1 < i2 ? i1 : i2][j];
+            const float rb = bh[j1 < j2 ? j1 : j2] * abs_r[i][j1 < j2 ? j2 : j1] + bh[j1 < j2 ? j2 : j1] * abs_r[i][j1 < j2 ? j1 : j2];
+            const float sv = t[i2] * r[i1][j] - t[i1] * r[i2][j];
+            const float len2 = 1.0f - r[i][j] * r[i][j];
+            if (len2 > ORC_EPSILON) {
+                const float len = sqrtf(len2);
+                const float pen = ((ra + rb) - fabsf(sv)) / len;
+                if (pen < best_pen) { best_pen = pen; best_s = sv; best_kind = 2; best_i = i; best_j = j; best_len = len; }
+            }
+        }
+    }
+    orc_vec3 L;
+    if (best_kind == 0) L = m_col(&a->orientation, best_i);
+    else if (best_kind == 1) L = m_col(&b->orientation, best_i);
+    else {
+        const orc_vec3 u = m_col(&a->orientation, best_i), w = m_col(&b->orientation, best_j);
+        L.x = (u.y * w.z - u.z * w.y) / best_len;
+        L.y = (u.z * w.x - u.x * w.z) / best_len;
+        L.z = (u.x * w.y - u.y * w.x) / best_len;
+    }
+    if (best_s > 0.0f) { L.x = -L.x; L.y = -L.y; L.z = -L.z; } /* L pointed from a to b: the normal goes lo -> hi */
+    out[0] = L.x; out[1] = L.y; out[2] = L.z; out[3] = best_pen;
+}
+
+/* ------------------------------------------------------------------------ */
 /* FNV-1a + grid cells                                                       */
 /* ------------------------------------------------------------------------ */
 
@@ -426,6 +547,37 @@ void orc_batch_obb_obb(size_t n, const float *a16, const float *b16, uint8_t *ou
         out[i] = (uint8_t)orc_test_obb_obb(&oa, &ob);
     }
 }
+void orc_batch_contact_sphere_sphere(size_t n, const float *hi, const float *lo, float *out4)
+{
+    for (size_t i = 0; i < n; ++i) {
+        orc_sphere a, b;
+        load_sphere4(hi + 4 * i, &a);
+        load_sphere4(lo + 4 * i, &b);
+        orc_contact_sphere_sphere(&a, &b, out4 + 4 * i);
+    }
+}
+
+void orc_batch_contact_sphere_obb(size_t n, const float *s, const float *o16, const uint8_t *sphere_is_hi, float *out4)
+{
+    for (size_t i = 0; i < n; ++i) {
+        orc_sphere a;
+        orc_obb o;
+        load_sphere4(s + 4 * i, &a);
+        load_obb16(o16 + 16 * i, &o);
+        orc_contact_sphere_obb(&a, &o, sphere_is_hi[i], out4 + 4 * i);
+    }
+}
+
+void orc_batch_contact_obb_obb(size_t n, const float *a16, const float *b16, float *out4)
+{
+    for (size_t i = 0; i < n; ++i) {
+        orc_obb a, b;
+        load_obb16(a16 + 16 * i, &a);
+        load_obb16(b16 + 16 * i, &b);
+        orc_contact_obb_obb(&a, &b, out4 + 4 * i);
+    }
+}
+
 void orc_batch_aabb_aabb(size_t n, const float *a6, const float *b6, uint8_t *out)
 {
     for (size_t i = 0; i < n; ++i) {

@@ -90,6 +90,14 @@ void orc_batch_obb_obb(size_t n, const float *a_obb16, const float *b_obb16, uin
 void orc_batch_aabb_aabb(size_t n, const float *a_minmax6, const float *b_minmax6, uint8_t *out);
 void orc_batch_fnv1a_gridcell(size_t n, const int16_t *cells_xyz, uint64_t *out);
 
+/* ---- contacts (normal.xyz, depth): NOT in the reference -- PARITY UNPINNED (see gunship_oracle.c) ---- */
+void orc_contact_sphere_sphere(const orc_sphere *hi, const orc_sphere *lo, float out[4]);
+void orc_contact_sphere_obb(const orc_sphere *s, const orc_obb *o, int sphere_is_hi, float out[4]);
+void orc_contact_obb_obb(const orc_obb *hi, const orc_obb *lo, float out[4]);
+void orc_batch_contact_sphere_sphere(size_t n, const float *hi_cxyz_r, const float *lo_cxyz_r, float *out4);
+void orc_batch_contact_sphere_obb(size_t n, const float *s_cxyz_r, const float *obb16, const uint8_t *sphere_is_hi, float *out4);
+void orc_batch_contact_obb_obb(size_t n, const float *hi_obb16, const float *lo_obb16, float *out4);
+
 /* ---- the collision system (CollisionSystem::update = bvh_update + GridCollisionSystem::update) ---- */
 typedef struct orc_system orc_system;
 

@@ -64,6 +64,9 @@ def lib():
         L.orc_batch_obb_obb.argtypes = [C.c_size_t, _f32p, _f32p, _u8p]
         L.orc_batch_aabb_aabb.argtypes = [C.c_size_t, _f32p, _f32p, _u8p]
         L.orc_batch_fnv1a_gridcell.argtypes = [C.c_size_t, _i16p, _u64p]
+        L.orc_batch_contact_sphere_sphere.argtypes = [C.c_size_t, _f32p, _f32p, _f32p]
+        L.orc_batch_contact_sphere_obb.argtypes = [C.c_size_t, _f32p, _f32p, _u8p, _f32p]
+        L.orc_batch_contact_obb_obb.argtypes = [C.c_size_t, _f32p, _f32p, _f32p]
         _lib = L
     return _lib
 
@@ -182,6 +185,27 @@ def batch_obb_obb(a, b) -> np.ndarray:
     a, b = _c(a, np.float32), _c(b, np.float32)
     out = np.zeros(a.shape[0], dtype=np.uint8)
     lib().orc_batch_obb_obb(a.shape[0], _p(a, _f32p), _p(b, _f32p), _p(out, _u8p))
+    return out
+
+
+def batch_contact_sphere_sphere(hi, lo) -> np.ndarray:
+    hi, lo = _c(hi, np.float32), _c(lo, np.float32)
+    out = np.zeros((hi.shape[0], 4), dtype=np.float32)
+    lib().orc_batch_contact_sphere_sphere(hi.shape[0], _p(hi, _f32p), _p(lo, _f32p), _p(out, _f32p))
+    return out
+
+
+def batch_contact_sphere_obb(s, o, sphere_is_hi) -> np.ndarray:
+    s, o, f = _c(s, np.float32), _c(o, np.float32), _c(sphere_is_hi, np.uint8)
+    out = np.zeros((s.shape[0], 4), dtype=np.float32)
+    lib().orc_batch_contact_sphere_obb(s.shape[0], _p(s, _f32p), _p(o, _f32p), _p(f, _u8p), _p(out, _f32p))
+    return out
+
+
+def batch_contact_obb_obb(hi, lo) -> np.ndarray:
+    hi, lo = _c(hi, np.float32), _c(lo, np.float32)
+    out = np.zeros((hi.shape[0], 4), dtype=np.float32)
+    lib().orc_batch_contact_obb_obb(hi.shape[0], _p(hi, _f32p), _p(lo, _f32p), _p(out, _f32p))
     return out
 
 

@@ -31,11 +31,25 @@ def test_library_exports_every_header_symbol():
     assert N.load().gsc_abi_version() == 1
 
 
-def test_struct_layouts_match_header():
-    # sizes as the C compiler lays them out (x86-64): see include/gunship_collision.h
-    assert C.sizeof(N.GscConfig) == 40
-    assert C.sizeof(N.GscStepOut) == 8 * 5 + 4 * 2 + 12 + 12 + 4 * 2 + 4 * 6 + 4 + 4 + 8   # 120: d_pairs is 8-aligned
-    assert C.sizeof(N.GscBounds) == 36
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof / offsetof as the C compiler sees the header vs the ctypes mirrors"""
+    import subprocess
+    src = tmp_path / "layout.c"
+    src.write_text('''#include <stdio.h>
+#include <stddef.h>
+#include "gunship_collision.h"
+int main(void) {
+    printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(gsc_config), sizeof(gsc_step_out), sizeof(gsc_bounds),
+           offsetof(gsc_step_out, cell_size), offsetof(gsc_step_out, stage_ms), offsetof(gsc_step_out, d_pairs),
+           offsetof(gsc_bounds, home_x_max));
+    return 0;
+}''')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    want = [C.sizeof(N.GscConfig), C.sizeof(N.GscStepOut), C.sizeof(N.GscBounds), N.GscStepOut.cell_size.offset,
+            N.GscStepOut.stage_ms.offset, N.GscStepOut.d_pairs.offset, N.GscBounds.home_x_max.offset]
+    assert got == want
 
 
 def test_no_cpu_fallback_without_a_device():
