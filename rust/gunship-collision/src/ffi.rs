@@ -8,6 +8,9 @@ pub const GSC_SPHERE: u8 = 0;
 pub const GSC_BOX: u8 = 1;
 pub const GSC_MESH: u8 = 2;
 pub const GSC_FLAG_TIMING: u32 = 1;
+pub const GSC_FLAG_CONTACTS: u32 = 4;
+pub const GSC_MAX_PEERS: usize = 16;
+pub const GSC_IPC_EXPORT_BYTES: usize = 256;
 pub const GSC_NUM_STAGES: usize = 6;
 pub const GSC_HALO_RECORD_BYTES: usize = 96;
 
@@ -40,6 +43,7 @@ pub struct gsc_step_out {
     pub stage_ms: [f32; GSC_NUM_STAGES],
     pub step_ms: f32,
     pub d_pairs: *const u32,
+    pub d_contacts: *const f32,
 }
 
 #[repr(C)]
@@ -63,12 +67,17 @@ extern "C" {
                                       d_scale3: *const f32) -> c_int;
     pub fn gsc_step(ctx: *mut gsc_ctx, out: *mut gsc_step_out) -> c_int;
     pub fn gsc_download_pairs(ctx: *mut gsc_ctx, dst: *mut u32, cap_pairs: u64, sorted: c_int, n_out: *mut u64) -> c_int;
+    pub fn gsc_download_contacts(ctx: *mut gsc_ctx, dst: *mut f32, cap_pairs: u64, sorted: c_int, n_out: *mut u64) -> c_int;
     pub fn gsc_debug_download(ctx: *mut gsc_ctx, what: c_int, dst: *mut c_void, dst_bytes: usize) -> c_int;
     pub fn gsc_test_sphere_sphere(device: c_int, n: usize, a4: *const f32, b4: *const f32, out: *mut u8) -> c_int;
     pub fn gsc_test_sphere_obb(device: c_int, n: usize, s4: *const f32, obb16: *const f32, out: *mut u8) -> c_int;
     pub fn gsc_test_obb_obb(device: c_int, n: usize, a16: *const f32, b16: *const f32, out: *mut u8) -> c_int;
     pub fn gsc_test_aabb_aabb(device: c_int, n: usize, a6: *const f32, b6: *const f32, out: *mut u8) -> c_int;
     pub fn gsc_fnv1a_gridcell(device: c_int, n: usize, cells3: *const i16, out: *mut u64) -> c_int;
+    pub fn gsc_contact_sphere_sphere(device: c_int, n: usize, hi4: *const f32, lo4: *const f32, out4: *mut f32) -> c_int;
+    pub fn gsc_contact_sphere_obb(device: c_int, n: usize, s4: *const f32, obb16: *const f32, sphere_is_hi: *const u8,
+                                  out4: *mut f32) -> c_int;
+    pub fn gsc_contact_obb_obb(device: c_int, n: usize, hi16: *const f32, lo16: *const f32, out4: *mut f32) -> c_int;
     pub fn gsc_sort_pairs_u32(device: c_int, n: usize, keys: *mut u32, vals: *mut u32, key_bits: c_int) -> c_int;
     pub fn gsc_phase_bounds(ctx: *mut gsc_ctx, local: *mut gsc_bounds) -> c_int;
     pub fn gsc_set_global_bounds(ctx: *mut gsc_ctx, global: *const gsc_bounds) -> c_int;
@@ -77,5 +86,10 @@ extern "C" {
     pub fn gsc_halo_select(ctx: *mut gsc_ctx, x_lo: i32, x_hi: i32, d_records: *mut c_void, cap_records: u32,
                            count: *mut u32) -> c_int;
     pub fn gsc_halo_append(ctx: *mut gsc_ctx, count: u32, d_records: *const c_void) -> c_int;
+    pub fn gsc_ipc_export(ctx: *mut gsc_ctx, blob: *mut c_void, blob_bytes: usize) -> c_int;
+    pub fn gsc_ipc_open_peer(ctx: *mut gsc_ctx, peer: u32, blob: *const c_void, blob_bytes: usize) -> c_int;
+    pub fn gsc_halo_push(ctx: *mut gsc_ctx, peer: u32, x_lo: i32, x_hi: i32, peer_n_local: u32) -> c_int;
+    pub fn gsc_halo_sync(ctx: *mut gsc_ctx) -> c_int;
+    pub fn gsc_halo_commit(ctx: *mut gsc_ctx, n_ghost: *mut u32) -> c_int;
     pub fn gsc_phase_finish(ctx: *mut gsc_ctx, out: *mut gsc_step_out) -> c_int;
 }
