@@ -47,6 +47,11 @@ class GscStepOut(C.Structure):
                 ("d_pairs", C.c_void_p), ("d_contacts", C.c_void_p)]
 
 
+class GscAdjacency(C.Structure):
+    _fields_ = [("n_entities", C.c_uint64), ("n_entries", C.c_uint64), ("d_entity", C.c_void_p),
+                ("d_offset", C.c_void_p), ("d_other", C.c_void_p)]
+
+
 class GscBounds(C.Structure):
     _fields_ = [("longest_axis", C.c_float), ("world_min", C.c_float * 3), ("world_max", C.c_float * 3),
                 ("status_flags", C.c_uint32), ("home_x_max", C.c_float)]
@@ -60,7 +65,7 @@ EXPORTS = (
     "gsc_sort_pairs_u32", "gsc_phase_bounds", "gsc_set_global_bounds", "gsc_local_x_range", "gsc_halo_select",
     "gsc_halo_append", "gsc_phase_finish", "gsc_set_x_window", "gsc_ipc_export", "gsc_ipc_open_peer", "gsc_halo_push",
     "gsc_halo_sync", "gsc_halo_commit", "gsc_download_contacts", "gsc_contact_sphere_sphere", "gsc_contact_sphere_obb",
-    "gsc_contact_obb_obb",
+    "gsc_contact_obb_obb", "gsc_build_adjacency", "gsc_download_adjacency",
 )
 
 _lib = None
@@ -88,6 +93,8 @@ def load():
     L.gsc_step.argtypes = [vp, C.POINTER(GscStepOut)]
     L.gsc_download_pairs.argtypes = [vp, u32p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
     L.gsc_debug_download.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.gsc_build_adjacency.argtypes = [vp, C.POINTER(GscAdjacency)]
+    L.gsc_download_adjacency.argtypes = [vp, u32p, u32p, u32p, C.c_uint64, C.c_uint64]
     L.gsc_download_contacts.argtypes = [vp, f32p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
     L.gsc_contact_sphere_sphere.argtypes = [C.c_int, C.c_size_t, f32p, f32p, f32p]
     L.gsc_contact_sphere_obb.argtypes = [C.c_int, C.c_size_t, f32p, f32p, u8p, f32p]

@@ -102,6 +102,17 @@ class CollisionContext:
             self._check(self._lib.gsc_download_contacts(self._h, _ptr(out), n.value, 1 if sorted else 0, C.byref(n)))
         return out
 
+    def adjacency(self):
+        """CollisionCallbackManager::process_collisions' per-entity lists (mod.rs:678-708) as CSR:
+        (entity[m], offset[m+1], other[2*n_pairs]); entity i collides with other[offset[i]:offset[i+1]]."""
+        a = N.GscAdjacency()
+        self._check(self._lib.gsc_build_adjacency(self._h, C.byref(a)))
+        ent = np.zeros(int(a.n_entities), dtype=np.uint32)
+        off = np.zeros(int(a.n_entities) + 1, dtype=np.uint32)
+        oth = np.zeros(int(a.n_entries), dtype=np.uint32)
+        self._check(self._lib.gsc_download_adjacency(self._h, _ptr(ent), _ptr(off), _ptr(oth), ent.shape[0], oth.shape[0]))
+        return ent, off, oth
+
     def pairs_packed(self, sorted: bool = True) -> np.ndarray:
         p = self.pairs(sorted).astype(np.uint64)
         return (p[:, 0] << np.uint64(32)) | p[:, 1]

@@ -25,9 +25,10 @@ thread_local std::string g_create_error;
 
 constexpr int kGridStrideBlocks = 148 * 8;  // 148 SMs x resident CTAs for the grid-stride kernels
 
-struct Buf {
-    void *p = nullptr;
-    size_t bytes = 0;
+// device allocations freed when the scope ends
+struct Scratch {
+    void *p[4] = { nullptr, nullptr, nullptr, nullptr };
+    ~Scratch() { for (void *q : p) if (q) cudaFree(q); }
 };
 
 }  // namespace
@@ -62,6 +63,10 @@ struct gsc_ctx {
     uint2 *d_pairs = nullptr, *d_cand_ss = nullptr, *d_cand_so = nullptr, *d_cand_oo = nullptr;
     uint2 *d_pairs_sorted = nullptr;
     float4 *d_contacts = nullptr, *d_contacts_sorted = nullptr;  // GSC_FLAG_CONTACTS
+    // adjacency (CSR) of the last step's pair set, built on demand
+    uint32_t *d_adj_entity = nullptr, *d_adj_offset = nullptr, *d_adj_other = nullptr;
+    uint64_t adj_cap = 0, adj_entities = 0, adj_entries = 0;
+    bool adj_valid = false;
     uint32_t *d_perm = nullptr;  // permutation that sorts the pairs of the last step
     bool perm_valid = false;
     FrameBlock *d_fb = nullptr;
@@ -271,7 +276,7 @@ void gsc_destroy(gsc_ctx *c)
         }
     void *bufs[] = { c->d_entity, c->d_gidx, c->d_kind, c->d_offset, c->d_size, c->d_pos, c->d_quat, c->d_scale, c->d_rec,
                      c->d_rec_sorted, c->d_qrec_sorted, c->d_obb, c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1], c->d_cell_start,
-                     c->d_wide, c->d_gaps, c->d_pairs, c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->d_pairs_sorted, c->d_contacts, c->d_contacts_sorted, c->d_perm, c->d_fb, c->d_sort_scratch,
+                     c->d_wide, c->d_gaps, c->d_pairs, c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->d_pairs_sorted, c->d_contacts, c->d_contacts_sorted, c->d_perm, c->d_adj_entity, c->d_adj_offset, c->d_adj_other, c->d_fb, c->d_sort_scratch,
                      c->d_halo_rec, c->d_halo_obb, c->d_halo_count };
     for (void *b : bufs)
         if (b) cudaFree(b);
@@ -411,6 +416,7 @@ static int stage_finish(gsc_ctx *c, gsc_step_out *out)
     CU(c, cudaStreamSynchronize(s));
     c->bounds_done = false;
     c->perm_valid = false;
+    c->adj_valid = false;
 
     const FrameBlock &h = *c->h_fb;
     c->last_pairs = std::min<uint64_t>(h.n_pairs, c->max_pairs);
@@ -791,6 +797,158 @@ int gsc_download_contacts(gsc_ctx *c, float *dst, uint64_t cap_pairs, int sorted
     return GSC_OK;
 }
 
+// ---- adjacency: what CollisionCallbackManager::process_collisions builds (mod.rs:678-708) ---------------------
+}  // extern "C"
+
+namespace {
+// every pair (a, b) contributes a -> b and b -> a (mod.rs:687-690)
+__global__ void k_adj_expand(const uint2 *pairs, uint32_t h, uint32_t *first, uint32_t *second)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= h) return;
+    const uint2 p = pairs[i];
+    first[2 * i] = p.x; second[2 * i] = p.y;
+    first[2 * i + 1] = p.y; second[2 * i + 1] = p.x;
+}
+__global__ void k_gather_u32(const uint32_t *src, const uint32_t *perm, uint32_t n, uint32_t *out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[perm[i]];
+}
+constexpr int kHeadTile = 1024;
+// pass 1: number of list heads (first[i] != first[i-1]) per tile; pass 3: their ranks -> entity / offset arrays
+__global__ void __launch_bounds__(256) k_adj_heads(const uint32_t *sorted_first, uint32_t m, uint32_t *tile_count,
+                                                 const uint32_t *tile_base, uint32_t *entity, uint32_t *offset)
+{
+    __shared__ uint32_t s_warp[8];
+    const uint32_t base = blockIdx.x * kHeadTile + threadIdx.x * 4;
+    uint32_t f[4], cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t i = base + k;
+        f[k] = (i < m && (i == 0 || sorted_first[i] != sorted_first[i - 1])) ? 1u : 0u;
+        cnt += f[k];
+    }
+    uint32_t total = 0;
+    uint32_t run = block_excl_scan256(cnt, s_warp, &total);
+    if (!tile_base) {
+        if (threadIdx.x == 0) tile_count[blockIdx.x] = total;
+        return;
+    }
+    run += tile_base[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (f[k]) {
+            entity[run] = sorted_first[base + k];
+            offset[run] = base + k;
+            ++run;
+        }
+}
+// pass 2: exclusive scan of the tile counts on one CTA; total -> *n_heads, offset[total] = m
+__global__ void __launch_bounds__(256) k_adj_scan_tiles(uint32_t *tile_count, uint32_t tiles, uint32_t m, uint32_t *n_heads,
+                                                      uint32_t *offset)
+{
+    __shared__ uint32_t s_warp[8];
+    uint32_t carry = 0;
+    for (uint32_t b = 0; b < tiles; b += 256) {
+        const uint32_t i = b + threadIdx.x;
+        const uint32_t v = i < tiles ? tile_count[i] : 0u;
+        uint32_t total = 0;
+        const uint32_t e = block_excl_scan256(v, s_warp, &total);
+        if (i < tiles) tile_count[i] = carry + e;
+        carry += total;
+    }
+    if (threadIdx.x == 0) {
+        *n_heads = carry;
+        offset[carry] = m;
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int gsc_build_adjacency(gsc_ctx *c, gsc_adjacency *out)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!out) return fail(c, GSC_ERR_INVALID, "gsc_build_adjacency: null output");
+    memset(out, 0, sizeof *out);
+    const uint64_t h = c->last_pairs;
+    if (2 * h >= (1ull << 30)) return fail(c, GSC_ERR_CAPACITY, "gsc_build_adjacency supports < 2^29 pairs");
+    const uint32_t m = (uint32_t)(2 * h);
+    if (!c->adj_valid) {
+        cudaStream_t s = c->stream;
+        if (c->adj_cap < m + 1ull) {
+            for (uint32_t **p : { &c->d_adj_entity, &c->d_adj_offset, &c->d_adj_other }) {
+                if (*p) cudaFree(*p);
+                *p = nullptr;
+            }
+            c->adj_cap = std::max<uint64_t>(m + 1ull, 2 * c->max_pairs / 4 + 1024);
+            CU(c, dmalloc(&c->d_adj_entity, c->adj_cap));
+            CU(c, dmalloc(&c->d_adj_offset, c->adj_cap + 1));
+            CU(c, dmalloc(&c->d_adj_other, c->adj_cap));
+        }
+        c->adj_entities = 0;
+        c->adj_entries = m;
+        if (m) {
+            uint32_t *first = nullptr, *second = nullptr, *k[2] = { nullptr, nullptr }, *v[2] = { nullptr, nullptr }, *tiles_buf = nullptr;
+            const uint32_t tiles = (m + kHeadTile - 1) / kHeadTile;
+            Scratch sc[2];
+            CU(c, dmalloc(&first, m)); sc[0].p[0] = first;
+            CU(c, dmalloc(&second, m)); sc[0].p[1] = second;
+            CU(c, dmalloc(&tiles_buf, tiles + 2)); sc[0].p[2] = tiles_buf;
+            for (int i = 0; i < 2; ++i) {
+                CU(c, dmalloc(&k[i], m)); sc[1].p[i] = k[i];
+                CU(c, dmalloc(&v[i], m)); sc[1].p[2 + i] = v[i];
+            }
+            const uint32_t hb = ((uint32_t)h + 255) / 256, mb = (m + 255) / 256;
+            k_adj_expand<<<hb, 256, 0, s>>>(c->d_pairs, (uint32_t)h, first, second);
+            // LSD over (first, second): by the neighbour first, then (stable) by the owning entity
+            CU(c, cudaMemcpyAsync(k[0], second, (size_t)m * 4, cudaMemcpyDeviceToDevice, s));
+            int w1 = 0, w2 = 0;
+            if (int rc = sort_standalone(c, s, m, k, v, true, 32, &w1)) return rc;
+            if (w1 != 0) { std::swap(k[0], k[1]); std::swap(v[0], v[1]); }
+            k_gather_u32<<<mb, 256, 0, s>>>(first, v[0], m, k[0]);
+            if (int rc = sort_standalone(c, s, m, k, v, false, 32, &w2)) return rc;
+            // k[w2] = owning entity of every entry, v[w2] = its position in the expanded list
+            k_gather_u32<<<mb, 256, 0, s>>>(second, v[w2], m, c->d_adj_other);
+            k_adj_heads<<<tiles, 256, 0, s>>>(k[w2], m, tiles_buf, nullptr, nullptr, nullptr);
+            k_adj_scan_tiles<<<1, 256, 0, s>>>(tiles_buf, tiles, m, tiles_buf + tiles, c->d_adj_offset);
+            k_adj_heads<<<tiles, 256, 0, s>>>(k[w2], m, nullptr, tiles_buf, c->d_adj_entity, c->d_adj_offset);
+            uint32_t n_heads = 0;
+            CU(c, cudaMemcpyAsync(&n_heads, tiles_buf + tiles, 4, cudaMemcpyDeviceToHost, s));
+            CU(c, cudaStreamSynchronize(s));
+            CU(c, cudaGetLastError());
+            c->adj_entities = n_heads;
+        }
+        c->adj_valid = true;
+    }
+    out->n_entities = c->adj_entities;
+    out->n_entries = c->adj_entries;
+    out->d_entity = c->d_adj_entity;
+    out->d_offset = c->d_adj_offset;
+    out->d_other = c->d_adj_other;
+    return GSC_OK;
+}
+
+int gsc_download_adjacency(gsc_ctx *c, uint32_t *entity, uint32_t *offset, uint32_t *other, uint64_t cap_entities,
+                           uint64_t cap_entries)
+{
+    gsc_adjacency a;
+    if (int rc = gsc_build_adjacency(c, &a)) return rc;
+    if (cap_entities < a.n_entities || cap_entries < a.n_entries)
+        return fail(c, GSC_ERR_CAPACITY, "gsc_download_adjacency: need room for %llu entities and %llu entries",
+                    (unsigned long long)a.n_entities, (unsigned long long)a.n_entries);
+    if (a.n_entries == 0) {
+        if (offset) offset[0] = 0;
+        return GSC_OK;
+    }
+    if (!entity || !offset || !other) return fail(c, GSC_ERR_INVALID, "gsc_download_adjacency: null array");
+    CU(c, cudaMemcpy(entity, a.d_entity, a.n_entities * 4, cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(offset, a.d_offset, (a.n_entities + 1) * 4, cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(other, a.d_other, a.n_entries * 4, cudaMemcpyDeviceToHost));
+    return GSC_OK;
+}
+
 int gsc_debug_download(gsc_ctx *c, int what, void *dst, size_t dst_bytes)
 {
     if (int rc = check_ctx(c)) return rc;
@@ -830,10 +988,6 @@ int gsc_debug_download(gsc_ctx *c, int what, void *dst, size_t dst_bytes)
 }  // extern "C"
 
 namespace {
-struct Scratch {
-    void *p[4] = { nullptr, nullptr, nullptr, nullptr };
-    ~Scratch() { for (void *q : p) if (q) cudaFree(q); }
-};
 int batch_fail(const char *what, cudaError_t e) { return fail(nullptr, GSC_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e)); }
 #define BT(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return batch_fail(#expr, e_); } while (0)
 

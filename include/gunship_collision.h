@@ -138,6 +138,23 @@ int gsc_download_pairs(gsc_ctx *ctx, uint32_t *dst, uint64_t cap_pairs, int sort
  * dst[4*i .. 4*i+3] = (nx, ny, nz, depth) of pair i in the order of gsc_download_pairs(sorted). */
 int gsc_download_contacts(gsc_ctx *ctx, float *dst, uint64_t cap_pairs, int sorted, uint64_t *n_out);
 
+/* ---- the consumer of the pair set: CollisionCallbackManager::process_collisions (mod.rs:678-708) builds, for
+ *      every entity, the list of entities it collides with (each pair contributes both directions, :687-690) and
+ *      invokes the callbacks with (entity, &[others]).  gsc_build_adjacency produces those lists on the device as
+ *      CSR: entity i of d_entity (ascending) collides with d_other[d_offset[i] .. d_offset[i+1]) (ascending; the
+ *      reference's order is a HashMap iteration order, i.e. unspecified).  Valid until the next step. ---- */
+typedef struct gsc_adjacency {
+    uint64_t n_entities;      /* entities with at least one collision */
+    uint64_t n_entries;       /* 2 * n_pairs */
+    const uint32_t *d_entity; /* DEVICE [n_entities] */
+    const uint32_t *d_offset; /* DEVICE [n_entities + 1] */
+    const uint32_t *d_other;  /* DEVICE [n_entries] */
+} gsc_adjacency;
+int gsc_build_adjacency(gsc_ctx *ctx, gsc_adjacency *out);
+/* same, copied to host arrays (entity[cap_entities], offset[cap_entities + 1], other[cap_entries]) */
+int gsc_download_adjacency(gsc_ctx *ctx, uint32_t *entity, uint32_t *offset, uint32_t *other, uint64_t cap_entities,
+                           uint64_t cap_entries);
+
 /* ---- stage-level read-back for parity tests (host buffers) ---- */
 enum {
     GSC_DBG_AABB        = 0, /* float[6n]: min xyz, max xyz per collider (AABB::from_collider) */

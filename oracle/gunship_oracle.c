@@ -1063,6 +1063,42 @@ uint64_t orc_last_cell_entries(const orc_system *s) { return s->last_entries; }
 uint32_t orc_last_wide_volumes(const orc_system *s) { return s->last_wide; }
 uint32_t orc_last_out_of_range(const orc_system *s) { return s->last_oor; }
 
+/* CollisionCallbackManager::process_collisions, the consumer of the pair set (mod.rs:678-708): every pair
+ * (entity, other) appends `other` to entity's list and `entity` to other's list (:687-690); callbacks then get
+ * (entity, &[others]) per entity with a non-empty list (:694-705).  HashMap iteration order is unspecified in the
+ * reference, so the lists are reported sorted: entities ascending, each list ascending.
+ * Returns the number of entities; entity[cap_e], offset[cap_e + 1], other[2 * n_pairs]. */
+static int cmp_u64_pair(const void *a, const void *b)
+{
+    const uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+uint64_t orc_process_collisions(orc_system *s, uint32_t *entity, uint32_t *offset, uint32_t *other, uint64_t cap_entities)
+{
+    const uint64_t h = orc_collisions_sorted(s, NULL, 0);
+    uint64_t *pairs = malloc((h ? h : 1) * sizeof(uint64_t));
+    uint64_t *ent = malloc((h ? 2 * h : 1) * sizeof(uint64_t));
+    orc_collisions_sorted(s, pairs, h);
+    for (uint64_t i = 0; i < h; ++i) {
+        const uint64_t a = pairs[i] >> 32, b = pairs[i] & 0xffffffffu;
+        ent[2 * i] = (a << 32) | b;      /* a's list gets b */
+        ent[2 * i + 1] = (b << 32) | a;  /* b's list gets a */
+    }
+    qsort(ent, 2 * h, sizeof(uint64_t), cmp_u64_pair);
+    uint64_t n = 0;
+    for (uint64_t i = 0; i < 2 * h; ++i) {
+        if (i == 0 || (ent[i] >> 32) != (ent[i - 1] >> 32)) {
+            if (n < cap_entities) { entity[n] = (uint32_t)(ent[i] >> 32); offset[n] = (uint32_t)i; }
+            ++n;
+        }
+        other[i] = (uint32_t)(ent[i] & 0xffffffffu);
+    }
+    if (n <= cap_entities) offset[n] = (uint32_t)(2 * h);
+    free(pairs);
+    free(ent);
+    return n;
+}
+
 /* SURVEY F9 second oracle */
 uint64_t orc_brute_force_sorted(orc_system *s, uint64_t *out, uint64_t cap)
 {

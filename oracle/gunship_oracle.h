@@ -127,6 +127,11 @@ uint64_t orc_last_cell_entries(const orc_system *s); /* (cell, volume) insertion
 uint32_t orc_last_wide_volumes(const orc_system *s); /* volumes whose AABB spanned >2 cells on an axis (debug_assert :403-410) */
 uint32_t orc_last_out_of_range(const orc_system *s); /* world_to_grid results that saturated i16 */
 
+/* CollisionCallbackManager::process_collisions (mod.rs:678-708): per-entity lists of colliding entities as CSR,
+ * entities and lists ascending.  Returns the entity count (call with cap_entities = 0 and `other` sized
+ * 2 * n_pairs to query). */
+uint64_t orc_process_collisions(orc_system *s, uint32_t *entity, uint32_t *offset, uint32_t *other, uint64_t cap_entities);
+
 /* second oracle: O(N^2) over the volumes built by orc_bvh_update:
  * { (E[i],E[j]) : j<i, test_volume(V[i],V[j]) }, sorted ascending packed u64. */
 uint64_t orc_brute_force_sorted(orc_system *s, uint64_t *out, uint64_t cap);

@@ -47,6 +47,15 @@ pub struct gsc_step_out {
 }
 
 #[repr(C)]
+pub struct gsc_adjacency {
+    pub n_entities: u64,
+    pub n_entries: u64,
+    pub d_entity: *const u32,
+    pub d_offset: *const u32,
+    pub d_other: *const u32,
+}
+
+#[repr(C)]
 pub struct gsc_bounds {
     pub longest_axis: f32,
     pub world_min: [f32; 3],
@@ -68,6 +77,9 @@ extern "C" {
     pub fn gsc_step(ctx: *mut gsc_ctx, out: *mut gsc_step_out) -> c_int;
     pub fn gsc_download_pairs(ctx: *mut gsc_ctx, dst: *mut u32, cap_pairs: u64, sorted: c_int, n_out: *mut u64) -> c_int;
     pub fn gsc_download_contacts(ctx: *mut gsc_ctx, dst: *mut f32, cap_pairs: u64, sorted: c_int, n_out: *mut u64) -> c_int;
+    pub fn gsc_build_adjacency(ctx: *mut gsc_ctx, out: *mut gsc_adjacency) -> c_int;
+    pub fn gsc_download_adjacency(ctx: *mut gsc_ctx, entity: *mut u32, offset: *mut u32, other: *mut u32, cap_entities: u64,
+                                  cap_entries: u64) -> c_int;
     pub fn gsc_debug_download(ctx: *mut gsc_ctx, what: c_int, dst: *mut c_void, dst_bytes: usize) -> c_int;
     pub fn gsc_test_sphere_sphere(device: c_int, n: usize, a4: *const f32, b4: *const f32, out: *mut u8) -> c_int;
     pub fn gsc_test_sphere_obb(device: c_int, n: usize, s4: *const f32, obb16: *const f32, out: *mut u8) -> c_int;

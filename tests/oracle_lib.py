@@ -141,6 +141,18 @@ class OracleSystem:
         lib().orc_brute_force_sorted(self._h, _p(out, _u64p), n)
         return out[:n]
 
+    def process_collisions(self):
+        """(entity, offset, other) CSR of CollisionCallbackManager::process_collisions (mod.rs:678-708)."""
+        L = lib()
+        L.orc_process_collisions.restype = C.c_uint64
+        L.orc_process_collisions.argtypes = [C.c_void_p, _u32p, _u32p, _u32p, C.c_uint64]
+        h = int(L.orc_collisions_sorted(self._h, None, 0))
+        other = np.zeros(max(2 * h, 1), dtype=np.uint32)
+        ent = np.zeros(max(2 * h, 1), dtype=np.uint32)
+        off = np.zeros(2 * h + 2, dtype=np.uint32)
+        n = int(L.orc_process_collisions(self._h, _p(ent, _u32p), _p(off, _u32p), _p(other, _u32p), 2 * h + 1))
+        return ent[:n].copy(), off[:n + 1].copy(), other[:2 * h].copy()
+
     def stats(self) -> dict:
         L = lib()
         return {"candidates": int(L.orc_last_candidates(self._h)), "cell_entries": int(L.orc_last_cell_entries(self._h)),
