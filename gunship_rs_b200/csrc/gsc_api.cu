@@ -142,8 +142,9 @@ inline uint32_t tiles_for(uint32_t n) { return (n + kSortTile - 1) / kSortTile; 
 
 // Runs the radix passes on `n` (key, value) pairs.  Passes beyond ctl->num_passes exit on the device.
 // scratch = [kRadix * tiles] tile histogram + [kRadix] digit totals
+// `have_pass0_hist`: the producer of the keys (k_cell_keys) already filled the tile histogram of pass 0
 void launch_sort(cudaStream_t s, uint32_t n, uint32_t *keys[2], uint32_t *vals[2], bool first_vals_identity,
-                 int max_passes, const SortControl *ctl, uint32_t *scratch)
+                 int max_passes, const SortControl *ctl, uint32_t *scratch, bool have_pass0_hist = false)
 {
     const uint32_t tiles = tiles_for(n);
     if (tiles == 0) return;
@@ -151,7 +152,7 @@ void launch_sort(cudaStream_t s, uint32_t n, uint32_t *keys[2], uint32_t *vals[2
     for (int pass = 0; pass < max_passes; ++pass) {
         const int in = pass & 1, out = in ^ 1;
         const uint32_t *vin = (pass == 0 && first_vals_identity) ? nullptr : vals[in];
-        k_radix_upsweep<<<tiles, kSortThreads, 0, s>>>(keys[in], n, pass, ctl, tile_hist, tiles);
+        if (pass > 0 || !have_pass0_hist) k_radix_upsweep<<<tiles, kSortThreads, 0, s>>>(keys[in], n, pass, ctl, tile_hist, tiles);
         k_radix_scan<<<kRadix, 256, 0, s>>>(tile_hist, tiles, pass, ctl, digit_total);
         k_radix_downsweep<<<tiles, kSortThreads, 0, s>>>(keys[in], vin, keys[out], vals[out], n, pass, ctl, tile_hist,
                                                         digit_total, tiles);
@@ -383,10 +384,10 @@ static int stage_finish(gsc_ctx *c, gsc_step_out *out)
     FrameBlock *fb = c->d_fb;
     k_grid_setup<<<1, 32, 0, s>>>(fb, c->max_cells, n_total, c->have_window ? 1 : 0, c->win_lo, c->win_hi);
     if (n_total) {
-        const uint32_t kb = std::min<uint32_t>((n_total + kKeyThreads - 1) / kKeyThreads, kGridStrideBlocks);
-        k_cell_keys<<<kb, kKeyThreads, 0, s>>>(n_total, c->d_rec, c->d_keys[0], c->d_wide, fb);
+        k_cell_keys<<<tiles_for(n_total), kKeyThreads, 0, s>>>(n_total, c->d_rec, c->d_keys[0], c->d_wide, c->d_sort_scratch,
+                                                              tiles_for(n_total), fb);
         if (timing) CU(c, cudaEventRecord(c->ev[2], s));
-        launch_sort(s, n_total, c->d_keys, c->d_vals, true, kMaxPasses, &fb->sort, c->d_sort_scratch);
+        launch_sort(s, n_total, c->d_keys, c->d_vals, true, kMaxPasses, &fb->sort, c->d_sort_scratch, true);
         if (timing) CU(c, cudaEventRecord(c->ev[3], s));
         const uint32_t tb = (n_total + 1 + kTableThreads - 1) / kTableThreads;
         SortedVolumes sv{ c->d_rec_sorted, c->d_qrec_sorted };

@@ -339,13 +339,27 @@ GSC_DEV bool home_cell(const Volume &v, const GridParams &g, int c_mn[3], int c_
 // multi-GPU partition are contiguous key ranges and cells of one (x,y) row are contiguous in z.
 constexpr int kKeyThreads = 256;
 
+// One CTA per sort tile (kSortTile volumes), so that the digit counts of the FIRST radix pass come for free:
+// tile_hist[d * num_tiles + tile] is what k_radix_upsweep would compute for pass 0.
 __global__ void __launch_bounds__(kKeyThreads)
 k_cell_keys(uint32_t n_total, const float4 *__restrict__ rec, uint32_t *__restrict__ keys,
-            uint32_t *__restrict__ wide_list, FrameBlock *__restrict__ fb)
+            uint32_t *__restrict__ wide_list, uint32_t *__restrict__ tile_hist, uint32_t num_tiles,
+            FrameBlock *__restrict__ fb)
 {
+    constexpr int WARPS = kKeyThreads / 32;
+    __shared__ uint32_t s_hist[WARPS][kRadix];
     const GridParams g = fb->grid;
     if (!g.valid) return;
-    for (uint32_t i = blockIdx.x * kKeyThreads + threadIdx.x; i < n_total; i += gridDim.x * kKeyThreads) {
+    const int tid = threadIdx.x, warp = tid >> 5;
+#pragma unroll
+    for (int i = 0; i < WARPS * kRadix / (4 * kKeyThreads); ++i)
+        reinterpret_cast<uint4 *>(&s_hist[0][0])[tid + i * kKeyThreads] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    const uint32_t tile = blockIdx.x, tile_base = tile * (uint32_t)kSortTile;
+#pragma unroll 4
+    for (int j = 0; j < kSortTile / kKeyThreads; ++j) {
+        const uint32_t i = tile_base + j * kKeyThreads + tid;
+        if (i >= n_total) break;
         const Volume v = volume_decode(__ldg(rec + 2 * (size_t)i), __ldg(rec + 2 * (size_t)i + 1));
         int c0[3], c1[3];
         const bool wide = home_cell(v, g, c0, c1);
@@ -362,7 +376,13 @@ k_cell_keys(uint32_t n_total, const float4 *__restrict__ rec, uint32_t *__restri
             key = ((uint32_t)c0[0] * (uint32_t)g.dims[1] + (uint32_t)c0[1]) * (uint32_t)g.dims[2] + (uint32_t)c0[2];
         }
         keys[i] = key;
+        atomicAdd(&s_hist[warp][key & 255u], 1u);
     }
+    __syncthreads();
+    uint32_t c = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) c += s_hist[w][tid];
+    tile_hist[(size_t)tid * num_tiles + tile] = c;
 }
 
 // Cell-ordered volumes, the array k_pairs streams (one 32 B record = one DRAM sector per volume):

@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(256)
 k_radix_scan(uint32_t *__restrict__ tile_hist, uint32_t num_tiles, int pass, const SortControl *__restrict__ ctl,
              uint32_t *__restrict__ digit_total)
 {
-    __shared__ uint32_t s_row[kScanChunk];
+    constexpr int PER = kScanChunk / 256;                 // entries per thread
+    __shared__ uint32_t s_row[kScanChunk + kScanChunk / PER];  // padded: entry i lives at i + i / PER (no bank conflicts)
     __shared__ uint32_t s_warp[8];
     if (pass >= ctl->num_passes) return;
     uint32_t *row = tile_hist + (size_t)blockIdx.x * num_tiles;
@@ -112,24 +113,24 @@ k_radix_scan(uint32_t *__restrict__ tile_hist, uint32_t num_tiles, int pass, con
     uint32_t carry = 0;
     for (uint32_t base = 0; base < num_tiles; base += kScanChunk) {
         const uint32_t cnt = min((uint32_t)kScanChunk, num_tiles - base);
-        for (uint32_t i = tid; i < kScanChunk; i += 256) s_row[i] = i < cnt ? row[base + i] : 0u;
+        for (uint32_t i = tid; i < kScanChunk; i += 256) s_row[i + i / PER] = i < cnt ? row[base + i] : 0u;
         __syncthreads();
         // thread t owns 16 consecutive entries
-        uint32_t v[kScanChunk / 256], sum = 0;
+        uint32_t v[PER], sum = 0;
 #pragma unroll
-        for (int k = 0; k < kScanChunk / 256; ++k) {
-            v[k] = s_row[tid * (kScanChunk / 256) + k];
+        for (int k = 0; k < PER; ++k) {
+            v[k] = s_row[tid * (PER + 1) + k];
             sum += v[k];
         }
         uint32_t total = 0;
         uint32_t run = carry + block_excl_scan256(sum, s_warp, &total);
 #pragma unroll
-        for (int k = 0; k < kScanChunk / 256; ++k) {
-            s_row[tid * (kScanChunk / 256) + k] = run;
+        for (int k = 0; k < PER; ++k) {
+            s_row[tid * (PER + 1) + k] = run;
             run += v[k];
         }
         __syncthreads();
-        for (uint32_t i = tid; i < cnt; i += 256) row[base + i] = s_row[i];
+        for (uint32_t i = tid; i < cnt; i += 256) row[base + i] = s_row[i + i / PER];
         carry += total;
         __syncthreads();
     }
