@@ -324,7 +324,7 @@ def main():
         "p50_step_ms": float(np.median(dev_ms)), "device_ms_per_step": float(np.mean(dev_ms)),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": 1e3 * wall_e2e / args.steps,
                 "h2d_bytes_per_step": n * 28, "d2h_bytes_per_step": int(d2h / args.steps)},
-        "gpu_launches": 21 * args.steps,
+        "gpu_launches": 19 * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic["bytes"] if traffic else None,

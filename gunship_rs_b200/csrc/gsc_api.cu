@@ -399,12 +399,12 @@ static int stage_finish(gsc_ctx *c, gsc_step_out *out)
         const uint32_t pb = (n_total + kPairThreads - 1) / kPairThreads;
         k_pairs<<<pb, kPairThreads, 0, s>>>(n_total, c->d_keys[0], c->d_keys[1], sv, c->d_cell_start, po, fb);
         if (timing) CU(c, cudaEventRecord(c->ev[5], s));
-        k_narrow_sphere_sphere<<<kGridStrideBlocks, kNarrowThreads, 0, s>>>(c->d_cand_ss, c->max_cands, c->d_rec, c->d_pairs,
-                                                                          c->d_contacts, c->max_pairs, fb);
-        k_narrow_sphere_obb<<<kGridStrideBlocks, kNarrowThreads, 0, s>>>(c->d_cand_so, c->max_cands, c->d_rec, c->d_obb,
-                                                                       c->d_pairs, c->d_contacts, c->max_pairs, fb);
-        k_narrow_obb_obb<<<kGridStrideBlocks, kNarrowThreads, 0, s>>>(c->d_cand_oo, c->max_cands, c->d_obb, c->d_pairs,
-                                                                    c->d_contacts, c->max_pairs, fb);
+        if (c->d_contacts)
+            k_narrow<true><<<148 * 4, kNarrowThreads, 0, s>>>(c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands, c->d_rec,
+                                                            c->d_obb, c->d_pairs, c->d_contacts, c->max_pairs, fb);
+        else
+            k_narrow<false><<<148 * 4, kNarrowThreads, 0, s>>>(c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands, c->d_rec,
+                                                             c->d_obb, c->d_pairs, nullptr, c->max_pairs, fb);
         k_wide_pairs<<<kGridStrideBlocks, kNarrowThreads, 0, s>>>(c->n_local, c->d_wide, c->d_rec, c->d_obb, c->d_pairs,
                                                                 c->d_contacts, c->max_pairs, fb);
         if (timing) CU(c, cudaEventRecord(c->ev[6], s));

@@ -7,8 +7,7 @@
 //   HashMap<GridCell, Vec<..>> grouping (grid_collision.rs:434)  -> k_radix_upsweep/scan/downsweep (gsc_sort.cuh)
 //   cell lookup                                                  -> k_cell_table_permute
 //   test_cell candidate generation + HashMap dedupe (:439-441,
-//   :497-511) + BoundVolume::test (bounding_volume.rs:124-132)   -> k_pairs, k_narrow_sphere_obb,
-//                                                                   k_narrow_obb_obb, k_wide_pairs
+//   :497-511) + BoundVolume::test (bounding_volume.rs:124-132)   -> k_pairs, k_narrow, k_wide_pairs
 //
 // Why neighbour search instead of the reference's 8-corner insertion: with cell = longest AABB
 // extent every AABB spans <= 2 cells per axis, so two volumes share a corner cell iff their home
@@ -88,6 +87,8 @@ struct FrameBlock {
     uint32_t xrange[2];  // ~(min home x + 32768), (max home x + 32768) of local volumes
     uint32_t n_gaps;      // long empty key gaps queued for k_fill_gaps
     uint32_t n_ghost_in;  // ghosts written into this context by peer GPUs this step (k_halo_push, system-scope atomic)
+    uint32_t narrow_ticket;  // work queue of k_narrow (chunks of the three candidate lists)
+    uint32_t pad1;
     GridParams grid;
     SortControl sort;
 };
@@ -725,99 +726,75 @@ constexpr int kNarrowThreads = 256;
 constexpr int kNarrowWarps = kNarrowThreads / 32;
 constexpr int kNarrowCap = 96;
 
-// Sphere::test_sphere (mod.rs:383-389): later.test_sphere(earlier); spheres come from the volume records
-__global__ void __launch_bounds__(kNarrowThreads)
-k_narrow_sphere_sphere(const uint2 *__restrict__ cand, unsigned long long cap_cands, const float4 *__restrict__ rec,
-                       uint2 *__restrict__ pairs, float4 *__restrict__ contacts, unsigned long long cap_pairs,
-                       FrameBlock *__restrict__ fb)
+// All three shape tests in ONE persistent kernel over a work queue of candidate chunks: box-box chunks first
+// (the long SAT tests), then sphere-box, then sphere-sphere.  Run as three kernels each of them was latency
+// bound with the GPU to itself (issue 9-22%, DRAM 38-58% of peak: one random 128 B line per record); mixed in
+// one grid, CTAs doing SAT arithmetic overlap with CTAs waiting on record gathers.
+constexpr int kNarrowChunk = kNarrowThreads * 2;  // candidates per ticket
+
+template <bool CONTACTS>
+__global__ void __launch_bounds__(kNarrowThreads, 4)
+k_narrow(const uint2 *__restrict__ cand_ss, const uint2 *__restrict__ cand_so, const uint2 *__restrict__ cand_oo,
+         unsigned long long cap_cands, const float4 *__restrict__ rec, const float4 *__restrict__ obb,
+         uint2 *__restrict__ pairs, float4 *__restrict__ contacts, unsigned long long cap_pairs, FrameBlock *__restrict__ fb)
 {
     __shared__ EmitBuf<kNarrowWarps, kNarrowCap> s_out;
+    __shared__ uint32_t s_ticket;
     emit_init(s_out);
-    __syncthreads();
-    const unsigned long long n = min(fb->n_ss, cap_cands);
-    const unsigned long long stride = (unsigned long long)gridDim.x * kNarrowThreads;
-    for (unsigned long long b = (unsigned long long)blockIdx.x * kNarrowThreads; b < n; b += stride) {
-        const unsigned long long i = b + threadIdx.x;
-        bool hit = false;
-        uint2 item = make_uint2(0, 0);
-        float4 ct = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < n) {
-            const uint2 c = cand[i];
-            const float4 h0 = __ldg(rec + 2 * (size_t)c.x), l0 = __ldg(rec + 2 * (size_t)c.y);
-            hit = test_sphere_sphere(h0.x, h0.y, h0.z, h0.w, l0.x, l0.y, l0.z, l0.w);
-            if (hit) {
-                const float4 h1 = __ldg(rec + 2 * (size_t)c.x + 1), l1 = __ldg(rec + 2 * (size_t)c.y + 1);
-                item = make_uint2(__float_as_uint(h1.x), __float_as_uint(l1.x));
-                if (contacts) ct = contact_sphere_sphere(h0.x, h0.y, h0.z, h0.w, l0.x, l0.y, l0.z, l0.w);
+    const unsigned long long n_oo = min(fb->n_oo, cap_cands), n_so = min(fb->n_so, cap_cands), n_ss = min(fb->n_ss, cap_cands);
+    const uint32_t c_oo = (uint32_t)((n_oo + kNarrowChunk - 1) / kNarrowChunk);
+    const uint32_t c_so = (uint32_t)((n_so + kNarrowChunk - 1) / kNarrowChunk);
+    const uint32_t c_ss = (uint32_t)((n_ss + kNarrowChunk - 1) / kNarrowChunk);
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_ticket = atomicAdd(&fb->narrow_ticket, 1u);
+        __syncthreads();
+        uint32_t t = s_ticket;
+        if (t >= c_oo + c_so + c_ss) break;
+        const int cls = t < c_oo ? 2 : (t < c_oo + c_so ? 1 : 0);
+        t -= cls == 2 ? 0u : (cls == 1 ? c_oo : c_oo + c_so);
+        const unsigned long long n = cls == 2 ? n_oo : (cls == 1 ? n_so : n_ss);
+        const uint2 *cand = cls == 2 ? cand_oo : (cls == 1 ? cand_so : cand_ss);
+#pragma unroll 1
+        for (int k = 0; k < kNarrowChunk / kNarrowThreads; ++k) {
+            const unsigned long long i = (unsigned long long)t * kNarrowChunk + k * kNarrowThreads + threadIdx.x;
+            bool hit = false;
+            uint2 item = make_uint2(0, 0);
+            float4 ct = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < n) {
+                const uint2 c = cand[i];
+                if (cls == 2) {  // OBB::test_obb (mod.rs:413-546) evaluated as later.test_obb(earlier) (grid_collision.rs:505, mod.rs:408)
+                    uint32_t ea, eb;
+                    const Obb a = obb_load(obb + 4 * (size_t)c.x, &ea);
+                    const Obb bb = obb_load(obb + 4 * (size_t)c.y, &eb);
+                    hit = test_obb_obb(a, bb);
+                    item = make_uint2(ea, eb);
+                    if (CONTACTS && hit) ct = contact_obb_obb(a, bb);
+                } else if (cls == 1) {  // Sphere::test_obb (mod.rs:391-394): either order calls sphere.test_obb(obb) (mod.rs:378,407)
+                    const bool hi_is_sphere = c.x >> 31;
+                    const uint32_t hi = c.x & 0x7fffffffu, lo = c.y;
+                    const uint32_t si = hi_is_sphere ? hi : lo, oi = hi_is_sphere ? lo : hi;
+                    const float4 s0 = __ldg(rec + 2 * (size_t)si), s1 = __ldg(rec + 2 * (size_t)si + 1);
+                    uint32_t oe;
+                    const Obb o = obb_load(obb + 4 * (size_t)oi, &oe);
+                    hit = test_sphere_obb(s0.x, s0.y, s0.z, s0.w, o);
+                    const uint32_t se = __float_as_uint(s1.x);
+                    item = hi_is_sphere ? make_uint2(se, oe) : make_uint2(oe, se);
+                    if (CONTACTS && hit) ct = contact_sphere_obb(s0.x, s0.y, s0.z, s0.w, o, hi_is_sphere);
+                } else {  // Sphere::test_sphere (mod.rs:383-389)
+                    const float4 h0 = __ldg(rec + 2 * (size_t)c.x), l0 = __ldg(rec + 2 * (size_t)c.y);
+                    hit = test_sphere_sphere(h0.x, h0.y, h0.z, h0.w, l0.x, l0.y, l0.z, l0.w);
+                    if (hit) {
+                        const float4 h1 = __ldg(rec + 2 * (size_t)c.x + 1), l1 = __ldg(rec + 2 * (size_t)c.y + 1);
+                        item = make_uint2(__float_as_uint(h1.x), __float_as_uint(l1.x));
+                        if (CONTACTS) ct = contact_sphere_sphere(h0.x, h0.y, h0.z, h0.w, l0.x, l0.y, l0.z, l0.w);
+                    }
+                }
             }
+            emit(s_out, hit, item, ct, pairs, CONTACTS ? contacts : nullptr, &fb->n_pairs, cap_pairs);
         }
-        emit(s_out, hit, item, ct, pairs, contacts, &fb->n_pairs, cap_pairs);
     }
-    emit_finish(s_out, pairs, contacts, &fb->n_pairs, cap_pairs);
-}
-
-// Sphere::test_obb (mod.rs:391-394) -- either order of the pair calls sphere.test_obb(obb) (mod.rs:378,407)
-__global__ void __launch_bounds__(kNarrowThreads)
-k_narrow_sphere_obb(const uint2 *__restrict__ cand, unsigned long long cap_cands, const float4 *__restrict__ rec,
-                    const float4 *__restrict__ obb, uint2 *__restrict__ pairs, float4 *__restrict__ contacts,
-                    unsigned long long cap_pairs, FrameBlock *__restrict__ fb)
-{
-    __shared__ EmitBuf<kNarrowWarps, kNarrowCap> s_out;
-    emit_init(s_out);
-    __syncthreads();
-    const unsigned long long n = min(fb->n_so, cap_cands);
-    const unsigned long long stride = (unsigned long long)gridDim.x * kNarrowThreads;
-    for (unsigned long long b = (unsigned long long)blockIdx.x * kNarrowThreads; b < n; b += stride) {
-        const unsigned long long i = b + threadIdx.x;
-        bool hit = false;
-        uint2 item = make_uint2(0, 0);
-        float4 ct = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < n) {
-            const uint2 c = cand[i];
-            const bool hi_is_sphere = c.x >> 31;
-            const uint32_t hi = c.x & 0x7fffffffu, lo = c.y;
-            const uint32_t si = hi_is_sphere ? hi : lo, oi = hi_is_sphere ? lo : hi;
-            const float4 s0 = __ldg(rec + 2 * (size_t)si), s1 = __ldg(rec + 2 * (size_t)si + 1);
-            uint32_t oe;
-            const Obb o = obb_load(obb + 4 * (size_t)oi, &oe);
-            hit = test_sphere_obb(s0.x, s0.y, s0.z, s0.w, o);
-            const uint32_t se = __float_as_uint(s1.x);
-            item = hi_is_sphere ? make_uint2(se, oe) : make_uint2(oe, se);
-            if (hit && contacts) ct = contact_sphere_obb(s0.x, s0.y, s0.z, s0.w, o, hi_is_sphere);
-        }
-        emit(s_out, hit, item, ct, pairs, contacts, &fb->n_pairs, cap_pairs);
-    }
-    emit_finish(s_out, pairs, contacts, &fb->n_pairs, cap_pairs);
-}
-
-// OBB::test_obb (mod.rs:413-546) evaluated as later.test_obb(earlier) (grid_collision.rs:505, mod.rs:408)
-__global__ void __launch_bounds__(kNarrowThreads)
-k_narrow_obb_obb(const uint2 *__restrict__ cand, unsigned long long cap_cands, const float4 *__restrict__ obb,
-                 uint2 *__restrict__ pairs, float4 *__restrict__ contacts, unsigned long long cap_pairs,
-                 FrameBlock *__restrict__ fb)
-{
-    __shared__ EmitBuf<kNarrowWarps, kNarrowCap> s_out;
-    emit_init(s_out);
-    __syncthreads();
-    const unsigned long long n = min(fb->n_oo, cap_cands);
-    const unsigned long long stride = (unsigned long long)gridDim.x * kNarrowThreads;
-    for (unsigned long long b = (unsigned long long)blockIdx.x * kNarrowThreads; b < n; b += stride) {
-        const unsigned long long i = b + threadIdx.x;
-        bool hit = false;
-        uint2 item = make_uint2(0, 0);
-        float4 ct = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < n) {
-            const uint2 c = cand[i];
-            uint32_t ea, eb;
-            const Obb a = obb_load(obb + 4 * (size_t)c.x, &ea);
-            const Obb bb = obb_load(obb + 4 * (size_t)c.y, &eb);
-            hit = test_obb_obb(a, bb);
-            item = make_uint2(ea, eb);
-            if (hit && contacts) ct = contact_obb_obb(a, bb);
-        }
-        emit(s_out, hit, item, ct, pairs, contacts, &fb->n_pairs, cap_pairs);
-    }
-    emit_finish(s_out, pairs, contacts, &fb->n_pairs, cap_pairs);
+    emit_finish(s_out, pairs, CONTACTS ? contacts : nullptr, &fb->n_pairs, cap_pairs);
 }
 
 // full BoundVolume::test (bounding_volume.rs:124-132) between two arbitrary volumes, `hi` = later index
