@@ -238,6 +238,11 @@ def main():
         h_pos[f].numpy()[:] = pos
         h_quat[f].numpy()[:] = quat
     h_scale = torch.from_numpy(scene.scale).pin_memory()
+    # the host layer marshals rotation / scale for the boxes only (spheres ignore them, mod.rs:313-317)
+    box = scene.kind == 1
+    n_box = int(box.sum())
+    h_bquat = [torch.from_numpy(np.ascontiguousarray(t.numpy()[box])).pin_memory() for t in h_quat]
+    h_bscale = torch.from_numpy(np.ascontiguousarray(scene.scale[box])).pin_memory()
     d_pos = [t.cuda() for t in h_pos]
     d_quat = [t.cuda() for t in h_quat]
     d_scale = h_scale.cuda()
@@ -280,13 +285,13 @@ def main():
 
     def step_e2e(i):
         f = i % nframes
-        ctx.update_transforms_ptr(h_pos[f].data_ptr(), h_quat[f].data_ptr(), 0)
+        ctx.update_transforms_packed_ptr(h_pos[f].data_ptr(), n_box, h_bquat[f].data_ptr(), 0)
         out = ctx.step()
         rc = lib.gsc_download_pairs(ctx._h, h_pairs.data_ptr(), h_pairs.numel() // 2, 0, C.byref(npairs))
         assert rc == 0, lib.gsc_last_error(ctx._h)
         return out
 
-    ctx.update_transforms_ptr(h_pos[0].data_ptr(), h_quat[0].data_ptr(), h_scale.data_ptr())
+    ctx.update_transforms_packed_ptr(h_pos[0].data_ptr(), n_box, h_bquat[0].data_ptr(), h_bscale.data_ptr())
     for i in range(args.warmup):
         step_e2e(i)
     torch.cuda.synchronize()
@@ -323,7 +328,8 @@ def main():
                    "box_fraction": round(f_box, 3), "contact_pairs_per_step": int(mean[0])},
         "p50_step_ms": float(np.median(dev_ms)), "device_ms_per_step": float(np.mean(dev_ms)),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": 1e3 * wall_e2e / args.steps,
-                "h2d_bytes_per_step": n * 28, "d2h_bytes_per_step": int(d2h / args.steps)},
+                "h2d_bytes_per_step": n * 12 + n_box * 16, "d2h_bytes_per_step": int(d2h / args.steps),
+                "note": "per step: positions of all colliders + rotations of the boxes from pinned host memory, contact pairs back"},
         "gpu_launches": 19 * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",

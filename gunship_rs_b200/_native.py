@@ -60,7 +60,7 @@ class GscBounds(C.Structure):
 # every symbol include/gunship_collision.h declares
 EXPORTS = (
     "gsc_create", "gsc_destroy", "gsc_last_error", "gsc_abi_version", "gsc_upload_colliders",
-    "gsc_update_transforms", "gsc_bind_device_transforms", "gsc_step", "gsc_download_pairs", "gsc_debug_download",
+    "gsc_update_transforms", "gsc_update_transforms_packed", "gsc_bind_device_transforms", "gsc_step", "gsc_download_pairs", "gsc_debug_download",
     "gsc_test_sphere_sphere", "gsc_test_sphere_obb", "gsc_test_obb_obb", "gsc_test_aabb_aabb", "gsc_fnv1a_gridcell",
     "gsc_sort_pairs_u32", "gsc_phase_bounds", "gsc_set_global_bounds", "gsc_local_x_range", "gsc_halo_select",
     "gsc_halo_append", "gsc_phase_finish", "gsc_set_x_window", "gsc_ipc_export", "gsc_ipc_open_peer", "gsc_halo_push",
@@ -89,6 +89,7 @@ def load():
     L.gsc_destroy.restype = None
     L.gsc_upload_colliders.argtypes = [vp, C.c_uint32, u32p, u8p, f32p, f32p, u32p]
     L.gsc_update_transforms.argtypes = [vp, C.c_uint32, f32p, f32p, f32p]
+    L.gsc_update_transforms_packed.argtypes = [vp, C.c_uint32, f32p, C.c_uint32, f32p, f32p]
     L.gsc_bind_device_transforms.argtypes = [vp, C.c_uint32, vp, vp, vp]
     L.gsc_step.argtypes = [vp, C.POINTER(GscStepOut)]
     L.gsc_download_pairs.argtypes = [vp, u32p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]

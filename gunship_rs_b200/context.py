@@ -62,12 +62,24 @@ class CollisionContext:
         e, k = _c(entity, np.uint32), _c(kind, np.uint8)
         o, s, g = _c(offset, np.float32), _c(size, np.float32), _c(global_index, np.uint32)
         self.n = int(e.shape[0])
+        self.n_box = int((k == N.GSC_BOX).sum())
         self._check(self._lib.gsc_upload_colliders(self._h, self.n, _ptr(e), _ptr(k), _ptr(o), _ptr(s), _ptr(g)))
 
     def update_transforms(self, pos, quat=None, scale=None):
         p, q, s = _c(pos, np.float32), _c(quat, np.float32), _c(scale, np.float32)
         self._keep = [p, q, s]  # stay alive until the step has consumed them
         self._check(self._lib.gsc_update_transforms(self._h, self.n, _ptr(p), _ptr(q), _ptr(s)))
+
+    def update_transforms_packed(self, pos, box_quat=None, box_scale=None):
+        """Rotation / scale for the boxes only, in collider order (gsc_update_transforms_packed)."""
+        p, q, s = _c(pos, np.float32), _c(box_quat, np.float32), _c(box_scale, np.float32)
+        self._keep = [p, q, s]
+        n_box = self.n_box if q is None else int(q.shape[0])
+        self._check(self._lib.gsc_update_transforms_packed(self._h, self.n, _ptr(p), n_box, _ptr(q), _ptr(s)))
+
+    def update_transforms_packed_ptr(self, pos_ptr: int, n_box: int, box_quat_ptr: int = 0, box_scale_ptr: int = 0):
+        self._check(self._lib.gsc_update_transforms_packed(self._h, self.n, pos_ptr or None, n_box, box_quat_ptr or None,
+                                                           box_scale_ptr or None))
 
     def update_transforms_ptr(self, pos_ptr: int, quat_ptr: int = 0, scale_ptr: int = 0):
         """Host pointers (e.g. pinned torch tensors' data_ptr()); arrays must outlive the next step()."""

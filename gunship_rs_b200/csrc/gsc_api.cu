@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "gsc_kernels.cuh"
 
@@ -46,7 +47,9 @@ struct gsc_ctx {
     bool have_colliders = false, have_transforms = false, have_gidx = false;
 
     // static collider data + transforms (SoA, as uploaded)
-    uint32_t *d_entity = nullptr, *d_gidx = nullptr;
+    uint32_t *d_entity = nullptr, *d_gidx = nullptr, *d_box_slot = nullptr;
+    uint32_t n_box = 0;
+    bool packed = false;  // d_quat / d_scale hold boxes only (gsc_update_transforms_packed)
     uint8_t *d_kind = nullptr;
     float *d_offset = nullptr, *d_size = nullptr;
     float *d_pos = nullptr, *d_quat = nullptr, *d_scale = nullptr;          // owned
@@ -222,6 +225,7 @@ int gsc_create(const gsc_config *cfg, gsc_ctx **out)
     CR(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CR(dmalloc(&c->d_entity, M));
     CR(dmalloc(&c->d_gidx, M));
+    CR(dmalloc(&c->d_box_slot, M));
     CR(dmalloc(&c->d_kind, M));
     CR(dmalloc(&c->d_offset, 3 * M));
     CR(dmalloc(&c->d_size, 3 * M));
@@ -275,7 +279,7 @@ void gsc_destroy(gsc_ctx *c)
             cudaIpcCloseMemHandle(p.obb);
             cudaIpcCloseMemHandle(p.fb);
         }
-    void *bufs[] = { c->d_entity, c->d_gidx, c->d_kind, c->d_offset, c->d_size, c->d_pos, c->d_quat, c->d_scale, c->d_rec,
+    void *bufs[] = { c->d_entity, c->d_gidx, c->d_box_slot, c->d_kind, c->d_offset, c->d_size, c->d_pos, c->d_quat, c->d_scale, c->d_rec,
                      c->d_rec_sorted, c->d_qrec_sorted, c->d_obb, c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1], c->d_cell_start,
                      c->d_wide, c->d_gaps, c->d_pairs, c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->d_pairs_sorted, c->d_contacts, c->d_contacts_sorted, c->d_perm, c->d_adj_entity, c->d_adj_offset, c->d_adj_other, c->d_fb, c->d_sort_scratch,
                      c->d_halo_rec, c->d_halo_obb, c->d_halo_count };
@@ -301,7 +305,16 @@ int gsc_upload_colliders(gsc_ctx *c, uint32_t n, const uint32_t *entity, const u
     for (uint32_t i = 0; i < n; ++i)
         if (kind[i] > GSC_BOX)
             return fail(c, GSC_ERR_KIND, "collider %u is a Mesh: unimplemented!() in the reference (mod.rs:331)", i);
+    // box_slot[i] = number of boxes before collider i: where a box finds its rotation / scale in the packed arrays
+    std::vector<uint32_t> slot(n);
+    uint32_t n_box = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        slot[i] = n_box;
+        n_box += kind[i] == GSC_BOX;
+    }
+    c->n_box = n_box;
     if (n) {
+        CU(c, cudaMemcpyAsync(c->d_box_slot, slot.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
         CU(c, cudaMemcpyAsync(c->d_entity, entity, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
         CU(c, cudaMemcpyAsync(c->d_kind, kind, (size_t)n, cudaMemcpyHostToDevice, c->stream));
         CU(c, cudaMemcpyAsync(c->d_offset, offset3, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
@@ -313,6 +326,7 @@ int gsc_upload_colliders(gsc_ctx *c, uint32_t n, const uint32_t *entity, const u
     c->have_gidx = global_index != nullptr;
     c->have_colliders = true;
     c->have_transforms = false;
+    c->packed = false;
     return GSC_OK;
 }
 
@@ -328,6 +342,30 @@ int gsc_update_transforms(gsc_ctx *c, uint32_t n, const float *pos3, const float
         if (quat4) CU(c, cudaMemcpyAsync(c->d_quat, quat4, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
         if (scale3) CU(c, cudaMemcpyAsync(c->d_scale, scale3, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
     }
+    if (c->packed && (!quat4 || !scale3) && c->n_box)
+        return fail(c, GSC_ERR_INVALID, "gsc_update_transforms: after a packed update, pass rotation and scale again");
+    c->packed = false;
+    c->b_pos = c->d_pos;
+    c->b_quat = c->d_quat;
+    c->b_scale = c->d_scale;
+    c->have_transforms = true;
+    return GSC_OK;
+}
+
+int gsc_update_transforms_packed(gsc_ctx *c, uint32_t n, const float *pos3, uint32_t n_box, const float *box_quat4,
+                                 const float *box_scale3)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!c->have_colliders || n != c->n_local || n_box != c->n_box)
+        return fail(c, GSC_ERR_INVALID, "gsc_update_transforms_packed: n=%u / n_box=%u do not match the uploaded %u colliders / %u boxes",
+                    n, n_box, c->n_local, c->n_box);
+    if (n && !pos3) return fail(c, GSC_ERR_INVALID, "gsc_update_transforms_packed: null positions");
+    if (n_box && !c->packed && (!box_quat4 || !box_scale3))
+        return fail(c, GSC_ERR_INVALID, "gsc_update_transforms_packed: the first packed update needs rotation and scale");
+    if (n) CU(c, cudaMemcpyAsync(c->d_pos, pos3, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+    if (n_box && box_quat4) CU(c, cudaMemcpyAsync(c->d_quat, box_quat4, (size_t)n_box * 16, cudaMemcpyHostToDevice, c->stream));
+    if (n_box && box_scale3) CU(c, cudaMemcpyAsync(c->d_scale, box_scale3, (size_t)n_box * 12, cudaMemcpyHostToDevice, c->stream));
+    c->packed = true;
     c->b_pos = c->d_pos;
     c->b_quat = c->d_quat;
     c->b_scale = c->d_scale;
@@ -343,6 +381,9 @@ int gsc_bind_device_transforms(gsc_ctx *c, uint32_t n, const float *d_pos3, cons
     if (n && !d_pos3) return fail(c, GSC_ERR_INVALID, "gsc_bind_device_transforms: null positions");
     if (d_quat4 && (reinterpret_cast<uintptr_t>(d_quat4) & 15))
         return fail(c, GSC_ERR_INVALID, "gsc_bind_device_transforms: quaternions must be 16-byte aligned");
+    if (c->packed && (!d_quat4 || !d_scale3) && c->n_box)
+        return fail(c, GSC_ERR_INVALID, "gsc_bind_device_transforms: after a packed update, pass rotation and scale again");
+    c->packed = false;
     c->b_pos = d_pos3;
     c->b_quat = d_quat4 ? d_quat4 : c->d_quat;
     c->b_scale = d_scale3 ? d_scale3 : c->d_scale;
@@ -365,7 +406,7 @@ static int stage_bounds(gsc_ctx *c)
     if (c->n_local) {
         const uint32_t blocks = (c->n_local + kBvhThreads - 1) / kBvhThreads;
         k_bvh_update<<<blocks, kBvhThreads, 0, s>>>(c->n_local, c->d_kind, c->d_offset, c->d_size, c->b_pos, c->b_quat,
-                                                   c->b_scale, c->d_entity, c->have_gidx ? c->d_gidx : nullptr, c->d_rec,
+                                                   c->b_scale, c->d_entity, c->have_gidx ? c->d_gidx : nullptr, c->packed ? c->d_box_slot : nullptr, c->d_rec,
                                                    c->d_obb, c->d_fb);
     }
     CU(c, cudaGetLastError());

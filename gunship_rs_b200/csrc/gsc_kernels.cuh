@@ -175,9 +175,11 @@ __global__ void __launch_bounds__(kBvhThreads)
 k_bvh_update(uint32_t n, const uint8_t *__restrict__ kind, const float *__restrict__ offset3,
              const float *__restrict__ size3, const float *__restrict__ pos3, const float *__restrict__ quat4,
              const float *__restrict__ scale3, const uint32_t *__restrict__ entity,
-             const uint32_t *__restrict__ gidx, float4 *__restrict__ rec, float4 *__restrict__ obb,
-             FrameBlock *__restrict__ fb)
+             const uint32_t *__restrict__ gidx, const uint32_t *__restrict__ box_slot, float4 *__restrict__ rec,
+             float4 *__restrict__ obb, FrameBlock *__restrict__ fb)
 {
+    // box_slot != nullptr: quat4 / scale3 are packed over the boxes only (gsc_update_transforms_packed);
+    // box_slot[i] = number of boxes before collider i
     const uint32_t i = blockIdx.x * kBvhThreads + threadIdx.x;
     float ext = 0.0f, mnx_max = -INFINITY;
     float mn[3] = { INFINITY, INFINITY, INFINITY }, mx[3] = { -INFINITY, -INFINITY, -INFINITY };
@@ -199,11 +201,12 @@ k_bvh_update(uint32_t n, const uint8_t *__restrict__ kind, const float *__restri
         } else if (k == 1) {
             Obb o;
             // mod.rs:320  half_widths = widths * scale * 0.5
-            o.hx = mul(mul(size3[3 * i], scale3[3 * i]), 0.5f);
-            o.hy = mul(mul(size3[3 * i + 1], scale3[3 * i + 1]), 0.5f);
-            o.hz = mul(mul(size3[3 * i + 2], scale3[3 * i + 2]), 0.5f);
+            const size_t t = box_slot ? box_slot[i] : i;  // where this box's rotation / scale live
+            o.hx = mul(mul(size3[3 * i], scale3[3 * t]), 0.5f);
+            o.hy = mul(mul(size3[3 * i + 1], scale3[3 * t + 1]), 0.5f);
+            o.hz = mul(mul(size3[3 * i + 2], scale3[3 * t + 2]), 0.5f);
             o.cx = cx; o.cy = cy; o.cz = cz;
-            const float4 q = reinterpret_cast<const float4 *>(quat4)[i];
+            const float4 q = reinterpret_cast<const float4 *>(quat4)[t];
             quat_to_mat3(q.x, q.y, q.z, q.w, o.m);  // mod.rs:322
             obb_aabb(o, mn, mx);
             obb_store(obb + 4 * (size_t)i, o, e);

@@ -367,6 +367,11 @@ def bench_multi_gpu(args, n, rank, world, local_rank, metric, unit, workload_nam
         h_pos.append(hp)
         h_quat.append(hq)
     h_scale = torch.from_numpy(np.ascontiguousarray(scene.scale[mine])).pin_memory()
+    # the host layer marshals rotation / scale for the boxes only (spheres ignore them, mod.rs:313-317)
+    box = scene.kind[mine] == 1
+    n_box = int(box.sum())
+    h_bquat = [torch.from_numpy(np.ascontiguousarray(t.numpy()[box])).pin_memory() for t in h_quat]
+    h_bscale = torch.from_numpy(np.ascontiguousarray(scene.scale[mine][box])).pin_memory()
     d_pos = [t.to(dev) for t in h_pos]
     d_quat = [t.to(dev) for t in h_quat]
     d_scale = h_scale.to(dev)
@@ -420,13 +425,13 @@ def bench_multi_gpu(args, n, rank, world, local_rank, metric, unit, workload_nam
 
     def step_e2e(i):
         f = i % nframes
-        ctx.update_transforms_ptr(h_pos[f].data_ptr(), h_quat[f].data_ptr(), 0)
+        ctx.update_transforms_packed_ptr(h_pos[f].data_ptr(), n_box, h_bquat[f].data_ptr(), 0)
         out = driver.step()
         rc = ctx._lib.gsc_download_pairs(ctx._h, h_pairs.data_ptr(), h_pairs.numel() // 2, 0, C.byref(npairs))
         assert rc == 0, ctx._lib.gsc_last_error(ctx._h)
         return out
 
-    ctx.update_transforms_ptr(h_pos[0].data_ptr(), h_quat[0].data_ptr(), h_scale.data_ptr())
+    ctx.update_transforms_packed_ptr(h_pos[0].data_ptr(), n_box, h_bquat[0].data_ptr(), h_bscale.data_ptr())
     for i in range(args.warmup):
         step_e2e(i)
     span_e2e, outs_e2e = timed(lambda i: step_e2e(args.warmup + i), args.steps)
@@ -444,7 +449,7 @@ def bench_multi_gpu(args, n, rank, world, local_rank, metric, unit, workload_nam
     sums = total([np.mean([o.n_pairs for o in outs]), np.mean([o.n_sphere_obb for o in outs]),
                   np.mean([o.n_obb_obb for o in outs]), np.mean([o.n_sphere_sphere for o in outs]),
                   np.mean([o.n_cells for o in outs]), float(driver.last_halo_in), float(n_local),
-                  np.mean([o.n_pairs for o in outs_e2e]) * 8.0])
+                  np.mean([o.n_pairs for o in outs_e2e]) * 8.0, float(n_box)])
     passes = int(outs[-1].sort_passes)
     if rank == 0:
         peak, peak_kind = measured_peak_gbs()
@@ -466,7 +471,7 @@ def bench_multi_gpu(args, n, rank, world, local_rank, metric, unit, workload_nam
                        "box_fraction": round(f_box, 3), "contact_pairs_per_step": int(sums[0]),
                        "halo_colliders_per_step": int(sums[5])},
             "e2e": {"value": n * args.steps / span_e2e, "unit": unit, "ms_per_step": 1e3 * span_e2e / args.steps,
-                    "h2d_bytes_per_step": n * 28, "d2h_bytes_per_step": int(sums[7])},
+                    "h2d_bytes_per_step": int(n * 12 + sums[8] * 16), "d2h_bytes_per_step": int(sums[7])},
             "gpu_launches": (13 + 4) * args.steps * world,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",

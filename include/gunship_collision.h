@@ -111,6 +111,13 @@ int gsc_upload_colliders(gsc_ctx *ctx, uint32_t n, const uint32_t *entity, const
  *      quat4 / scale3 may be NULL to keep the previous values. ---- */
 int gsc_update_transforms(gsc_ctx *ctx, uint32_t n, const float *pos3, const float *quat4, const float *scale3);
 
+/* same frame data with the rotation / scale arrays packed over the BOXES only, in collider order (box k of the
+ * dense array is the k-th collider with kind GSC_BOX): spheres ignore rotation and scale (mod.rs:313-317), so a
+ * host layer that marshals transforms anyway need not send them -- 12 B per collider + 28 B per box over PCIe
+ * instead of 40 B per collider.  box_quat4 / box_scale3 may be NULL to keep the previous packed values. */
+int gsc_update_transforms_packed(gsc_ctx *ctx, uint32_t n, const float *pos3, uint32_t n_box, const float *box_quat4,
+                                 const float *box_scale3);
+
 /* same, from DEVICE memory that the caller keeps alive until the next bind (no copy is made) */
 int gsc_bind_device_transforms(gsc_ctx *ctx, uint32_t n, const float *d_pos3, const float *d_quat4, const float *d_scale3);
 

@@ -72,6 +72,8 @@ extern "C" {
     pub fn gsc_upload_colliders(ctx: *mut gsc_ctx, n: u32, entity: *const u32, kind: *const u8, offset3: *const f32,
                                 size3: *const f32, global_index: *const u32) -> c_int;
     pub fn gsc_update_transforms(ctx: *mut gsc_ctx, n: u32, pos3: *const f32, quat4: *const f32, scale3: *const f32) -> c_int;
+    pub fn gsc_update_transforms_packed(ctx: *mut gsc_ctx, n: u32, pos3: *const f32, n_box: u32, box_quat4: *const f32,
+                                        box_scale3: *const f32) -> c_int;
     pub fn gsc_bind_device_transforms(ctx: *mut gsc_ctx, n: u32, d_pos3: *const f32, d_quat4: *const f32,
                                       d_scale3: *const f32) -> c_int;
     pub fn gsc_step(ctx: *mut gsc_ctx, out: *mut gsc_step_out) -> c_int;

@@ -265,3 +265,27 @@ def test_large_scene_properties():
             sure = sure[sure != i]
             mine = set(p[p[:, 0] == i + 1, 1].tolist()) | set(p[p[:, 1] == i + 1, 0].tolist())
             assert set((sure + 1).tolist()) <= mine
+
+
+def test_packed_transforms_give_the_same_pair_set():
+    """gsc_update_transforms_packed: rotation / scale for the boxes only (spheres ignore them, mod.rs:313-317)"""
+    s = scenes.by_config(3, 30000)
+    oracle = O.OracleSystem()
+    box = s.kind == 1
+    with G.CollisionContext(s.n) as ctx:
+        ctx.upload_colliders(s.entity, s.kind, s.offset, s.size)
+        for f in (0, 2):
+            pos, quat = s.frame(f)
+            ctx.update_transforms_packed(pos, quat[box], s.scale[box] if f == 0 else None)
+            ctx.step()
+            assert np.array_equal(ctx.pairs_packed(sorted=True), oracle.step(s, pos, quat))
+        # back to the dense form, then packed again
+        pos, quat = s.frame(3)
+        ctx.update_transforms(pos, quat, s.scale)
+        ctx.step()
+        assert np.array_equal(ctx.pairs_packed(sorted=True), oracle.step(s, pos, quat))
+        with pytest.raises(G.GscError):
+            ctx.update_transforms_packed(pos)          # the first packed update after a dense one needs rot + scale
+        with pytest.raises(G.GscError):
+            ctx.update_transforms_packed(pos, quat[box][:-1], s.scale[box][:-1])   # wrong box count
+    oracle.close()
