@@ -609,10 +609,10 @@ k_pairs(uint32_t n_total, const uint32_t *__restrict__ keys_a, const uint32_t *_
             // row base key kk = key + dx * dims.y * dims.z + dy * dims.z  (apron => always a valid cell)
             const uint32_t kk = key - (r < 3 ? dydz : 0u) + (r == 2 ? dz : 0u) - ((r == 0 || r == 3) ? dz : 0u);
             const bool use = active && (r != 2 || ry);
-            lo[r] = use ? __ldg(cell_start + kk - 1) : 0u;
-            hi[r] = use ? __ldg(cell_start + kk + (r == 4 ? 1u : zhi)) : 0u;
+            lo[r] = use ? ldg_gather_u32(cell_start + kk - 1) : 0u;
+            hi[r] = use ? ldg_gather_u32(cell_start + kk + (r == 4 ? 1u : zhi)) : 0u;
         }
-        qsame = active ? __ldg(cell_start + key) : 0u;
+        qsame = active ? ldg_gather_u32(cell_start + key) : 0u;
     }
 
     // The five runs are walked one after the other (row-outer): a warp then spends sum_r max_lane(len_r)
@@ -777,7 +777,7 @@ k_narrow(const uint2 *__restrict__ cand_ss, const uint2 *__restrict__ cand_so, c
                     const bool hi_is_sphere = c.x >> 31;
                     const uint32_t hi = c.x & 0x7fffffffu, lo = c.y;
                     const uint32_t si = hi_is_sphere ? hi : lo, oi = hi_is_sphere ? lo : hi;
-                    const float4 s0 = __ldg(rec + 2 * (size_t)si), s1 = __ldg(rec + 2 * (size_t)si + 1);
+                    const float4 s0 = ldg_gather(rec + 2 * (size_t)si), s1 = ldg_gather(rec + 2 * (size_t)si + 1);
                     uint32_t oe;
                     const Obb o = obb_load(obb + 4 * (size_t)oi, &oe);
                     hit = test_sphere_obb(s0.x, s0.y, s0.z, s0.w, o);
@@ -785,10 +785,10 @@ k_narrow(const uint2 *__restrict__ cand_ss, const uint2 *__restrict__ cand_so, c
                     item = hi_is_sphere ? make_uint2(se, oe) : make_uint2(oe, se);
                     if (CONTACTS && hit) ct = contact_sphere_obb(s0.x, s0.y, s0.z, s0.w, o, hi_is_sphere);
                 } else {  // Sphere::test_sphere (mod.rs:383-389)
-                    const float4 h0 = __ldg(rec + 2 * (size_t)c.x), l0 = __ldg(rec + 2 * (size_t)c.y);
+                    const float4 h0 = ldg_gather(rec + 2 * (size_t)c.x), l0 = ldg_gather(rec + 2 * (size_t)c.y);
                     hit = test_sphere_sphere(h0.x, h0.y, h0.z, h0.w, l0.x, l0.y, l0.z, l0.w);
                     if (hit) {
-                        const float4 h1 = __ldg(rec + 2 * (size_t)c.x + 1), l1 = __ldg(rec + 2 * (size_t)c.y + 1);
+                        const float4 h1 = ldg_gather(rec + 2 * (size_t)c.x + 1), l1 = ldg_gather(rec + 2 * (size_t)c.y + 1);
                         item = make_uint2(__float_as_uint(h1.x), __float_as_uint(l1.x));
                         if (CONTACTS) ct = contact_sphere_sphere(h0.x, h0.y, h0.z, h0.w, l0.x, l0.y, l0.z, l0.w);
                     }

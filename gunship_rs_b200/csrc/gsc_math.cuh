@@ -28,6 +28,13 @@ GSC_DEV float4 ldg_gather(const float4 *p)
     return v;
 }
 
+GSC_DEV uint32_t ldg_gather_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 // vector.rs:190-196  Dot: x*x' + y*y' + z*z'
 GSC_DEV float dot3(float ax, float ay, float az, float bx, float by, float bz)
 {
@@ -54,7 +61,7 @@ GSC_DEV void obb_store(float4 *dst, const Obb &o, uint32_t entity)
 
 GSC_DEV Obb obb_load(const float4 *src, uint32_t *entity)
 {
-    const float4 q0 = __ldg(src + 0), q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3);
+    const float4 q0 = ldg_gather(src + 0), q1 = ldg_gather(src + 1), q2 = ldg_gather(src + 2), q3 = ldg_gather(src + 3);
     Obb o;
     o.cx = q0.x; o.cy = q0.y; o.cz = q0.z;
     o.m[0][0] = q0.w; o.m[0][1] = q1.x; o.m[0][2] = q1.y;
