@@ -75,3 +75,42 @@ def test_two_ranks_report_the_single_context_pair_set(tmp_path, cfg, n, ownershi
             # foreign volumes of the one cell column the cut runs through
             assert 0 < halo[1][0] < 0.35 * halo[1][2] and halo[0][0] < halo[1][0]
     oracle.close()
+
+
+def test_phase_calls_single_rank_equal_gsc_step():
+    """gsc_phase_bounds / gsc_set_global_bounds / gsc_local_x_range / gsc_set_x_window / gsc_phase_finish on ONE context
+    reproduce gsc_step; a window that misses a local collider is rejected."""
+    import oracle_lib as O
+    from gunship_rs_b200 import _native as N
+    from gunship_rs_b200 import context as G
+    from gunship_rs_b200 import scenes
+    s = scenes.by_config(3, 20000)
+    oracle = O.OracleSystem()
+    want = oracle.step(s)
+    vol = oracle.volumes()
+    cell = np.float32(oracle.longest_axis)
+    home_x = np.floor(vol["aabb_min"][:, 0] / cell).astype(np.int64)
+    with G.CollisionContext(s.n) as ctx:
+        ctx.upload_colliders(s.entity, s.kind, s.offset, s.size)
+        ctx.update_transforms(s.pos, s.quat, s.scale)
+        b = ctx.phase_bounds()
+        assert np.float32(b.longest_axis) == cell and np.float32(b.home_x_max) == vol["aabb_min"][:, 0].max()
+        assert np.array_equal(np.array(list(b.world_min), np.float32), vol["aabb_min"][:, :3].min(axis=0))
+        ctx.set_global_bounds(b)
+        assert ctx.local_x_range() == (int(home_x.min()), int(home_x.max()))
+        ctx.set_x_window(int(home_x.min()) - 1, int(home_x.max()))
+        out = ctx.phase_finish()
+        assert out.grid_dims[0] == home_x.max() - home_x.min() + 3          # window clamped to the world, + apron
+        assert np.array_equal(ctx.pairs_packed(sorted=True), want)
+        # a window that does not cover every local collider is a caller bug
+        ctx.update_transforms(s.pos, s.quat, s.scale)
+        ctx.set_global_bounds(ctx.phase_bounds())
+        ctx.set_x_window(int(home_x.min()) + 2, int(home_x.max()))
+        with pytest.raises(G.GscError) as ei:
+            ctx.phase_finish()
+        assert ei.value.code == N.GSC_ERR_INVALID
+        # and the plain step still works afterwards
+        ctx.update_transforms(s.pos, s.quat, s.scale)
+        ctx.step()
+        assert np.array_equal(ctx.pairs_packed(sorted=True), want)
+    oracle.close()
