@@ -50,6 +50,11 @@ struct gsc_ctx {
     uint32_t *d_entity = nullptr, *d_gidx = nullptr, *d_box_slot = nullptr;
     uint32_t n_box = 0;
     bool packed = false;  // d_quat / d_scale hold boxes only (gsc_update_transforms_packed)
+    // host -> device transform copies are cut into chunks; bvh_update starts on a chunk as soon as it has landed
+    static constexpr int kChunks = 8;
+    uint32_t chunk_begin[kChunks + 1] = {}, chunk_box[kChunks + 1] = {};
+    cudaEvent_t ev_chunk[kChunks] = {};
+    bool chunked = false;
     uint8_t *d_kind = nullptr;
     float *d_offset = nullptr, *d_size = nullptr;
     float *d_pos = nullptr, *d_quat = nullptr, *d_scale = nullptr;          // owned
@@ -94,7 +99,7 @@ struct gsc_ctx {
     bool bounds_done = false, global_bounds_set = false;
 
     cudaEvent_t ev[GSC_NUM_STAGES + 1] = {};
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_fence = nullptr;
 };
 
 namespace {
@@ -254,8 +259,10 @@ int gsc_create(const gsc_config *cfg, gsc_ctx **out)
     CR(cudaHostAlloc((void **)&c->h_fb, sizeof(FrameBlock), cudaHostAllocDefault));
     CR(cudaHostAlloc((void **)&c->h_enc, 8 * sizeof(uint32_t), cudaHostAllocDefault));
     for (auto &ev : c->ev) CR(cudaEventCreate(&ev));
+    for (auto &ev : c->ev_chunk) CR(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CR(cudaEventCreate(&c->ev_begin));
     CR(cudaEventCreate(&c->ev_end));
+    CR(cudaEventCreateWithFlags(&c->ev_fence, cudaEventDisableTiming));
     // identity quaternion / unit scale so a sphere-only caller may pass NULL for them
     k_fill_default_transforms<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>((uint32_t)M, c->d_quat, c->d_scale);
     CR(cudaGetLastError());
@@ -289,8 +296,11 @@ void gsc_destroy(gsc_ctx *c)
     if (c->h_enc) cudaFreeHost(c->h_enc);
     for (auto &ev : c->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto &ev : c->ev_chunk)
+        if (ev) cudaEventDestroy(ev);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
+    if (c->ev_fence) cudaEventDestroy(c->ev_fence);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -313,6 +323,11 @@ int gsc_upload_colliders(gsc_ctx *c, uint32_t n, const uint32_t *entity, const u
         n_box += kind[i] == GSC_BOX;
     }
     c->n_box = n_box;
+    for (int k = 0; k <= gsc_ctx::kChunks; ++k) {
+        const uint32_t b = k == gsc_ctx::kChunks ? n : (uint32_t)(((uint64_t)n * k / gsc_ctx::kChunks) & ~4095ull);
+        c->chunk_begin[k] = b;
+        c->chunk_box[k] = b < n ? slot[b] : n_box;
+    }
     if (n) {
         CU(c, cudaMemcpyAsync(c->d_box_slot, slot.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
         CU(c, cudaMemcpyAsync(c->d_entity, entity, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
@@ -327,6 +342,27 @@ int gsc_upload_colliders(gsc_ctx *c, uint32_t n, const uint32_t *entity, const u
     c->have_colliders = true;
     c->have_transforms = false;
     c->packed = false;
+    c->chunked = false;
+    return GSC_OK;
+}
+
+// Host -> device copy of one frame's transforms, cut into chunks on the copy stream with an event per chunk, so
+// that the next step's bvh_update overlaps the tail of the transfer (PCIe is the slowest link of the e2e step).
+// `box_packed`: quat / scale arrays are indexed by box slot instead of collider index.
+static int copy_transforms(gsc_ctx *c, uint32_t n, const float *pos3, const float *quat4, const float *scale3, bool box_packed)
+{
+    cudaStream_t cs = c->copy_stream;
+    CU(c, cudaEventRecord(c->ev_fence, c->stream));  // the copy must not overtake work still reading the old frame
+    CU(c, cudaStreamWaitEvent(cs, c->ev_fence, 0));
+    for (int k = 0; k < gsc_ctx::kChunks; ++k) {
+        const size_t b = c->chunk_begin[k], e = c->chunk_begin[k + 1];
+        const size_t qb = box_packed ? c->chunk_box[k] : b, qe = box_packed ? c->chunk_box[k + 1] : e;
+        if (e > b) CU(c, cudaMemcpyAsync(c->d_pos + 3 * b, pos3 + 3 * b, (e - b) * 12, cudaMemcpyHostToDevice, cs));
+        if (quat4 && qe > qb) CU(c, cudaMemcpyAsync(c->d_quat + 4 * qb, quat4 + 4 * qb, (qe - qb) * 16, cudaMemcpyHostToDevice, cs));
+        if (scale3 && qe > qb) CU(c, cudaMemcpyAsync(c->d_scale + 3 * qb, scale3 + 3 * qb, (qe - qb) * 12, cudaMemcpyHostToDevice, cs));
+        CU(c, cudaEventRecord(c->ev_chunk[k], cs));
+    }
+    c->chunked = true;
     return GSC_OK;
 }
 
@@ -336,14 +372,9 @@ int gsc_update_transforms(gsc_ctx *c, uint32_t n, const float *pos3, const float
     if (!c->have_colliders || n != c->n_local)
         return fail(c, GSC_ERR_INVALID, "gsc_update_transforms: n=%u does not match the %u uploaded colliders", n, c->n_local);
     if (n && !pos3) return fail(c, GSC_ERR_INVALID, "gsc_update_transforms: null positions");
-    if (n) {
-        // the three arrays go over two streams so the copies overlap on the two DMA engines
-        CU(c, cudaMemcpyAsync(c->d_pos, pos3, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
-        if (quat4) CU(c, cudaMemcpyAsync(c->d_quat, quat4, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
-        if (scale3) CU(c, cudaMemcpyAsync(c->d_scale, scale3, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
-    }
     if (c->packed && (!quat4 || !scale3) && c->n_box)
         return fail(c, GSC_ERR_INVALID, "gsc_update_transforms: after a packed update, pass rotation and scale again");
+    if (int rc = copy_transforms(c, n, pos3, quat4, scale3, false)) return rc;
     c->packed = false;
     c->b_pos = c->d_pos;
     c->b_quat = c->d_quat;
@@ -362,9 +393,7 @@ int gsc_update_transforms_packed(gsc_ctx *c, uint32_t n, const float *pos3, uint
     if (n && !pos3) return fail(c, GSC_ERR_INVALID, "gsc_update_transforms_packed: null positions");
     if (n_box && !c->packed && (!box_quat4 || !box_scale3))
         return fail(c, GSC_ERR_INVALID, "gsc_update_transforms_packed: the first packed update needs rotation and scale");
-    if (n) CU(c, cudaMemcpyAsync(c->d_pos, pos3, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
-    if (n_box && box_quat4) CU(c, cudaMemcpyAsync(c->d_quat, box_quat4, (size_t)n_box * 16, cudaMemcpyHostToDevice, c->stream));
-    if (n_box && box_scale3) CU(c, cudaMemcpyAsync(c->d_scale, box_scale3, (size_t)n_box * 12, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = copy_transforms(c, n, pos3, box_quat4, box_scale3, true)) return rc;
     c->packed = true;
     c->b_pos = c->d_pos;
     c->b_quat = c->d_quat;
@@ -384,6 +413,7 @@ int gsc_bind_device_transforms(gsc_ctx *c, uint32_t n, const float *d_pos3, cons
     if (c->packed && (!d_quat4 || !d_scale3) && c->n_box)
         return fail(c, GSC_ERR_INVALID, "gsc_bind_device_transforms: after a packed update, pass rotation and scale again");
     c->packed = false;
+    c->chunked = false;
     c->b_pos = d_pos3;
     c->b_quat = d_quat4 ? d_quat4 : c->d_quat;
     c->b_scale = d_scale3 ? d_scale3 : c->d_scale;
@@ -403,11 +433,15 @@ static int stage_bounds(gsc_ctx *c)
     c->n_ghost = 0;
     const bool timing = c->cfg.flags & GSC_FLAG_TIMING;
     if (timing) CU(c, cudaEventRecord(c->ev[0], s));
-    if (c->n_local) {
-        const uint32_t blocks = (c->n_local + kBvhThreads - 1) / kBvhThreads;
-        k_bvh_update<<<blocks, kBvhThreads, 0, s>>>(c->n_local, c->d_kind, c->d_offset, c->d_size, c->b_pos, c->b_quat,
-                                                   c->b_scale, c->d_entity, c->have_gidx ? c->d_gidx : nullptr, c->packed ? c->d_box_slot : nullptr, c->d_rec,
-                                                   c->d_obb, c->d_fb);
+    for (int k = 0; k < gsc_ctx::kChunks && c->n_local; ++k) {
+        // owned transforms arrive chunk by chunk on the copy stream; caller-bound device arrays are one chunk
+        const uint32_t b = c->chunked ? c->chunk_begin[k] : 0, e = c->chunked ? c->chunk_begin[k + 1] : c->n_local;
+        if (c->chunked) CU(c, cudaStreamWaitEvent(s, c->ev_chunk[k], 0));
+        if (e > b)
+            k_bvh_update<<<(e - b + kBvhThreads - 1) / kBvhThreads, kBvhThreads, 0, s>>>(
+                b, e, c->d_kind, c->d_offset, c->d_size, c->b_pos, c->b_quat, c->b_scale, c->d_entity,
+                c->have_gidx ? c->d_gidx : nullptr, c->packed ? c->d_box_slot : nullptr, c->d_rec, c->d_obb, c->d_fb);
+        if (!c->chunked) break;
     }
     CU(c, cudaGetLastError());
     if (timing) CU(c, cudaEventRecord(c->ev[1], s));

@@ -172,7 +172,7 @@ GSC_DEV void emit_finish(EmitBuf<WARPS, CAP> &b, uint2 *__restrict__ out, float4
 constexpr int kBvhThreads = 256;
 
 __global__ void __launch_bounds__(kBvhThreads)
-k_bvh_update(uint32_t n, const uint8_t *__restrict__ kind, const float *__restrict__ offset3,
+k_bvh_update(uint32_t first, uint32_t n, const uint8_t *__restrict__ kind, const float *__restrict__ offset3,
              const float *__restrict__ size3, const float *__restrict__ pos3, const float *__restrict__ quat4,
              const float *__restrict__ scale3, const uint32_t *__restrict__ entity,
              const uint32_t *__restrict__ gidx, const uint32_t *__restrict__ box_slot, float4 *__restrict__ rec,
@@ -180,7 +180,8 @@ k_bvh_update(uint32_t n, const uint8_t *__restrict__ kind, const float *__restri
 {
     // box_slot != nullptr: quat4 / scale3 are packed over the boxes only (gsc_update_transforms_packed);
     // box_slot[i] = number of boxes before collider i
-    const uint32_t i = blockIdx.x * kBvhThreads + threadIdx.x;
+    // colliders [first, n): the host layer launches one grid per arriving chunk of a host-to-device transform copy
+    const uint32_t i = first + blockIdx.x * kBvhThreads + threadIdx.x;
     float ext = 0.0f, mnx_max = -INFINITY;
     float mn[3] = { INFINITY, INFINITY, INFINITY }, mx[3] = { -INFINITY, -INFINITY, -INFINITY };
     uint32_t st = 0;
