@@ -239,7 +239,7 @@ int gsc_create(const gsc_config *cfg, gsc_ctx **out)
     CR(dmalloc(&c->d_scale, 3 * M));
     CR(dmalloc(&c->d_rec, 2 * M));
     CR(dmalloc(&c->d_rec_sorted, 2 * M));
-    CR(dmalloc(&c->d_qrec_sorted, M));
+    CR(dmalloc(&c->d_qrec_sorted, M + kPairTrip));  // k_pairs reads whole trips
     CR(dmalloc(&c->d_obb, 4 * M));
     for (int i = 0; i < 2; ++i) {
         CR(dmalloc(&c->d_keys[i], M));

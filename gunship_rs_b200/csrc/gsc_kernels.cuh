@@ -648,9 +648,12 @@ k_pairs(uint32_t n_total, const uint32_t *__restrict__ keys_a, const uint32_t *_
         const uint32_t qe = hi[r];
 #pragma unroll 1
         for (uint32_t q = lo[r]; q < qe; q += kPairTrip) {
+            // (reads up to kPairTrip - 1 records past the run: always inside the array, which is padded, and
+            // masked out of the test below)
+            const uint4 *bp = sv.q + q;
             uint4 b[kPairTrip];
 #pragma unroll
-            for (int k = 0; k < kPairTrip; ++k) b[k] = __ldg(sv.q + min(q + k, qe - 1));
+            for (int k = 0; k < kPairTrip; ++k) b[k] = __ldg(bp + k);
 #pragma unroll
             for (int k = 0; k < kPairTrip; ++k) {
                 const uint32_t qk = q + k;
