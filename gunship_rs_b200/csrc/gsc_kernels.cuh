@@ -575,7 +575,7 @@ __device__ __noinline__ void pair_drain_lane(PairShared &sh, uint32_t p, uint32_
     }
 }
 
-__global__ void __launch_bounds__(kPairThreads, 20)
+__global__ void __launch_bounds__(kPairThreads, 18)
 k_pairs(uint32_t n_total, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ keys_b,
         SortedVolumes sv, const uint32_t *__restrict__ cell_start, PairOut out, FrameBlock *__restrict__ fb)
 {
