@@ -786,7 +786,7 @@ int sort_standalone(gsc_ctx *c, cudaStream_t s, uint32_t n, uint32_t *keys[2], u
     const size_t words = 4 + sort_scratch_words(n);
     CU(c, cudaMalloc((void **)&scratch, words * 4));
     SortControl *ctl = reinterpret_cast<SortControl *>(scratch);
-    SortControl h{ passes, key_bits };
+    SortControl h{ passes, key_bits, radix_digit_bits(key_bits) };
     CU(c, cudaMemcpyAsync(ctl, &h, sizeof h, cudaMemcpyHostToDevice, s));
     launch_sort(s, n, keys, vals, identity, passes, ctl, scratch + 4);
     CU(c, cudaGetLastError());

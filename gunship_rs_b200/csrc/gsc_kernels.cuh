@@ -280,6 +280,7 @@ __global__ void k_grid_setup(FrameBlock *fb, unsigned long long max_cells, uint3
     for (int a = 0; a < 3; ++a) { g.origin[a] = 0; g.dims[a] = 0; g.qorg[a] = 0.0f; g.qscale[a] = 0.0f; }
     fb->sort.num_passes = 0;
     fb->sort.key_bits = 0;
+    fb->sort.digit_bits = 0;
     uint32_t st = 0;
     if (n_total == 0 || fb->bounds[0] == 0) {  // nothing to do (no colliders): valid stays 0, not an error
         fb->grid = g;
@@ -320,6 +321,7 @@ __global__ void k_grid_setup(FrameBlock *fb, unsigned long long max_cells, uint3
                 while ((1ull << bits) <= cells) ++bits;  // keys take values 0..cells (cells == wide)
                 fb->sort.num_passes = radix_passes(bits);
                 fb->sort.key_bits = bits;
+                fb->sort.digit_bits = radix_digit_bits(bits);
             }
         }
     }
@@ -352,12 +354,13 @@ k_cell_keys(uint32_t n_total, const float4 *__restrict__ rec, uint32_t *__restri
             FrameBlock *__restrict__ fb)
 {
     constexpr int WARPS = kKeyThreads / 32;
-    __shared__ uint32_t s_hist[WARPS][kRadix];
+    __shared__ __align__(16) uint16_t s_hist[WARPS][kRadix];
     const GridParams g = fb->grid;
     if (!g.valid) return;
     const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t mask = (1u << fb->sort.digit_bits) - 1u;
 #pragma unroll
-    for (int i = 0; i < WARPS * kRadix / (4 * kKeyThreads); ++i)
+    for (int i = 0; i < WARPS * kRadix / (8 * kKeyThreads); ++i)
         reinterpret_cast<uint4 *>(&s_hist[0][0])[tid + i * kKeyThreads] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     const uint32_t tile = blockIdx.x, tile_base = tile * (uint32_t)kSortTile;
@@ -381,13 +384,18 @@ k_cell_keys(uint32_t n_total, const float4 *__restrict__ rec, uint32_t *__restri
             key = ((uint32_t)c0[0] * (uint32_t)g.dims[1] + (uint32_t)c0[1]) * (uint32_t)g.dims[2] + (uint32_t)c0[2];
         }
         keys[i] = key;
-        atomicAdd(&s_hist[warp][key & 255u], 1u);
+        hist_add(s_hist[warp], key & mask);
     }
     __syncthreads();
-    uint32_t c = 0;
+    uint32_t c0 = 0, c1 = 0;
 #pragma unroll
-    for (int w = 0; w < WARPS; ++w) c += s_hist[w][tid];
-    tile_hist[(size_t)tid * num_tiles + tile] = c;
+    for (int w = 0; w < WARPS; ++w) {
+        const uint32_t v = reinterpret_cast<const uint32_t *>(s_hist[w])[tid];
+        c0 += v & 0xffffu;
+        c1 += v >> 16;
+    }
+    tile_hist[(size_t)(2 * tid) * num_tiles + tile] = c0;
+    tile_hist[(size_t)(2 * tid + 1) * num_tiles + tile] = c1;
 }
 
 // Cell-ordered volumes, the array k_pairs streams (one 32 B record = one DRAM sector per volume):

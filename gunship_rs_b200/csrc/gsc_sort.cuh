@@ -3,7 +3,7 @@
 // Replaces the reference's per-thread `HashMap<GridCell, Vec<*const BoundVolume>>` grouping
 // (grid_collision.rs:107, 434-444): colliders are grouped by cell by SORTING (key, index) pairs.
 //
-// LSD, 8-bit digits, three kernels per pass (upsweep / scan / downsweep, see below):
+// LSD, digits of up to 9 bits (the width is chosen per sort so that the passes share the key bits evenly), three kernels per pass (upsweep / scan / downsweep, see below):
 //   * the downsweep takes a tile of THREADS*IPT items per CTA, ranks them with warp-level
 //     __match_any_sync multisplit (stable), adds the scanned tile/digit offsets, stages the tile
 //     digit-sorted in shared memory and writes each digit run contiguously.
@@ -15,21 +15,28 @@
 
 namespace gsc {
 
-constexpr int kRadixBits = 8;
+constexpr int kRadixBits = 9;            // widest digit: 512 bins
 constexpr int kRadix = 1 << kRadixBits;
-constexpr int kMaxPasses = 4;  // 32-bit keys
-constexpr int kSortThreads = 256;
+constexpr int kMaxPasses = 4;            // 32-bit keys
+constexpr int kSortThreads = 256;        // each thread owns the two digits 2t and 2t+1
 constexpr int kSortIpt = 16;
 constexpr int kSortTile = kSortThreads * kSortIpt;
 
-// number of 8-bit passes for keys < 2^key_bits
+// passes for keys < 2^key_bits, and the digit width the passes share: 27-bit cell keys (16M colliders at 0.25 per cell)
+// take 3 passes of 9 bits instead of 4 of 8; 24 bits take 3 of 8; 32 bits 4 of 8
 __host__ __device__ inline int radix_passes(int key_bits) { return key_bits <= 0 ? 0 : (key_bits + kRadixBits - 1) / kRadixBits; }
+__host__ __device__ inline int radix_digit_bits(int key_bits)
+{
+    const int p = radix_passes(key_bits);
+    return p ? (key_bits + p - 1) / p : 0;
+}
 
 // Per-step control block living in device memory: written by k_grid_setup, read by the sort passes,
 // so that the number of passes (a function of the data-dependent grid size) needs no host round trip.
 struct SortControl {
     int num_passes;
-    int key_bits;  // significant key bits: the last pass ranks on fewer than 8
+    int key_bits;    // significant key bits
+    int digit_bits;  // radix_digit_bits(key_bits): every pass ranks on this many bits (the last one possibly fewer)
 };
 
 // exclusive scan of one value per thread over the first 256 threads of a CTA (all threads call)
@@ -59,22 +66,26 @@ __device__ __forceinline__ uint32_t block_excl_scan256(uint32_t v, uint32_t *s_w
 // ---- one radix pass = upsweep (per-tile digit counts) -> scan (over tiles, per digit) -> downsweep ----
 // A decoupled look-back ("onesweep") pass was measured first: on B200 the sort is instruction-issue bound, not
 // bandwidth bound (44 GB/s of HBM per SM), and the look-back's polling loops were half of all issued
-// instructions.  The extra 4 B/item read of the upsweep costs ~12 us per pass at 16M; the polling cost 70.
+// instructions.  The extra 4 B/item read of the upsweep costs ~20 us per pass at 16M; the polling cost 70.
 //   tile_hist[d * num_tiles + t] : count of digit d in tile t, then its exclusive prefix over tiles
 //   digit_total[d]               : count of digit d in the whole array
 //   ctl->num_passes is data dependent: passes beyond it exit at once and the ping-pong simply stops.
+
+// digit counters of one warp as u16 pairs: word t holds the digits 2t (low half) and 2t+1 (high half)
+__device__ __forceinline__ void hist_add(uint16_t *h, uint32_t d) { atomicAdd(reinterpret_cast<uint32_t *>(h) + (d >> 1), 1u << ((d & 1u) * 16)); }
 
 __global__ void __launch_bounds__(kSortThreads)
 k_radix_upsweep(const uint32_t *__restrict__ keys_in, uint32_t n, int pass, const SortControl *__restrict__ ctl,
                 uint32_t *__restrict__ tile_hist, uint32_t num_tiles)
 {
     constexpr int WARPS = kSortThreads / 32;
-    __shared__ uint32_t s_hist[WARPS][kRadix];
+    __shared__ __align__(16) uint16_t s_hist[WARPS][kRadix];  // a warp counts at most 512 items: u16 is plenty
     if (pass >= ctl->num_passes) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int shift = pass * kRadixBits;
+    const int shift = pass * ctl->digit_bits;
+    const uint32_t mask = (1u << ctl->digit_bits) - 1u;
 #pragma unroll
-    for (int i = 0; i < WARPS * kRadix / (4 * kSortThreads); ++i)
+    for (int i = 0; i < WARPS * kRadix / (8 * kSortThreads); ++i)
         reinterpret_cast<uint4 *>(&s_hist[0][0])[tid + i * kSortThreads] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     const uint32_t tile = blockIdx.x, tile_base = tile * (uint32_t)kSortTile;
@@ -88,16 +99,21 @@ k_radix_upsweep(const uint32_t *__restrict__ keys_in, uint32_t n, int pass, cons
     // plain shared atomics on the warp's private counters (MATCH.ANY-based aggregation was measured 5x slower:
     // the instruction serialises over the distinct values in the warp)
 #pragma unroll
-    for (int j = 0; j < kSortIpt; ++j) atomicAdd(&s_hist[warp][(key[j] >> shift) & 255u], 1u);
+    for (int j = 0; j < kSortIpt; ++j) hist_add(s_hist[warp], (key[j] >> shift) & mask);
     __syncthreads();
-    uint32_t c = 0;
+    uint32_t c0 = 0, c1 = 0;
 #pragma unroll
-    for (int w = 0; w < WARPS; ++w) c += s_hist[w][tid];
-    tile_hist[(size_t)tid * num_tiles + tile] = c;  // (padding of the last tile lands in digit 255 of that tile: harmless)
+    for (int w = 0; w < WARPS; ++w) {
+        const uint32_t v = reinterpret_cast<const uint32_t *>(s_hist[w])[tid];
+        c0 += v & 0xffffu;
+        c1 += v >> 16;
+    }
+    tile_hist[(size_t)(2 * tid) * num_tiles + tile] = c0;  // (padding of the last tile lands in the top digit of that tile: harmless)
+    tile_hist[(size_t)(2 * tid + 1) * num_tiles + tile] = c1;
 }
 
 // grid = kRadix CTAs: CTA d turns the counts of digit d into exclusive prefixes over the tiles.
-// The row is pulled through shared memory so that global accesses are coalesced 16 B per thread.
+// The row is pulled through shared memory so that global accesses are coalesced.
 constexpr int kScanChunk = 4096;  // tiles per round (16 KB of shared memory)
 
 __global__ void __launch_bounds__(256)
@@ -108,6 +124,10 @@ k_radix_scan(uint32_t *__restrict__ tile_hist, uint32_t num_tiles, int pass, con
     __shared__ uint32_t s_row[kScanChunk + kScanChunk / PER];  // padded: entry i lives at i + i / PER (no bank conflicts)
     __shared__ uint32_t s_warp[8];
     if (pass >= ctl->num_passes) return;
+    if (blockIdx.x >= (1u << ctl->digit_bits)) {  // digits this sort does not use
+        if (threadIdx.x == 0) digit_total[blockIdx.x] = 0;
+        return;
+    }
     uint32_t *row = tile_hist + (size_t)blockIdx.x * num_tiles;
     const int tid = threadIdx.x;
     uint32_t carry = 0;
@@ -115,7 +135,6 @@ k_radix_scan(uint32_t *__restrict__ tile_hist, uint32_t num_tiles, int pass, con
         const uint32_t cnt = min((uint32_t)kScanChunk, num_tiles - base);
         for (uint32_t i = tid; i < kScanChunk; i += 256) s_row[i + i / PER] = i < cnt ? row[base + i] : 0u;
         __syncthreads();
-        // thread t owns 16 consecutive entries
         uint32_t v[PER], sum = 0;
 #pragma unroll
         for (int k = 0; k < PER; ++k) {
@@ -149,9 +168,13 @@ k_radix_downsweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
 {
     constexpr int WARPS = kSortThreads / 32;
     constexpr int WTILE = 32 * kSortIpt;
-    __shared__ __align__(16) uint32_t s_hist[WARPS][kRadix];  // per-warp digit counts, then offsets within the digit
+    // per-warp digit counts, then offsets within the digit; dead once the keys are staged, so the staged values
+    // reuse the same 16 KB (keeps the kernel under the 48 KB of static shared memory)
+    static_assert(sizeof(uint32_t) * WARPS * kRadix == sizeof(uint32_t) * kSortTile, "hist/vals alias");
+    __shared__ __align__(16) uint32_t s_alias[kSortTile];
+    uint32_t(*s_hist)[kRadix] = reinterpret_cast<uint32_t(*)[kRadix]>(s_alias);
+    uint32_t *s_vals = s_alias;
     __shared__ uint32_t s_keys[kSortTile];
-    __shared__ uint32_t s_vals[kSortTile];
     __shared__ uint32_t s_bin[kRadix];   // first tile position of each digit
     __shared__ uint32_t s_goff[kRadix];  // output position of digit run d minus its tile position
     __shared__ uint32_t s_warp[8];
@@ -159,16 +182,18 @@ k_radix_downsweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
     if (pass >= ctl->num_passes) return;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int shift = pass * kRadixBits;
+    const int shift = pass * ctl->digit_bits;
+    const uint32_t mask = (1u << ctl->digit_bits) - 1u;
 #pragma unroll
     for (int i = 0; i < WARPS * kRadix / (4 * kSortThreads); ++i)
-        reinterpret_cast<uint4 *>(&s_hist[0][0])[tid + i * kSortThreads] = make_uint4(0u, 0u, 0u, 0u);
+        reinterpret_cast<uint4 *>(s_alias)[tid + i * kSortThreads] = make_uint4(0u, 0u, 0u, 0u);
     const uint32_t tile = blockIdx.x;
     const uint32_t tile_base = tile * (uint32_t)kSortTile;
     const uint32_t warp_base = tile_base + warp * WTILE + lane;
-    // this tile's output offsets: issued now, consumed after the ranking
-    const uint32_t tile_excl = tile_hist[(size_t)tid * num_tiles + tile];
-    const uint32_t dtotal = digit_total[tid];
+    // this tile's output offsets for the thread's two digits: issued now, consumed after the ranking
+    const uint32_t tile_excl0 = tile_hist[(size_t)(2 * tid) * num_tiles + tile];
+    const uint32_t tile_excl1 = tile_hist[(size_t)(2 * tid + 1) * num_tiles + tile];
+    const uint2 dtotal = reinterpret_cast<const uint2 *>(digit_total)[tid];
 
     uint32_t key[kSortIpt];
 #pragma unroll
@@ -181,12 +206,12 @@ k_radix_downsweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
     // ---- stable ranking inside the warp: order is (j, lane) == original order ----
     // peers = lanes holding the same digit, from one ballot per significant digit bit (MATCH.ANY serialises over
     // the distinct values of the warp and was measured ~50 cycles per instruction and SM)
-    const int digit_bits = min(kRadixBits, ctl->key_bits - shift);
+    const int digit_bits = min(ctl->digit_bits, ctl->key_bits - shift);
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint16_t rank[kSortIpt];
 #pragma unroll
     for (int j = 0; j < kSortIpt; ++j) {
-        const uint32_t d = (key[j] >> shift) & 255u;
+        const uint32_t d = (key[j] >> shift) & mask;
         uint32_t peers = 0xffffffffu;
 #pragma unroll
         for (int b = 0; b < kRadixBits; ++b) {
@@ -205,24 +230,29 @@ k_radix_downsweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
     }
     __syncthreads();
 
-    // ---- per digit (thread t owns digit t): warp counts -> offsets within the digit, tile count ----
-    uint32_t tile_count = 0;
+    // ---- per digit pair (thread t owns digits 2t, 2t+1): warp counts -> offsets within the digit, tile counts ----
+    uint32_t cnt0 = 0, cnt1 = 0;
 #pragma unroll
     for (int w = 0; w < WARPS; ++w) {
-        const uint32_t cnt = s_hist[w][tid];
-        s_hist[w][tid] = tile_count;
-        tile_count += cnt;
+        uint2 *pair = reinterpret_cast<uint2 *>(s_hist[w]) + tid;
+        const uint2 v = *pair;
+        *pair = make_uint2(cnt0, cnt1);
+        cnt0 += v.x;
+        cnt1 += v.y;
     }
-    const uint32_t digit_base = block_excl_scan256(dtotal, s_warp, nullptr);
-    const uint32_t bin_start = block_excl_scan256(tile_count, s_warp, nullptr);
-    s_bin[tid] = bin_start;
-    s_goff[tid] = digit_base + tile_excl - bin_start;
+    // exclusive scans over the 512 digits in digit order: scan the pair sums, the odd digit adds its even sibling
+    const uint32_t digit_base = block_excl_scan256(dtotal.x + dtotal.y, s_warp, nullptr);
+    const uint32_t bin_start = block_excl_scan256(cnt0 + cnt1, s_warp, nullptr);
+    s_bin[2 * tid] = bin_start;
+    s_bin[2 * tid + 1] = bin_start + cnt0;
+    s_goff[2 * tid] = digit_base + tile_excl0 - bin_start;
+    s_goff[2 * tid + 1] = digit_base + dtotal.x + tile_excl1 - (bin_start + cnt0);
     __syncthreads();
 
     // ---- stage the tile digit-sorted in shared memory ----
 #pragma unroll
     for (int j = 0; j < kSortIpt; ++j) {
-        const uint32_t d = (key[j] >> shift) & 255u;
+        const uint32_t d = (key[j] >> shift) & mask;
         const uint32_t pos = (uint32_t)rank[j] + s_hist[warp][d] + s_bin[d];
         rank[j] = (uint16_t)pos;
         s_keys[pos] = key[j];
@@ -237,6 +267,7 @@ k_radix_downsweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
 #pragma unroll
         for (int j = 0; j < kSortIpt; ++j) key[j] = warp_base + j * 32;
     }
+    __syncthreads();  // every warp is done reading the counters that s_vals overwrites
 #pragma unroll
     for (int j = 0; j < kSortIpt; ++j) s_vals[rank[j]] = key[j];
     __syncthreads();
@@ -249,7 +280,7 @@ k_radix_downsweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
         const uint32_t i = tid + j * kSortThreads;
         if (i < valid) {
             const uint32_t k = s_keys[i];
-            const uint32_t dst = s_goff[(k >> shift) & 255u] + i;
+            const uint32_t dst = s_goff[(k >> shift) & mask] + i;
             keys_out[dst] = k;
             vals_out[dst] = s_vals[i];
         }
