@@ -19,7 +19,9 @@ GSC_HALO_RECORD_BYTES = 96
 GSC_MAX_PEERS = 16
 GSC_IPC_EXPORT_BYTES = 256
 STAGE_NAMES = ("bvh_update", "cell_keys", "sort", "cell_table", "pairs", "narrow")
-(GSC_DBG_AABB, GSC_DBG_SORTED_KEYS, GSC_DBG_SORTED_IDX, GSC_DBG_CELL_START, GSC_DBG_OBB) = range(5)
+(GSC_DBG_AABB, GSC_DBG_SORTED_KEYS, GSC_DBG_SORTED_IDX, GSC_DBG_CELL_START, GSC_DBG_OBB, GSC_DBG_ENTITY, GSC_DBG_KIND,
+ GSC_DBG_OFFSET, GSC_DBG_SIZE) = range(9)
+GSC_NO_PARENT = 0xFFFFFFFF
 
 ERROR_NAMES = {GSC_ERR_INVALID: "GSC_ERR_INVALID", GSC_ERR_CUDA: "GSC_ERR_CUDA", GSC_ERR_NCCL: "GSC_ERR_NCCL",
                GSC_ERR_CAPACITY: "GSC_ERR_CAPACITY", GSC_ERR_RANGE: "GSC_ERR_RANGE", GSC_ERR_KIND: "GSC_ERR_KIND"}
@@ -65,7 +67,9 @@ EXPORTS = (
     "gsc_sort_pairs_u32", "gsc_phase_bounds", "gsc_set_global_bounds", "gsc_local_x_range", "gsc_halo_select",
     "gsc_halo_append", "gsc_phase_finish", "gsc_set_x_window", "gsc_ipc_export", "gsc_ipc_open_peer", "gsc_halo_push",
     "gsc_halo_sync", "gsc_halo_commit", "gsc_download_contacts", "gsc_contact_sphere_sphere", "gsc_contact_sphere_obb",
-    "gsc_contact_obb_obb", "gsc_build_adjacency", "gsc_download_adjacency",
+    "gsc_contact_obb_obb", "gsc_build_adjacency", "gsc_download_adjacency", "gsc_step_begin", "gsc_step_end",
+    "gsc_append_colliders", "gsc_remove_colliders", "gsc_collider_count", "gsc_hierarchy_upload", "gsc_hierarchy_update",
+    "gsc_hierarchy_download",
 )
 
 _lib = None
@@ -92,6 +96,14 @@ def load():
     L.gsc_update_transforms_packed.argtypes = [vp, C.c_uint32, f32p, C.c_uint32, f32p, f32p]
     L.gsc_bind_device_transforms.argtypes = [vp, C.c_uint32, vp, vp, vp]
     L.gsc_step.argtypes = [vp, C.POINTER(GscStepOut)]
+    L.gsc_step_begin.argtypes = [vp]
+    L.gsc_step_end.argtypes = [vp, C.POINTER(GscStepOut)]
+    L.gsc_append_colliders.argtypes = [vp, C.c_uint32, u32p, u8p, f32p, f32p]
+    L.gsc_remove_colliders.argtypes = [vp, C.c_uint32, u32p]
+    L.gsc_collider_count.argtypes = [vp, C.POINTER(C.c_uint32)]
+    L.gsc_hierarchy_upload.argtypes = [vp, C.c_uint32, C.c_uint32, u32p, u32p, C.c_uint32, u32p]
+    L.gsc_hierarchy_update.argtypes = [vp, f32p, f32p, f32p]
+    L.gsc_hierarchy_download.argtypes = [vp, f32p, f32p, f32p, f32p]
     L.gsc_download_pairs.argtypes = [vp, u32p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
     L.gsc_debug_download.argtypes = [vp, C.c_int, vp, C.c_size_t]
     L.gsc_build_adjacency.argtypes = [vp, C.POINTER(GscAdjacency)]

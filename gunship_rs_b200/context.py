@@ -96,6 +96,56 @@ class CollisionContext:
         self._check(rc)
         return out
 
+    # the same step in two halves: the next frame's update_transforms* may be issued in between (gsc_step_begin)
+    def step_begin(self):
+        self._check(self._lib.gsc_step_begin(self._h))
+
+    def step_end(self) -> N.GscStepOut:
+        out = N.GscStepOut()
+        rc = self._lib.gsc_step_end(self._h, C.byref(out))
+        self.last = out
+        self._check(rc)
+        return out
+
+    # lifecycle after the first upload: ColliderManager::assign / BoundingVolumeManager::destroy_immediate
+    def append_colliders(self, entity, kind, offset, size):
+        e, k = _c(entity, np.uint32), _c(kind, np.uint8)
+        o, s = _c(offset, np.float32), _c(size, np.float32)
+        self._check(self._lib.gsc_append_colliders(self._h, int(e.shape[0]), _ptr(e), _ptr(k), _ptr(o), _ptr(s)))
+        self.n += int(e.shape[0])
+        self.n_box += int((k == N.GSC_BOX).sum())
+
+    def remove_colliders(self, index):
+        """swap_remove the dense positions index[0], index[1], ... in that order (bounding_volume.rs:82-104)."""
+        i = _c(index, np.uint32)
+        self._check(self._lib.gsc_remove_colliders(self._h, int(i.shape[0]), _ptr(i)))
+        self.n = self.collider_count()
+        self.n_box = int((self.debug(N.GSC_DBG_KIND) == N.GSC_BOX).sum()) if self.n else 0
+
+    def collider_count(self) -> int:
+        n = C.c_uint32(0)
+        self._check(self._lib.gsc_collider_count(self._h, C.byref(n)))
+        return int(n.value)
+
+    # TransformManager::update_transforms on the device (component/transform.rs:243-251, 588-608)
+    def hierarchy_upload(self, row_begin, parent, collider_node):
+        rb, p, cn = _c(row_begin, np.uint32), _c(parent, np.uint32), _c(collider_node, np.uint32)
+        self.n_nodes = int(p.shape[0])
+        self._check(self._lib.gsc_hierarchy_upload(self._h, self.n_nodes, int(rb.shape[0]) - 1, _ptr(rb), _ptr(p),
+                                                   int(cn.shape[0]), _ptr(cn)))
+
+    def hierarchy_update(self, local_pos=None, local_quat=None, local_scale=None):
+        p, q, s = _c(local_pos, np.float32), _c(local_quat, np.float32), _c(local_scale, np.float32)
+        self._check(self._lib.gsc_hierarchy_update(self._h, _ptr(p), _ptr(q), _ptr(s)))
+
+    def hierarchy_download(self):
+        """derived (pos[n,3], quat[n,4], scale[n,3], matrix[n,4,4]) of every node"""
+        n = self.n_nodes
+        pos, quat = np.zeros((n, 3), np.float32), np.zeros((n, 4), np.float32)
+        scale, mat = np.zeros((n, 3), np.float32), np.zeros((n, 4, 4), np.float32)
+        self._check(self._lib.gsc_hierarchy_download(self._h, _ptr(pos), _ptr(quat), _ptr(scale), _ptr(mat)))
+        return pos, quat, scale, mat
+
     def pairs(self, sorted: bool = True) -> np.ndarray:
         """(n,2) uint32: (entity of later volume, entity of earlier volume) -- grid_collision.rs:119,497."""
         n = C.c_uint64(0)
@@ -137,6 +187,10 @@ class CollisionContext:
             out = np.zeros((n, 16), dtype=np.float32)
         elif what == N.GSC_DBG_CELL_START:
             out = np.zeros(int(self.last.n_cells) + 1, dtype=np.uint32)
+        elif what == N.GSC_DBG_KIND:
+            out = np.zeros(n, dtype=np.uint8)
+        elif what in (N.GSC_DBG_OFFSET, N.GSC_DBG_SIZE):
+            out = np.zeros((n, 3), dtype=np.float32)
         else:
             out = np.zeros(n, dtype=np.uint32)
         self._check(self._lib.gsc_debug_download(self._h, what, _ptr(out), out.nbytes))

@@ -14,8 +14,10 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
+#include "gsc_hierarchy.cuh"
 #include "gsc_kernels.cuh"
 
 using namespace gsc;
@@ -97,6 +99,16 @@ struct gsc_ctx {
     uint64_t max_pairs = 0, max_cands = 0, max_cells = 0;
     uint64_t last_pairs = 0;
     bool bounds_done = false, global_bounds_set = false;
+    std::vector<uint8_t> h_kind;  // host mirror of d_kind: box slots / chunk cuts are recomputed from it on append / remove
+
+    // transform hierarchy (gsc_hierarchy_*): local and derived values per node, device resident
+    uint32_t hier_nodes = 0, hier_cap = 0, hier_colliders = 0;
+    std::vector<uint32_t> hier_row_begin;
+    uint32_t *d_hier_parent = nullptr, *d_hier_node = nullptr;
+    float *d_lpos = nullptr, *d_lquat = nullptr, *d_lscale = nullptr;
+    float *d_dpos = nullptr, *d_dquat = nullptr, *d_dscale = nullptr, *d_dmat = nullptr;
+    bool hier_local[3] = { false, false, false }, hier_derived = false;
+    bool in_flight = false;  // gsc_step_begin enqueued a step that gsc_step_end has not collected yet
 
     cudaEvent_t ev[GSC_NUM_STAGES + 1] = {};
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_fence = nullptr;
@@ -121,6 +133,11 @@ int fail(gsc_ctx *c, int code, const char *fmt, ...)
         cudaError_t e_ = (expr);                                                                      \
         if (e_ != cudaSuccess)                                                                        \
             return fail((c), GSC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define NOT_IN_FLIGHT(c, what)                                                                                \
+    do {                                                                                                      \
+        if ((c)->in_flight) return fail((c), GSC_ERR_INVALID, what ": a step is in flight (call gsc_step_end first)"); \
     } while (0)
 
 template <class T>
@@ -186,6 +203,30 @@ int status_to_error(gsc_ctx *c, const FrameBlock &fb)
     if (st & kStRange) return fail(c, GSC_ERR_RANGE, "a grid coordinate leaves the i16 range of GridCoord (grid_collision.rs:535)");
     if (st & kStWindow) return fail(c, GSC_ERR_INVALID, "gsc_set_x_window does not cover the home cell of a local collider");
     if (st & kStCells) return fail(c, GSC_ERR_CAPACITY, "dense cell table too small: raise gsc_config.max_cells (have %llu)", (unsigned long long)c->max_cells);
+    return GSC_OK;
+}
+
+// box_slot[i] = number of boxes before collider i (where a box finds its rotation / scale in the packed arrays of
+// gsc_update_transforms_packed), and the chunk cuts of the host-to-device transform copies; from the host mirror of kind
+int rebuild_box_slots(gsc_ctx *c)
+{
+    const uint32_t n = c->n_local;
+    std::vector<uint32_t> slot(n);
+    uint32_t n_box = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        slot[i] = n_box;
+        n_box += c->h_kind[i] == GSC_BOX;
+    }
+    c->n_box = n_box;
+    for (int k = 0; k <= gsc_ctx::kChunks; ++k) {
+        const uint32_t b = k == gsc_ctx::kChunks ? n : (uint32_t)(((uint64_t)n * k / gsc_ctx::kChunks) & ~4095ull);
+        c->chunk_begin[k] = b;
+        c->chunk_box[k] = b < n ? slot[b] : n_box;
+    }
+    if (n) {
+        CU(c, cudaMemcpyAsync(c->d_box_slot, slot.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));  // `slot` dies with this scope
+    }
     return GSC_OK;
 }
 
@@ -289,7 +330,8 @@ void gsc_destroy(gsc_ctx *c)
     void *bufs[] = { c->d_entity, c->d_gidx, c->d_box_slot, c->d_kind, c->d_offset, c->d_size, c->d_pos, c->d_quat, c->d_scale, c->d_rec,
                      c->d_rec_sorted, c->d_qrec_sorted, c->d_obb, c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1], c->d_cell_start,
                      c->d_wide, c->d_gaps, c->d_pairs, c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->d_pairs_sorted, c->d_contacts, c->d_contacts_sorted, c->d_perm, c->d_adj_entity, c->d_adj_offset, c->d_adj_other, c->d_fb, c->d_sort_scratch,
-                     c->d_halo_rec, c->d_halo_obb, c->d_halo_count };
+                     c->d_halo_rec, c->d_halo_obb, c->d_halo_count, c->d_hier_parent, c->d_hier_node, c->d_lpos, c->d_lquat,
+                     c->d_lscale, c->d_dpos, c->d_dquat, c->d_dscale, c->d_dmat };
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (c->h_fb) cudaFreeHost(c->h_fb);
@@ -310,26 +352,16 @@ int gsc_upload_colliders(gsc_ctx *c, uint32_t n, const uint32_t *entity, const u
                          const float *size3, const uint32_t *global_index)
 {
     if (int rc = check_ctx(c)) return rc;
+    NOT_IN_FLIGHT(c, "gsc_upload_colliders");
     if (n > c->cap) return fail(c, GSC_ERR_CAPACITY, "gsc_upload_colliders: %u colliders > max_colliders %u", n, c->cap);
     if (n && (!entity || !kind || !offset3 || !size3)) return fail(c, GSC_ERR_INVALID, "gsc_upload_colliders: null array");
     for (uint32_t i = 0; i < n; ++i)
         if (kind[i] > GSC_BOX)
             return fail(c, GSC_ERR_KIND, "collider %u is a Mesh: unimplemented!() in the reference (mod.rs:331)", i);
-    // box_slot[i] = number of boxes before collider i: where a box finds its rotation / scale in the packed arrays
-    std::vector<uint32_t> slot(n);
-    uint32_t n_box = 0;
-    for (uint32_t i = 0; i < n; ++i) {
-        slot[i] = n_box;
-        n_box += kind[i] == GSC_BOX;
-    }
-    c->n_box = n_box;
-    for (int k = 0; k <= gsc_ctx::kChunks; ++k) {
-        const uint32_t b = k == gsc_ctx::kChunks ? n : (uint32_t)(((uint64_t)n * k / gsc_ctx::kChunks) & ~4095ull);
-        c->chunk_begin[k] = b;
-        c->chunk_box[k] = b < n ? slot[b] : n_box;
-    }
+    c->h_kind.assign(kind, kind + n);
+    c->n_local = n;
+    if (int rc = rebuild_box_slots(c)) return rc;
     if (n) {
-        CU(c, cudaMemcpyAsync(c->d_box_slot, slot.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
         CU(c, cudaMemcpyAsync(c->d_entity, entity, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
         CU(c, cudaMemcpyAsync(c->d_kind, kind, (size_t)n, cudaMemcpyHostToDevice, c->stream));
         CU(c, cudaMemcpyAsync(c->d_offset, offset3, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
@@ -337,12 +369,104 @@ int gsc_upload_colliders(gsc_ctx *c, uint32_t n, const uint32_t *entity, const u
         if (global_index) CU(c, cudaMemcpyAsync(c->d_gidx, global_index, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
     }
     CU(c, cudaStreamSynchronize(c->stream));
-    c->n_local = n;
     c->have_gidx = global_index != nullptr;
     c->have_colliders = true;
     c->have_transforms = false;
     c->packed = false;
     c->chunked = false;
+    c->hier_colliders = 0;
+    return GSC_OK;
+}
+
+int gsc_collider_count(gsc_ctx *c, uint32_t *n_out)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!n_out) return fail(c, GSC_ERR_INVALID, "gsc_collider_count: null output");
+    *n_out = c->n_local;
+    return GSC_OK;
+}
+
+// ColliderManager::assign after the first upload: the dense arrays grow at the end (struct_component_manager.rs:83-96,
+// bounding_volume.rs:394-407); the colliders already on the device are not touched.
+int gsc_append_colliders(gsc_ctx *c, uint32_t n_new, const uint32_t *entity, const uint8_t *kind, const float *offset3,
+                         const float *size3)
+{
+    if (int rc = check_ctx(c)) return rc;
+    NOT_IN_FLIGHT(c, "gsc_append_colliders");
+    if (!c->have_colliders) return fail(c, GSC_ERR_INVALID, "gsc_append_colliders before gsc_upload_colliders");
+    if (c->have_gidx) return fail(c, GSC_ERR_INVALID, "gsc_append_colliders: contexts with explicit global indices (slabs) re-upload instead");
+    if (n_new && (!entity || !kind || !offset3 || !size3)) return fail(c, GSC_ERR_INVALID, "gsc_append_colliders: null array");
+    const uint32_t n0 = c->n_local;
+    if ((uint64_t)n0 + n_new > c->cap)
+        return fail(c, GSC_ERR_CAPACITY, "gsc_append_colliders: %u + %u colliders > max_colliders %u", n0, n_new, c->cap);
+    for (uint32_t i = 0; i < n_new; ++i)
+        if (kind[i] > GSC_BOX)
+            return fail(c, GSC_ERR_KIND, "collider %u is a Mesh: unimplemented!() in the reference (mod.rs:331)", n0 + i);
+    if (n_new) {
+        CU(c, cudaMemcpyAsync(c->d_entity + n0, entity, (size_t)n_new * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->d_kind + n0, kind, (size_t)n_new, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->d_offset + 3 * (size_t)n0, offset3, (size_t)n_new * 12, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->d_size + 3 * (size_t)n0, size3, (size_t)n_new * 12, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
+    c->h_kind.insert(c->h_kind.end(), kind, kind + n_new);
+    c->n_local = n0 + n_new;
+    if (int rc = rebuild_box_slots(c)) return rc;
+    c->have_transforms = false;
+    c->packed = false;
+    c->chunked = false;
+    c->hier_colliders = 0;
+    return GSC_OK;
+}
+
+// BoundingVolumeManager::destroy_immediate (bounding_volume.rs:82-104) for a sequence of dense indices: each one is a
+// swap_remove (the last element moves into the hole).  The host works out the NET moves of the whole sequence --
+// position -> original position of the element that ends up there -- and one kernel applies them to the static
+// arrays on the device.  Every source lies at or behind the new length and every destination before it, so the
+// gather has no read-after-write hazard.
+int gsc_remove_colliders(gsc_ctx *c, uint32_t n_remove, const uint32_t *index)
+{
+    if (int rc = check_ctx(c)) return rc;
+    NOT_IN_FLIGHT(c, "gsc_remove_colliders");
+    if (!c->have_colliders) return fail(c, GSC_ERR_INVALID, "gsc_remove_colliders before gsc_upload_colliders");
+    if (c->have_gidx) return fail(c, GSC_ERR_INVALID, "gsc_remove_colliders: contexts with explicit global indices (slabs) re-upload instead");
+    if (n_remove && !index) return fail(c, GSC_ERR_INVALID, "gsc_remove_colliders: null index array");
+    if (n_remove > c->n_local) return fail(c, GSC_ERR_INVALID, "gsc_remove_colliders: %u removals from %u colliders", n_remove, c->n_local);
+    for (uint32_t k = 0; k < n_remove; ++k)  // validate before anything is touched
+        if (index[k] >= c->n_local - k)
+            return fail(c, GSC_ERR_INVALID, "gsc_remove_colliders: index[%u] = %u but only %u colliders are left", k, index[k], c->n_local - k);
+    uint32_t len = c->n_local;
+    std::unordered_map<uint32_t, uint32_t> origin;  // position -> original position of its current element (absent: itself)
+    origin.reserve(2 * (size_t)n_remove + 8);
+    auto at = [&](uint32_t pos) { auto it = origin.find(pos); return it == origin.end() ? pos : it->second; };
+    for (uint32_t k = 0; k < n_remove; ++k) {
+        const uint32_t i = index[k];
+        const uint32_t last = len - 1;
+        if (i != last) origin[i] = at(last);
+        origin.erase(last);
+        c->h_kind[i] = c->h_kind[last];  // the same swap_remove on the host mirror
+        c->h_kind.pop_back();
+        len = last;
+    }
+    std::vector<uint2> moves;
+    moves.reserve(origin.size());
+    for (const auto &kv : origin)
+        if (kv.first < len && kv.second != kv.first) moves.push_back(make_uint2(kv.first, kv.second));
+    if (!moves.empty()) {
+        Scratch tmp;
+        CU(c, cudaMalloc(&tmp.p[0], moves.size() * sizeof(uint2)));
+        CU(c, cudaMemcpyAsync(tmp.p[0], moves.data(), moves.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+        k_apply_moves<<<(unsigned)((moves.size() + 255) / 256), 256, 0, c->stream>>>((uint32_t)moves.size(), (const uint2 *)tmp.p[0],
+                                                                                     c->d_kind, c->d_offset, c->d_size, c->d_entity);
+        CU(c, cudaGetLastError());
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
+    c->n_local = len;
+    if (int rc = rebuild_box_slots(c)) return rc;
+    c->have_transforms = false;
+    c->packed = false;
+    c->chunked = false;
+    c->hier_colliders = 0;
     return GSC_OK;
 }
 
@@ -352,7 +476,9 @@ int gsc_upload_colliders(gsc_ctx *c, uint32_t n, const uint32_t *entity, const u
 static int copy_transforms(gsc_ctx *c, uint32_t n, const float *pos3, const float *quat4, const float *scale3, bool box_packed)
 {
     cudaStream_t cs = c->copy_stream;
-    CU(c, cudaEventRecord(c->ev_fence, c->stream));  // the copy must not overtake work still reading the old frame
+    // The copy must not overtake the one reader of the transform arrays: bvh_update of the last enqueued step
+    // (ev_fence is recorded right behind it).  The REST of a step in flight (gsc_step_begin) keeps running under
+    // the transfer -- that overlap is the point of the begin/end form.
     CU(c, cudaStreamWaitEvent(cs, c->ev_fence, 0));
     for (int k = 0; k < gsc_ctx::kChunks; ++k) {
         const size_t b = c->chunk_begin[k], e = c->chunk_begin[k + 1];
@@ -444,6 +570,7 @@ static int stage_bounds(gsc_ctx *c)
         if (!c->chunked) break;
     }
     CU(c, cudaGetLastError());
+    CU(c, cudaEventRecord(c->ev_fence, s));  // the frame's transforms are consumed: the next frame's copy may land
     if (timing) CU(c, cudaEventRecord(c->ev[1], s));
     c->bounds_done = true;
     c->global_bounds_set = false;
@@ -451,7 +578,7 @@ static int stage_bounds(gsc_ctx *c)
     return GSC_OK;
 }
 
-static int stage_finish(gsc_ctx *c, gsc_step_out *out)
+static int stage_enqueue(gsc_ctx *c)
 {
     cudaStream_t s = c->stream;
     const bool timing = c->cfg.flags & GSC_FLAG_TIMING;
@@ -489,11 +616,17 @@ static int stage_finish(gsc_ctx *c, gsc_step_out *out)
     CU(c, cudaGetLastError());
     CU(c, cudaMemcpyAsync(c->h_fb, fb, sizeof(FrameBlock), cudaMemcpyDeviceToHost, s));
     CU(c, cudaEventRecord(c->ev_end, s));
-    CU(c, cudaStreamSynchronize(s));
     c->bounds_done = false;
     c->perm_valid = false;
     c->adj_valid = false;
+    c->last_pairs = 0;
+    return GSC_OK;
+}
 
+static int stage_collect(gsc_ctx *c, gsc_step_out *out)
+{
+    const bool timing = c->cfg.flags & GSC_FLAG_TIMING;
+    CU(c, cudaStreamSynchronize(c->stream));
     const FrameBlock &h = *c->h_fb;
     c->last_pairs = std::min<uint64_t>(h.n_pairs, c->max_pairs);
     if (out) {
@@ -528,16 +661,42 @@ static int stage_finish(gsc_ctx *c, gsc_step_out *out)
     return GSC_OK;
 }
 
+static int stage_finish(gsc_ctx *c, gsc_step_out *out)
+{
+    if (int rc = stage_enqueue(c)) return rc;
+    return stage_collect(c, out);
+}
+
 int gsc_step(gsc_ctx *c, gsc_step_out *out)
 {
     if (int rc = check_ctx(c)) return rc;
+    NOT_IN_FLIGHT(c, "gsc_step");
     if (int rc = stage_bounds(c)) return rc;
     return stage_finish(c, out);
+}
+
+int gsc_step_begin(gsc_ctx *c)
+{
+    if (int rc = check_ctx(c)) return rc;
+    NOT_IN_FLIGHT(c, "gsc_step_begin");
+    if (int rc = stage_bounds(c)) return rc;
+    if (int rc = stage_enqueue(c)) return rc;
+    c->in_flight = true;
+    return GSC_OK;
+}
+
+int gsc_step_end(gsc_ctx *c, gsc_step_out *out)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!c->in_flight) return fail(c, GSC_ERR_INVALID, "gsc_step_end without gsc_step_begin");
+    c->in_flight = false;
+    return stage_collect(c, out);
 }
 
 int gsc_phase_bounds(gsc_ctx *c, gsc_bounds *local)
 {
     if (int rc = check_ctx(c)) return rc;
+    NOT_IN_FLIGHT(c, "gsc_phase_bounds");
     if (!local) return fail(c, GSC_ERR_INVALID, "gsc_phase_bounds: null output");
     if (int rc = stage_bounds(c)) return rc;
     CU(c, cudaMemcpyAsync(c->h_fb, c->d_fb, sizeof(FrameBlock), cudaMemcpyDeviceToHost, c->stream));
@@ -835,6 +994,7 @@ static int ensure_sorted_perm(gsc_ctx *c)
 int gsc_download_pairs(gsc_ctx *c, uint32_t *dst, uint64_t cap_pairs, int sorted, uint64_t *n_out)
 {
     if (int rc = check_ctx(c)) return rc;
+    NOT_IN_FLIGHT(c, "gsc_download_pairs");
     const uint64_t n = c->last_pairs;
     if (n_out) *n_out = n;
     if (n == 0 || (!dst && cap_pairs == 0)) return GSC_OK;  // (NULL, 0) only queries the count
@@ -855,6 +1015,7 @@ int gsc_download_pairs(gsc_ctx *c, uint32_t *dst, uint64_t cap_pairs, int sorted
 int gsc_download_contacts(gsc_ctx *c, float *dst, uint64_t cap_pairs, int sorted, uint64_t *n_out)
 {
     if (int rc = check_ctx(c)) return rc;
+    NOT_IN_FLIGHT(c, "gsc_download_contacts");
     if (!c->d_contacts) return fail(c, GSC_ERR_INVALID, "gsc_download_contacts: the context was created without GSC_FLAG_CONTACTS");
     const uint64_t n = c->last_pairs;
     if (n_out) *n_out = n;
@@ -946,6 +1107,7 @@ extern "C" {
 int gsc_build_adjacency(gsc_ctx *c, gsc_adjacency *out)
 {
     if (int rc = check_ctx(c)) return rc;
+    NOT_IN_FLIGHT(c, "gsc_build_adjacency");
     if (!out) return fail(c, GSC_ERR_INVALID, "gsc_build_adjacency: null output");
     memset(out, 0, sizeof *out);
     const uint64_t h = c->last_pairs;
@@ -1025,9 +1187,115 @@ int gsc_download_adjacency(gsc_ctx *c, uint32_t *entity, uint32_t *offset, uint3
     return GSC_OK;
 }
 
+// ---- transform hierarchy (the step before the path) --------------------------------------------
+
+int gsc_hierarchy_upload(gsc_ctx *c, uint32_t n_nodes, uint32_t n_rows, const uint32_t *row_begin, const uint32_t *parent,
+                         uint32_t n_colliders, const uint32_t *collider_node)
+{
+    if (int rc = check_ctx(c)) return rc;
+    NOT_IN_FLIGHT(c, "gsc_hierarchy_upload");
+    if (!c->have_colliders || n_colliders != c->n_local)
+        return fail(c, GSC_ERR_INVALID, "gsc_hierarchy_upload: n_colliders=%u does not match the %u uploaded colliders", n_colliders, c->n_local);
+    if (!row_begin || (n_nodes && !parent) || (n_colliders && !collider_node))
+        return fail(c, GSC_ERR_INVALID, "gsc_hierarchy_upload: null array");
+    if (row_begin[0] != 0 || row_begin[n_rows] != n_nodes)
+        return fail(c, GSC_ERR_INVALID, "gsc_hierarchy_upload: row_begin must run from 0 to n_nodes");
+    for (uint32_t r = 0; r < n_rows; ++r) {
+        if (row_begin[r + 1] < row_begin[r]) return fail(c, GSC_ERR_INVALID, "gsc_hierarchy_upload: row_begin is not ascending");
+        for (uint32_t i = row_begin[r]; i < row_begin[r + 1]; ++i) {
+            const bool ok = r == 0 ? parent[i] == GSC_NO_PARENT : (parent[i] >= row_begin[r - 1] && parent[i] < row_begin[r]);
+            if (!ok) return fail(c, GSC_ERR_INVALID, "gsc_hierarchy_upload: node %u of row %u has parent %u outside row %d", i, r, parent[i], (int)r - 1);
+        }
+    }
+    for (uint32_t k = 0; k < n_colliders; ++k)
+        if (collider_node[k] >= n_nodes)
+            return fail(c, GSC_ERR_INVALID, "gsc_hierarchy_upload: collider %u names node %u of %u", k, collider_node[k], n_nodes);
+    if (n_nodes > c->hier_cap) {
+        float **fbufs[] = { &c->d_lpos, &c->d_lquat, &c->d_lscale, &c->d_dpos, &c->d_dquat, &c->d_dscale, &c->d_dmat };
+        const size_t per[] = { 3, 4, 3, 3, 4, 3, 16 };
+        for (int i = 0; i < 7; ++i) {
+            if (*fbufs[i]) cudaFree(*fbufs[i]);
+            *fbufs[i] = nullptr;
+            CU(c, dmalloc(fbufs[i], per[i] * (size_t)n_nodes));
+        }
+        if (c->d_hier_parent) cudaFree(c->d_hier_parent);
+        c->d_hier_parent = nullptr;
+        CU(c, dmalloc(&c->d_hier_parent, n_nodes));
+        c->hier_cap = n_nodes;
+        c->hier_local[0] = c->hier_local[1] = c->hier_local[2] = false;
+    }
+    if (!c->d_hier_node) CU(c, dmalloc(&c->d_hier_node, c->cap));
+    if (n_nodes) CU(c, cudaMemcpyAsync(c->d_hier_parent, parent, (size_t)n_nodes * 4, cudaMemcpyHostToDevice, c->stream));
+    if (n_colliders) CU(c, cudaMemcpyAsync(c->d_hier_node, collider_node, (size_t)n_colliders * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->hier_nodes = n_nodes;
+    c->hier_row_begin.assign(row_begin, row_begin + n_rows + 1);
+    c->hier_colliders = n_colliders;
+    c->hier_derived = false;
+    return GSC_OK;
+}
+
+int gsc_hierarchy_update(gsc_ctx *c, const float *local_pos3, const float *local_quat4, const float *local_scale3)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (c->hier_row_begin.empty() || c->hier_colliders != c->n_local)
+        return fail(c, GSC_ERR_INVALID, "gsc_hierarchy_update: no hierarchy uploaded for the current %u colliders", c->n_local);
+    cudaStream_t s = c->stream;
+    const size_t n = c->hier_nodes;
+    const float *src[3] = { local_pos3, local_quat4, local_scale3 };
+    float *dst[3] = { c->d_lpos, c->d_lquat, c->d_lscale };
+    const size_t per[3] = { 12, 16, 12 };
+    for (int i = 0; i < 3; ++i) {
+        if (src[i]) {
+            if (n) CU(c, cudaMemcpyAsync(dst[i], src[i], n * per[i], cudaMemcpyHostToDevice, s));
+            c->hier_local[i] = true;
+        } else if (!c->hier_local[i]) {
+            return fail(c, GSC_ERR_INVALID, "gsc_hierarchy_update: the first update needs position, rotation and scale");
+        }
+    }
+    const uint32_t rows = (uint32_t)c->hier_row_begin.size() - 1;
+    for (uint32_t r = 0; r < rows; ++r) {  // one launch per row: a row only depends on the one above it
+        const uint32_t b = c->hier_row_begin[r], e = c->hier_row_begin[r + 1];
+        if (e > b)
+            k_transform_row<<<(e - b + kHierThreads - 1) / kHierThreads, kHierThreads, 0, s>>>(
+                b, e, c->d_hier_parent, c->d_lpos, reinterpret_cast<const float4 *>(c->d_lquat), c->d_lscale, c->d_dpos,
+                reinterpret_cast<float4 *>(c->d_dquat), c->d_dscale, reinterpret_cast<float4 *>(c->d_dmat));
+    }
+    // a host-to-device transform copy still landing in the owned arrays must not be overtaken
+    if (c->chunked) CU(c, cudaStreamWaitEvent(s, c->ev_chunk[gsc_ctx::kChunks - 1], 0));
+    if (c->n_local)
+        k_hier_bind<<<(c->n_local + 255) / 256, 256, 0, s>>>(c->n_local, c->d_hier_node, c->d_dpos,
+                                                            reinterpret_cast<const float4 *>(c->d_dquat), c->d_dscale, c->d_pos,
+                                                            reinterpret_cast<float4 *>(c->d_quat), c->d_scale);
+    CU(c, cudaGetLastError());
+    CU(c, cudaStreamSynchronize(s));  // the caller's host arrays are borrowed for the call only
+    c->hier_derived = true;
+    c->packed = false;
+    c->chunked = false;
+    c->b_pos = c->d_pos;
+    c->b_quat = c->d_quat;
+    c->b_scale = c->d_scale;
+    c->have_transforms = true;
+    return GSC_OK;
+}
+
+int gsc_hierarchy_download(gsc_ctx *c, float *pos3, float *quat4, float *scale3, float *matrix16)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!c->hier_derived) return fail(c, GSC_ERR_INVALID, "gsc_hierarchy_download before gsc_hierarchy_update");
+    const size_t n = c->hier_nodes;
+    if (n == 0) return GSC_OK;
+    if (pos3) CU(c, cudaMemcpy(pos3, c->d_dpos, n * 12, cudaMemcpyDeviceToHost));
+    if (quat4) CU(c, cudaMemcpy(quat4, c->d_dquat, n * 16, cudaMemcpyDeviceToHost));
+    if (scale3) CU(c, cudaMemcpy(scale3, c->d_dscale, n * 12, cudaMemcpyDeviceToHost));
+    if (matrix16) CU(c, cudaMemcpy(matrix16, c->d_dmat, n * 64, cudaMemcpyDeviceToHost));
+    return GSC_OK;
+}
+
 int gsc_debug_download(gsc_ctx *c, int what, void *dst, size_t dst_bytes)
 {
     if (int rc = check_ctx(c)) return rc;
+    NOT_IN_FLIGHT(c, "gsc_debug_download");
     if (!dst) return fail(c, GSC_ERR_INVALID, "gsc_debug_download: null destination");
     const uint32_t n = c->n_local + c->n_ghost;
     const FrameBlock &h = *c->h_fb;
@@ -1052,6 +1320,10 @@ int gsc_debug_download(gsc_ctx *c, int what, void *dst, size_t dst_bytes)
     case GSC_DBG_SORTED_IDX: src = c->d_vals[which]; bytes = (size_t)n * 4; break;
     case GSC_DBG_CELL_START: src = c->d_cell_start; bytes = ((size_t)h.grid.num_cells + 1) * 4; break;
     case GSC_DBG_OBB: src = c->d_obb; bytes = (size_t)n * 64; break;
+    case GSC_DBG_ENTITY: src = c->d_entity; bytes = (size_t)c->n_local * 4; break;
+    case GSC_DBG_KIND: src = c->d_kind; bytes = (size_t)c->n_local; break;
+    case GSC_DBG_OFFSET: src = c->d_offset; bytes = (size_t)c->n_local * 12; break;
+    case GSC_DBG_SIZE: src = c->d_size; bytes = (size_t)c->n_local * 12; break;
     default: return fail(c, GSC_ERR_INVALID, "gsc_debug_download: unknown item %d", what);
     }
     if (dst_bytes < bytes) return fail(c, GSC_ERR_CAPACITY, "gsc_debug_download: need %zu bytes", bytes);

@@ -124,6 +124,57 @@ int gsc_bind_device_transforms(gsc_ctx *ctx, uint32_t n, const float *d_pos3, co
 /* ---- the step: CollisionSystem::update (mod.rs:590-611) minus the callback dispatch ---- */
 int gsc_step(gsc_ctx *ctx, gsc_step_out *out);
 
+/* the same step in two halves, for a host loop that overlaps the NEXT frame's transform upload with this frame's
+ * step (PCIe is the slowest link of a step fed from host memory): gsc_step_begin enqueues the whole step and
+ * returns; gsc_step_end waits for it and reports exactly what gsc_step would have.  Between the two the only calls
+ * allowed on the context are gsc_update_transforms / _packed / gsc_bind_device_transforms for the next frame -- the
+ * copy is ordered behind bvh_update of the step in flight (the one reader of the transform arrays) and runs under
+ * the rest of it.  The reference's update blocks (grid_collision.rs:262-272); gsc_step keeps that form. */
+int gsc_step_begin(gsc_ctx *ctx);
+int gsc_step_end(gsc_ctx *ctx, gsc_step_out *out);
+
+/* ---- collider lifecycle after the first upload ----
+ * ColliderManager::assign appends to the dense arrays (struct_component_manager.rs:83-96; BoundingVolumeManager
+ * pushes a volume the first time bvh_update meets the entity, bounding_volume.rs:394-407): gsc_append_colliders adds
+ * n_new colliders behind the uploaded ones without touching those.
+ * Destruction is a swap_remove of the dense arrays (BoundingVolumeManager::destroy_immediate,
+ * bounding_volume.rs:82-104, driven by the cleanup loop of CollisionSystem::update, mod.rs:605-609): the last
+ * element moves into the hole, so the INDEX order -- which orients every output tuple and fixes the OBB-OBB argument
+ * order -- changes exactly as in the reference.  gsc_remove_colliders applies the removals index[0], index[1], ...
+ * in that order, each index meaning the dense position at the time of its removal (what the reference's
+ * `indices.remove(&entity)` yields), to the device-resident static arrays; nothing is re-uploaded.
+ * After either call the next frame's transforms must be provided for the new count before the next step. */
+int gsc_append_colliders(gsc_ctx *ctx, uint32_t n_new, const uint32_t *entity, const uint8_t *kind,
+                         const float *offset3, const float *size3);
+int gsc_remove_colliders(gsc_ctx *ctx, uint32_t n_remove, const uint32_t *index);
+/* colliders currently registered on the device */
+int gsc_collider_count(gsc_ctx *ctx, uint32_t *n_out);
+
+/* ---- the step BEFORE the path: transform derivation ----
+ * TransformManager::update_transforms walks the rows of the hierarchy (row = depth; "the transforms in a row can be
+ * processed independently so they should be done in parallel", component/transform.rs:243-251) and
+ * TransformData::update (:588-600) derives, per node,
+ *     matrix_derived   = parent.matrix_derived * (T(position) * (R(rotation) * S(scale)))      (:593, :602-608)
+ *     position_derived = matrix_derived.translation_part()                                     (:595)
+ *     rotation_derived = parent.rotation_derived * rotation                                    (:596, quaternion.rs:164-169)
+ *     scale_derived    = scale * parent.scale_derived                                          (:597)
+ * with the identity dummy as the parent of a root (:47-61).  Here: one kernel launch per row, one thread per node,
+ * f32 operation order as written in lib/polygon_math (Matrix4 * Matrix4 matrix.rs:207-243, all four products of
+ * every element kept); the derived values stay on the device and feed bvh_update directly, so a frame needs no
+ * separate gsc_update_transforms.
+ * Nodes are numbered row by row: row r holds nodes row_begin[r] .. row_begin[r+1]-1; parent[i] is a node of the
+ * previous row (GSC_NO_PARENT for the nodes of row 0).  collider_node[k] names the node whose derived transform
+ * collider k of the dense array reads (mod.rs:311-333). */
+#define GSC_NO_PARENT 0xffffffffu
+int gsc_hierarchy_upload(gsc_ctx *ctx, uint32_t n_nodes, uint32_t n_rows, const uint32_t *row_begin,
+                         const uint32_t *parent, uint32_t n_colliders, const uint32_t *collider_node);
+/* one frame: local position / rotation (x,y,z,w) / scale of every node from HOST memory (NULL keeps the previous
+ * values of that array), derive, and bind the colliders' transforms for the next step */
+int gsc_hierarchy_update(gsc_ctx *ctx, const float *local_pos3, const float *local_quat4, const float *local_scale3);
+/* derived values of every node, to HOST memory (any pointer may be NULL): pos3[3n], quat4[4n], scale3[3n],
+ * matrix16[16n] row-major */
+int gsc_hierarchy_download(gsc_ctx *ctx, float *pos3, float *quat4, float *scale3, float *matrix16);
+
 /* copy the contact pairs of the last step to host memory: dst[2*i] = entity of the later (higher
  * index) volume, dst[2*i+1] = entity of the earlier one -- the tuple order of
  * GridCollisionSystem::collisions (grid_collision.rs:119,497).  sorted != 0 orders them ascending by
@@ -169,7 +220,11 @@ enum {
                                 (x-major; wide volumes carry n_cells) */
     GSC_DBG_SORTED_IDX  = 2, /* uint32[n]: collider indices after the radix sort */
     GSC_DBG_CELL_START  = 3, /* uint32[n_cells+1]: first sorted position of each cell */
-    GSC_DBG_OBB         = 4  /* float[16n]: centre xyz, orientation row-major 9, half widths 3, entity bits */
+    GSC_DBG_OBB         = 4, /* float[16n]: centre xyz, orientation row-major 9, half widths 3, entity bits */
+    GSC_DBG_ENTITY      = 5, /* uint32[n]: entity of every collider in dense-array order */
+    GSC_DBG_KIND        = 6, /* uint8[n]: kind, dense-array order */
+    GSC_DBG_OFFSET      = 7, /* float[3n]: collider offset, dense-array order */
+    GSC_DBG_SIZE        = 8  /* float[3n]: radius,-,- / box widths, dense-array order */
 };
 int gsc_debug_download(gsc_ctx *ctx, int what, void *dst, size_t dst_bytes);
 

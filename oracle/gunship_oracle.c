@@ -1112,3 +1112,101 @@ uint64_t orc_brute_force_sorted(orc_system *s, uint64_t *out, uint64_t cap)
     if (n <= cap) qsort(out, n, sizeof(uint64_t), cmp_u64);
     return n;
 }
+
+/* ======================================================================================================
+ * Transform derivation -- the step BEFORE the collision path.
+ * TransformManager::update_transforms (component/transform.rs:243-251) walks the rows (row = depth) and calls
+ * TransformData::update (:588-600) on every node.  The reference holds no test for it: PARITY UNPINNED beyond
+ * the restated arithmetic and the identity-parent property.
+ * `Matrix4::from_quaternion` (:604) no longer exists in lib/polygon_math; the only in-tree quaternion -> Matrix4
+ * definition is `From<Orientation> for Matrix4` (matrix.rs:160-172), which is what is restated here.
+ * ====================================================================================================== */
+typedef struct { float m[4][4]; } orc_mat4;
+
+/* matrix.rs:207-243: every element is (a0*b0) + (a1*b1) + (a2*b2) + (a3*b3), summed left to right */
+static orc_mat4 m4_mul(const orc_mat4 *a, const orc_mat4 *b)
+{
+    orc_mat4 r;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            r.m[i][j] = (a->m[i][0] * b->m[0][j]) + (a->m[i][1] * b->m[1][j]) + (a->m[i][2] * b->m[2][j]) + (a->m[i][3] * b->m[3][j]);
+    return r;
+}
+
+static orc_mat4 m4_identity(void)
+{
+    orc_mat4 r;
+    memset(&r, 0, sizeof r);
+    r.m[0][0] = r.m[1][1] = r.m[2][2] = r.m[3][3] = 1.0f;
+    return r;
+}
+
+/* TransformData::local_matrix (transform.rs:602-608): position * (rotation * scale) */
+static orc_mat4 transform_local_matrix(const float p[3], const float q[4], const float s[3])
+{
+    orc_mat4 position = m4_identity(), rotation = m4_identity(), scale = m4_identity();
+    position.m[0][3] = p[0]; position.m[1][3] = p[1]; position.m[2][3] = p[2]; /* matrix.rs:44-56 */
+    orc_mat3 r3;
+    orc_quat_to_mat3(q, &r3);                                                   /* matrix.rs:160-172, same formulas as :392-402 */
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) rotation.m[i][j] = r3.m[i][j];
+    scale.m[0][0] = s[0]; scale.m[1][1] = s[1]; scale.m[2][2] = s[2];           /* matrix.rs:103-110 */
+    const orc_mat4 rs = m4_mul(&rotation, &scale);
+    return m4_mul(&position, &rs);
+}
+
+/* row_begin[n_rows + 1]; parent[i] = node of the previous row or 0xffffffff (the identity dummy, transform.rs:47-61).
+ * Outputs per node: pos3, quat4 (x,y,z,w), scale3, matrix16 (row-major).  Rows in order, as update_transforms. */
+void orc_transform_update(uint32_t n_rows, const uint32_t *row_begin, const uint32_t *parent, const float *lpos3,
+                          const float *lquat4, const float *lscale3, float *dpos3, float *dquat4, float *dscale3,
+                          float *dmat16)
+{
+    for (uint32_t r = 0; r < n_rows; ++r)
+        for (uint32_t i = row_begin[r]; i < row_begin[r + 1]; ++i) {
+            orc_mat4 pm = m4_identity();
+            float pq[4] = { 0.0f, 0.0f, 0.0f, 1.0f }, ps[3] = { 1.0f, 1.0f, 1.0f };
+            if (parent[i] != 0xffffffffu) {
+                const uint32_t p = parent[i];
+                memcpy(&pm, dmat16 + 16 * (size_t)p, sizeof pm);
+                memcpy(pq, dquat4 + 4 * (size_t)p, sizeof pq);
+                memcpy(ps, dscale3 + 3 * (size_t)p, sizeof ps);
+            }
+            const float *q = lquat4 + 4 * (size_t)i, *s = lscale3 + 3 * (size_t)i;
+            const orc_mat4 local = transform_local_matrix(lpos3 + 3 * (size_t)i, q, s);
+            const orc_mat4 derived = m4_mul(&pm, &local);                       /* :593 */
+            memcpy(dmat16 + 16 * (size_t)i, &derived, sizeof derived);
+            dpos3[3 * (size_t)i] = derived.m[0][3];                             /* :595, matrix.rs:137-139 */
+            dpos3[3 * (size_t)i + 1] = derived.m[1][3];
+            dpos3[3 * (size_t)i + 2] = derived.m[2][3];
+            /* :596 parent.rotation_derived * self.rotation; quaternion.rs:164-169:
+             *   v = cross(a.v, b.v) + b.w * a.v + a.w * b.v ; w = a.w * b.w - dot(a.v, b.v)   (vector.rs:66-72, 190-196) */
+            const float ax = pq[0], ay = pq[1], az = pq[2], aw = pq[3], bx = q[0], by = q[1], bz = q[2], bw = q[3];
+            const float cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+            dquat4[4 * (size_t)i] = (cx + ax * bw) + bx * aw;
+            dquat4[4 * (size_t)i + 1] = (cy + ay * bw) + by * aw;
+            dquat4[4 * (size_t)i + 2] = (cz + az * bw) + bz * aw;
+            dquat4[4 * (size_t)i + 3] = aw * bw - (ax * bx + ay * by + az * bz);
+            /* :597 self.scale * parent.scale_derived */
+            dscale3[3 * (size_t)i] = s[0] * ps[0];
+            dscale3[3 * (size_t)i + 1] = s[1] * ps[1];
+            dscale3[3 * (size_t)i + 2] = s[2] * ps[2];
+        }
+}
+
+/* ======================================================================================================
+ * Collider lifecycle: BoundingVolumeManager::destroy_immediate (bounding_volume.rs:82-104) is a
+ * swap_remove of the dense `entities` / `components` arrays: the last element moves into the hole (nothing moves
+ * when the hole IS the last element).  `order[n]` stands for the dense arrays (one id per element); removals are
+ * applied in the given order, each index addressing the array as it is at that moment.  Returns the new length,
+ * or (uint32_t)-1 on an out-of-range index (the reference's `indices.remove` would have returned None).
+ * ====================================================================================================== */
+uint32_t orc_swap_remove_sequence(uint32_t *order, uint32_t n, const uint32_t *index, uint32_t n_remove)
+{
+    for (uint32_t k = 0; k < n_remove; ++k) {
+        const uint32_t i = index[k];
+        if (i >= n) return (uint32_t)-1;
+        order[i] = order[n - 1]; /* Vec::swap_remove */
+        --n;
+    }
+    return n;
+}

@@ -136,6 +136,14 @@ uint64_t orc_process_collisions(orc_system *s, uint32_t *entity, uint32_t *offse
  * { (E[i],E[j]) : j<i, test_volume(V[i],V[j]) }, sorted ascending packed u64. */
 uint64_t orc_brute_force_sorted(orc_system *s, uint64_t *out, uint64_t cap);
 
+/* ---- the step before the path: TransformData::update row by row (component/transform.rs:243-251, 588-608);
+ *      PARITY UNPINNED (the reference has no test of it) ---- */
+void orc_transform_update(uint32_t n_rows, const uint32_t *row_begin, const uint32_t *parent, const float *lpos3,
+                          const float *lquat4, const float *lscale3, float *dpos3, float *dquat4, float *dscale3,
+                          float *dmat16);
+/* ---- lifecycle: a sequence of destroy_immediate calls = swap_removes of the dense arrays (bounding_volume.rs:82-104) ---- */
+uint32_t orc_swap_remove_sequence(uint32_t *order, uint32_t n, const uint32_t *index, uint32_t n_remove);
+
 #ifdef __cplusplus
 }
 #endif

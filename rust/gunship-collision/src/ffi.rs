@@ -77,6 +77,18 @@ extern "C" {
     pub fn gsc_bind_device_transforms(ctx: *mut gsc_ctx, n: u32, d_pos3: *const f32, d_quat4: *const f32,
                                       d_scale3: *const f32) -> c_int;
     pub fn gsc_step(ctx: *mut gsc_ctx, out: *mut gsc_step_out) -> c_int;
+    pub fn gsc_step_begin(ctx: *mut gsc_ctx) -> c_int;
+    pub fn gsc_step_end(ctx: *mut gsc_ctx, out: *mut gsc_step_out) -> c_int;
+    pub fn gsc_append_colliders(ctx: *mut gsc_ctx, n_new: u32, entity: *const u32, kind: *const u8, offset3: *const f32,
+                                size3: *const f32) -> c_int;
+    pub fn gsc_remove_colliders(ctx: *mut gsc_ctx, n_remove: u32, index: *const u32) -> c_int;
+    pub fn gsc_collider_count(ctx: *mut gsc_ctx, n_out: *mut u32) -> c_int;
+    pub fn gsc_hierarchy_upload(ctx: *mut gsc_ctx, n_nodes: u32, n_rows: u32, row_begin: *const u32, parent: *const u32,
+                                n_colliders: u32, collider_node: *const u32) -> c_int;
+    pub fn gsc_hierarchy_update(ctx: *mut gsc_ctx, local_pos3: *const f32, local_quat4: *const f32,
+                                local_scale3: *const f32) -> c_int;
+    pub fn gsc_hierarchy_download(ctx: *mut gsc_ctx, pos3: *mut f32, quat4: *mut f32, scale3: *mut f32,
+                                  matrix16: *mut f32) -> c_int;
     pub fn gsc_download_pairs(ctx: *mut gsc_ctx, dst: *mut u32, cap_pairs: u64, sorted: c_int, n_out: *mut u64) -> c_int;
     pub fn gsc_download_contacts(ctx: *mut gsc_ctx, dst: *mut f32, cap_pairs: u64, sorted: c_int, n_out: *mut u64) -> c_int;
     pub fn gsc_build_adjacency(ctx: *mut gsc_ctx, out: *mut gsc_adjacency) -> c_int;

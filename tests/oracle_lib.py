@@ -242,3 +242,33 @@ def obb16(center, orientation, half) -> np.ndarray:
     out[3:12] = np.asarray(orientation, dtype=np.float32).reshape(9)
     out[12:15] = half
     return out
+
+
+def transform_update(row_begin, parent, lpos, lquat, lscale):
+    """TransformManager::update_transforms restated (component/transform.rs:243-251, 588-608): derived
+    (pos[n,3], quat[n,4], scale[n,3], matrix[n,4,4]) of every node, rows in order."""
+    L = lib()
+    L.orc_transform_update.restype = None
+    L.orc_transform_update.argtypes = [C.c_uint32, _u32p, _u32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p]
+    rb, p = _c(row_begin, np.uint32), _c(parent, np.uint32)
+    lp, lq, ls = _c(lpos, np.float32), _c(lquat, np.float32), _c(lscale, np.float32)
+    n = p.shape[0]
+    dpos, dquat = np.zeros((n, 3), np.float32), np.zeros((n, 4), np.float32)
+    dscale, dmat = np.zeros((n, 3), np.float32), np.zeros((n, 4, 4), np.float32)
+    L.orc_transform_update(rb.shape[0] - 1, _p(rb, _u32p), _p(p, _u32p), _p(lp, _f32p), _p(lq, _f32p), _p(ls, _f32p),
+                           _p(dpos, _f32p), _p(dquat, _f32p), _p(dscale, _f32p), _p(dmat, _f32p))
+    return dpos, dquat, dscale, dmat
+
+
+def swap_remove_sequence(order, index):
+    """A sequence of BoundingVolumeManager::destroy_immediate calls (bounding_volume.rs:82-104) on the dense array
+    `order`; returns the surviving array."""
+    L = lib()
+    L.orc_swap_remove_sequence.restype = C.c_uint32
+    L.orc_swap_remove_sequence.argtypes = [_u32p, C.c_uint32, _u32p, C.c_uint32]
+    o = np.array(order, dtype=np.uint32, copy=True)
+    i = _c(index, np.uint32)
+    n = int(L.orc_swap_remove_sequence(_p(o, _u32p), o.shape[0], _p(i, _u32p), i.shape[0]))
+    if n == 0xFFFFFFFF:
+        raise IndexError("swap_remove index out of range")
+    return o[:n]
