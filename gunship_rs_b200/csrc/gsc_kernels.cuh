@@ -75,7 +75,7 @@ struct GridParams {
     int32_t dims[3];
     uint32_t num_cells;  // dims product; also the key given to wide volumes
     int32_t valid;
-    float qorg[3], qscale[3];  // 16-bit conservative box quantisation of k_pairs: t = (v - qorg) * qscale in [0, 65535]
+    float qorg[3], qscale[3], qmargin;  // conservative box quantisation of k_pairs: t = (v - qorg) * qscale, qscale = 128 / cell (x, y), 64 / cell (z)
 };
 
 // Per-step device control block.  Zeroed at the start of every step.
@@ -171,7 +171,7 @@ GSC_DEV void emit_finish(EmitBuf<WARPS, CAP> &b, uint2 *__restrict__ out, float4
 // bounds (needed to place the dense grid), reduced warp -> CTA -> one atomic per CTA.
 constexpr int kBvhThreads = 256;
 
-__global__ void __launch_bounds__(kBvhThreads)
+__global__ void __launch_bounds__(kBvhThreads, 6)
 k_bvh_update(uint32_t first, uint32_t n, const uint8_t *__restrict__ kind, const float *__restrict__ offset3,
              const float *__restrict__ size3, const float *__restrict__ pos3, const float *__restrict__ quat4,
              const float *__restrict__ scale3, const uint32_t *__restrict__ entity,
@@ -209,7 +209,7 @@ k_bvh_update(uint32_t first, uint32_t n, const uint8_t *__restrict__ kind, const
             o.cx = cx; o.cy = cy; o.cz = cz;
             const float4 q = reinterpret_cast<const float4 *>(quat4)[t];
             quat_to_mat3(q.x, q.y, q.z, q.w, o.m);  // mod.rs:322
-            obb_aabb(o, mn, mx);
+            obb_aabb_fast(o, mn, mx);  // == the 8-vertex walk of bounding_volume.rs:161-327, bit for bit
             obb_store(obb + 4 * (size_t)i, o, e);
             rec[2 * (size_t)i] = make_float4(mn[0], mn[1], mn[2], mx[0]);
             rec[2 * (size_t)i + 1] = make_float4(mx[1], mx[2], __uint_as_float(g), __uint_as_float((i << 4) | kMetaBox));
@@ -278,6 +278,7 @@ __global__ void k_grid_setup(FrameBlock *fb, unsigned long long max_cells, uint3
     g.num_cells = 0;
     g.cell_size = ord2f(fb->bounds[0]);
     for (int a = 0; a < 3; ++a) { g.origin[a] = 0; g.dims[a] = 0; g.qorg[a] = 0.0f; g.qscale[a] = 0.0f; }
+    g.qmargin = 1.0f;
     fb->sort.num_passes = 0;
     fb->sort.key_bits = 0;
     fb->sort.digit_bits = 0;
@@ -294,7 +295,10 @@ __global__ void k_grid_setup(FrameBlock *fb, unsigned long long max_cells, uint3
             const float wmin = ord2f(~fb->bounds[1 + a]), wmax = ord2f(fb->bounds[4 + a]);
             const float ext = wmax - wmin;
             g.qorg[a] = wmin;
-            g.qscale[a] = ext > 0.0f ? 65535.0f / ext : 0.0f;  // flat world on this axis: everything quantises to [0, 1]
+            g.qscale[a] = __fdiv_rn(a == 2 ? 64.0f : 128.0f, g.cell_size);
+            // f32 error of t = (v - wmin) * qscale is < 3 * 2^-24 * t: one quantum of slack covers it up to t = 2^21
+            // (16384 cells on an axis); beyond that widen the slack
+            g.qmargin = fmaxf(g.qmargin, 1.0f + ceilf(ext * g.qscale[a] * 2.4e-7f - 0.5f));
             float lo = cell_coord_f(wmin, g.cell_size);
             float hi = cell_coord_f(wmax, g.cell_size);
             if (a == 0 && has_window) {  // only the slab's columns get cells; home cells outside are dropped by k_cell_keys
@@ -404,23 +408,39 @@ k_cell_keys(uint32_t n_total, const float4 *__restrict__ rec, uint32_t *__restri
 // the next cell along y / z (cell(max) > cell(min)), which is what lets k_pairs prune rows exactly.
 constexpr uint32_t kMetaReachY = 4u, kMetaReachZ = 8u;
 
-// and, for the filter loop of k_pairs, a 16 B conservatively quantised copy per volume:
-//   q[p] = (qmax.x << 16 | qmin.x, qmax.y << 16 | qmin.y, qmax.z << 16 | qmin.z, gidx << 4 | meta flags)
-// qmin = floor(t) - 1, qmax = ceil(t) + 1 with t = (v - world_min) * 65535 / world_extent, clamped to
-// [0, 65535]: the f32 rounding error of t is < 0.01 quanta, so exact overlap always implies quantised overlap
-// (never a false negative); the exact test runs on the survivors only.
+// and, for the filter loop of k_pairs, an 8 B conservatively quantised box per volume plus its ordering word:
+//   q[p]  = (Wmin, Wmax | G)      w3[p] = gidx << 4 | meta flags
+// Each W packs the three axes of the quantised min (max) corner into one word -- x: bits 0-9, y: bits 11-20, z: bits
+// 22-30 -- with a guard bit G above every field (bits 10, 21, 31).  The quantum is cell/128 on x, y and cell/64 on z,
+// qmin = floor(t) - margin, qmax = ceil(t) + margin with t = (v - world_min) * quanta_per_cell / cell, and only the
+// LOW bits of the integer are kept: coordinates are compared modulo 8 cells.  That is enough because k_pairs only
+// ever compares volumes whose home cells differ by at most one per axis: A.max - B.min and B.max - A.min then lie
+// in (-2, 3) cells = (-256, 384) quanta (x, y) resp. (-128, 192) (z), inside the signed range of the field.  So
+//   t1 = (A.Wmax | G) - B.Wmin,   t2 = (B.Wmax | G) - A.Wmin      (the guard bits absorb the borrows)
+// hold the three differences each, and the boxes overlap on every axis  <=>  no field of t1 or t2 is negative
+//   <=>  ((t1 | t2) & kQSign) == 0:
+// two subtractions and one logic op per candidate instead of six compares.  Exact overlap always implies quantised
+// overlap (never a false negative; the f32 error of t is below the margin); the exact test runs on the survivors only.
+constexpr uint32_t kQGuard = (1u << 10) | (1u << 21) | (1u << 31);
+constexpr uint32_t kQSign = (1u << 9) | (1u << 20) | (1u << 30);
+
 struct SortedVolumes {
     float4 *v;
-    uint4 *q;
+    uint2 *q;
+    uint32_t *w3;
 };
 
-GSC_DEV uint32_t quant_lo(float v, float org, float scale)
+GSC_DEV uint32_t quant_lo(float v, float org, float scale, float margin)
 {
-    return (uint32_t)fminf(fmaxf(floorf((v - org) * scale) - 1.0f, 0.0f), 65535.0f);
+    return (uint32_t)fmaxf(floorf((v - org) * scale) - margin, 0.0f);
 }
-GSC_DEV uint32_t quant_hi(float v, float org, float scale)
+GSC_DEV uint32_t quant_hi(float v, float org, float scale, float margin)
 {
-    return (uint32_t)fminf(fmaxf(ceilf((v - org) * scale) + 1.0f, 0.0f), 65535.0f);
+    return (uint32_t)(ceilf((v - org) * scale) + margin);
+}
+GSC_DEV uint32_t quant_pack(uint32_t x, uint32_t y, uint32_t z)
+{
+    return (x & 1023u) | ((y & 1023u) << 11) | ((z & 511u) << 22);
 }
 
 // ---- stage 3: cell start table + cell-order permutation of the volume records ---------------------
@@ -457,12 +477,14 @@ k_cell_table_permute(uint32_t n_total, const uint32_t *__restrict__ keys_a, cons
         if (cell_coord_f(v.mx[2], g.cell_size) > cell_coord_f(v.mn[2], g.cell_size)) meta |= kMetaReachZ;
         sv.v[2 * (size_t)p] = make_float4(v.mn[0], v.mn[1], v.mn[2], v.mx[0]);
         sv.v[2 * (size_t)p + 1] = make_float4(v.mx[1], v.mx[2], __uint_as_float(v.gidx), __uint_as_float(meta));
-        uint4 qv;
-        qv.x = (quant_hi(v.mx[0], g.qorg[0], g.qscale[0]) << 16) | quant_lo(v.mn[0], g.qorg[0], g.qscale[0]);
-        qv.y = (quant_hi(v.mx[1], g.qorg[1], g.qscale[1]) << 16) | quant_lo(v.mn[1], g.qorg[1], g.qscale[1]);
-        qv.z = (quant_hi(v.mx[2], g.qorg[2], g.qscale[2]) << 16) | quant_lo(v.mn[2], g.qorg[2], g.qscale[2]);
-        qv.w = (v.gidx << 4) | (meta & 15u);
-        sv.q[p] = qv;
+        const uint32_t wmin = quant_pack(quant_lo(v.mn[0], g.qorg[0], g.qscale[0], g.qmargin),
+                                         quant_lo(v.mn[1], g.qorg[1], g.qscale[1], g.qmargin),
+                                         quant_lo(v.mn[2], g.qorg[2], g.qscale[2], g.qmargin));
+        const uint32_t wmax = quant_pack(quant_hi(v.mx[0], g.qorg[0], g.qscale[0], g.qmargin),
+                                         quant_hi(v.mx[1], g.qorg[1], g.qscale[1], g.qmargin),
+                                         quant_hi(v.mx[2], g.qorg[2], g.qscale[2], g.qmargin));
+        sv.q[p] = make_uint2(wmin, wmax | kQGuard);
+        sv.w3[p] = (v.gidx << 4) | (meta & 15u);
     }
     const int64_t len = hi - lo + 1;
     if (len > kGapLong) {  // a huge run of empty cells (space between clusters / slabs): hand it to k_fill_gaps
@@ -596,18 +618,17 @@ k_pairs(uint32_t n_total, const uint32_t *__restrict__ keys_a, const uint32_t *_
     __syncthreads();
 
     const uint32_t p = blockIdx.x * kPairThreads + tid;
-    // A's quantised box: lo = qmin << 16 (compared with B's whole word), hi = qmax (compared with B's low half)
-    uint32_t alo0 = 0, alo1 = 0, alo2 = 0, ahi0 = 0, ahi1 = 0, ahi2 = 0, a_w3 = 0, qsame = 0;
+    // A's quantised box: packed min corner and guarded packed max corner (see SortedVolumes)
+    uint32_t a_min = 0, a_maxg = 0, a_w3 = 0, qsame = 0;
     uint32_t lo[kPairRows], hi[kPairRows];
 #pragma unroll
     for (int r = 0; r < kPairRows; ++r) lo[r] = hi[r] = 0;
     if (p < n_total) {
-        const uint4 aq = __ldg(sv.q + p);
+        const uint2 aq = __ldg(sv.q + p);
         const uint32_t key = keys[p];
-        alo0 = aq.x << 16; ahi0 = aq.x >> 16;
-        alo1 = aq.y << 16; ahi1 = aq.y >> 16;
-        alo2 = aq.z << 16; ahi2 = aq.z >> 16;
-        a_w3 = aq.w;
+        a_min = aq.x;
+        a_maxg = aq.y;
+        a_w3 = __ldg(sv.w3 + p);
         // ghosts only serve as the earlier volume; wide volumes (key == num_cells) go to k_wide_pairs
         const bool active = !(a_w3 & kMetaGhost) && key < g.num_cells;
         const uint32_t dz = (uint32_t)g.dims[2], dydz = (uint32_t)g.dims[1] * dz;
@@ -631,12 +652,12 @@ k_pairs(uint32_t n_total, const uint32_t *__restrict__ keys_a, const uint32_t *_
     const uint32_t pa0 = (uint32_t)__cvta_generic_to_shared(&sh.priv[tid]);
     constexpr uint32_t kSlotStride = kPairThreads * 4u;
     uint32_t pa = pa0;
-    // quantised AABB::test_aabb (bounding_volume.rs:338-343, 411-419; inclusive): separated on an axis iff
-    // B.qmax < A.qmin  <=>  whole word (B.qmax << 16 | B.qmin) < A.qmin << 16,  or  B.qmin > A.qmax
-    auto test = [&](uint32_t q, uint32_t w0, uint32_t w1, uint32_t w2, bool take) {
-        const bool sep = w0 < alo0 || (w0 & 0xffffu) > ahi0 || w1 < alo1 || (w1 & 0xffffu) > ahi1 || w2 < alo2 ||
-                         (w2 & 0xffffu) > ahi2;
-        if (!sep && take) {
+    // quantised AABB::test_aabb (bounding_volume.rs:338-343, 411-419; inclusive): three packed differences per
+    // subtraction, overlap on every axis iff no field went negative
+    auto test = [&](uint32_t q, uint2 b, bool take) {
+        const uint32_t t1 = a_maxg - b.x;  // A.qmax - B.qmin per axis
+        const uint32_t t2 = b.y - a_min;   // B.qmax - A.qmin per axis
+        if ((((t1 | t2) & kQSign) == 0u) && take) {
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(pa), "r"(q) : "memory");
             pa += kSlotStride;
         }
@@ -658,14 +679,19 @@ k_pairs(uint32_t n_total, const uint32_t *__restrict__ keys_a, const uint32_t *_
         for (uint32_t q = lo[r]; q < qe; q += kPairTrip) {
             // (reads up to kPairTrip - 1 records past the run: always inside the array, which is padded, and
             // masked out of the test below)
-            const uint4 *bp = sv.q + q;
-            uint4 b[kPairTrip];
+            const uint2 *bp = sv.q + q;
+            uint2 b[kPairTrip];
+            uint32_t w[kPairTrip];
 #pragma unroll
             for (int k = 0; k < kPairTrip; ++k) b[k] = __ldg(bp + k);
+            if (own) {
+#pragma unroll
+                for (int k = 0; k < kPairTrip; ++k) w[k] = __ldg(sv.w3 + q + k);
+            }
 #pragma unroll
             for (int k = 0; k < kPairTrip; ++k) {
                 const uint32_t qk = q + k;
-                test(qk, b[k].x, b[k].y, b[k].z, qk < qe && (!own || qk < qsame || b[k].w < a_w3));
+                test(qk, b[k], qk < qe && (!own || qk < qsame || w[k] < a_w3));
             }
             drain_if_full();
         }
@@ -811,6 +837,10 @@ k_narrow(const uint2 *__restrict__ cand_ss, const uint2 *__restrict__ cand_so, c
     }
     emit_finish(s_out, pairs, CONTACTS ? contacts : nullptr, &fb->n_pairs, cap_pairs);
 }
+// (Measured and dropped: a software-pipelined variant that staged the NEXT candidate's records in thread-private
+// shared-memory slots with cp.async while testing the current one ran this stage in 1.0-1.2 ms instead of 0.46 ms at
+// 16M -- eight scattered 16 B LDGSTS per thread cost far more in the L1/L2 request path than the overlap wins; the
+// gathers already overlap across the 32 resident warps of an SM.)
 
 // full BoundVolume::test (bounding_volume.rs:124-132) between two arbitrary volumes, `hi` = later index
 GSC_DEV bool test_volume_full(const Volume &hi, const Volume &lo, const float4 *__restrict__ obb, uint32_t *e_hi,

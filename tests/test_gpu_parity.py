@@ -289,3 +289,41 @@ def test_packed_transforms_give_the_same_pair_set():
         with pytest.raises(G.GscError):
             ctx.update_transforms_packed(pos, quat[box][:-1], s.scale[box][:-1])   # wrong box count
     oracle.close()
+
+
+def test_box_aabb_without_the_vertex_walk_is_bit_exact_also_for_degenerate_boxes():
+    """k_bvh_update computes a box AABB as centre -+ (|m0 hx| + |m1 hy|) + |m2 hz| per axis instead of walking the 8
+    vertices (bounding_volume.rs:161-327); zero-extent axes take the literal path.  Bits must match the oracle's
+    vertex walk, signs of zero included."""
+    rng = np.random.default_rng(23)
+    n = 40000
+    q = rng.normal(size=(n, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    q[: n // 8] = [0, 0, 0, 1]                         # axis-aligned: exact zeros in the matrix
+    q[n // 8: n // 4] = [np.sqrt(0.5), 0, 0, np.sqrt(0.5)]
+    scale = rng.uniform(0.5, 3.5, size=(n, 3)).astype(np.float32)
+    scale[rng.random((n, 3)) < 0.15] = 0.0              # flat / line / point boxes
+    pos = rng.uniform(-40, 40, size=(n, 3)).astype(np.float32)
+    pos[rng.random((n, 3)) < 0.1] = 0.0
+    pos[rng.random((n, 3)) < 0.05] = -0.0
+    pos[:, 0] += np.where(rng.random(n) < 0.05, np.float32(1e6), np.float32(0))  # large offsets: heavy rounding
+    kind = np.ones(n, dtype=np.uint8)
+    entity = np.arange(1, n + 1, dtype=np.uint32)
+    offset = np.zeros((n, 3), dtype=np.float32)
+    offset[rng.random((n, 3)) < 0.3] = -0.0
+    size = np.ones((n, 3), dtype=np.float32)
+    size[0] = 0.0
+    sysm = O.OracleSystem(8, 4)
+    sysm.bvh_update(entity, kind, offset, size, pos, q.astype(np.float32), scale)
+    vol = sysm.volumes()
+    with G.CollisionContext(n, max_cells=1 << 27) as ctx:
+        ctx.upload_colliders(entity, kind, offset, size)
+        ctx.update_transforms(pos, q.astype(np.float32), scale)
+        try:
+            ctx.step()
+        except N.GscError as e:  # the grid may not fit (1e6 offsets): the AABBs were still produced by stage 0
+            assert e.code in (N.GSC_ERR_CAPACITY, N.GSC_ERR_RANGE)
+        aabb = ctx.debug(N.GSC_DBG_AABB)
+        assert np.array_equal(aabb[:, :3].view(np.uint32), vol["aabb_min"][:, :3].view(np.uint32))
+        assert np.array_equal(aabb[:, 3:].view(np.uint32), vol["aabb_max"][:, :3].view(np.uint32))
+    sysm.close()
