@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgunship_collision.so")
+# GSC_LIB: development knob -- load another build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("GSC_LIB") or os.path.join(_HERE, "libgunship_collision.so")
 
 GSC_OK, GSC_ERR_INVALID, GSC_ERR_CUDA, GSC_ERR_NCCL, GSC_ERR_CAPACITY, GSC_ERR_RANGE, GSC_ERR_KIND = range(7)
 GSC_SPHERE, GSC_BOX, GSC_MESH = 0, 1, 2
