@@ -449,6 +449,7 @@ GSC_DEV uint32_t quant_pack(uint32_t x, uint32_t y, uint32_t z)
 constexpr int kTableThreads = 256;
 constexpr int kGapLong = 1 << 14;  // empty-cell runs longer than this are filled by the whole grid
 constexpr int kGapCap = 4096;
+constexpr int kWarpFillMax = 4096;  // cells a warp fills transposed; wider spans (rare) go gap by gap
 
 __global__ void __launch_bounds__(kTableThreads)
 k_cell_table_permute(uint32_t n_total, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ vals_a,
@@ -463,12 +464,10 @@ k_cell_table_permute(uint32_t n_total, const uint32_t *__restrict__ keys_a, cons
     const uint32_t *vals = in_b ? vals_b : vals_a;
     const uint32_t p = blockIdx.x * kTableThreads + threadIdx.x;  // p in [0, n_total]
     const uint32_t C = g.num_cells;
-    int64_t lo = 0, hi = -1;
-    if (p <= n_total) {
-        const uint32_t k = p < n_total ? min(keys[p], C) : C;
-        lo = p > 0 ? (int64_t)keys[p - 1] + 1 : 0;
-        hi = k;
-    }
+    // thread p fills start[] for the cells of the key gap (key[p-1], key[p]] (keys clamped to C; positions behind
+    // n_total count as key C, so their gaps are empty and the kernel needs no tail special case)
+    const uint32_t kcur = p < n_total ? min(keys[p], C) : C;
+    const uint32_t klo = p == 0 ? 0u : (p - 1 < n_total ? min(keys[p - 1], C) : C) + 1u;
     if (p < n_total) {
         const uint32_t i = vals[p];
         const Volume v = volume_decode(ldg_gather(rec + 2 * (size_t)i), ldg_gather(rec + 2 * (size_t)i + 1));
@@ -486,8 +485,31 @@ k_cell_table_permute(uint32_t n_total, const uint32_t *__restrict__ keys_a, cons
         sv.q[p] = make_uint2(wmin, wmax | kQGuard);
         sv.w3[p] = (v.gidx << 4) | (meta & 15u);
     }
+    // The warp's 32 positions own the contiguous cells [first, last].  Normally the warp fills them TRANSPOSED: lane l
+    // takes cells first + l, first + 32 + l, ... and finds each cell's start -- position of the first key >= the
+    // cell -- by a 5-step binary search over the warp's sorted keys (shuffles).  32 cells per trip whatever the gap
+    // sizes, instead of every lane walking its own gap (sparse space: 20-cell gaps in every lane, 32 serial loops).
+    const int lane = threadIdx.x & 31;
+    const uint32_t first = __shfl_sync(0xffffffffu, klo, 0), last = __shfl_sync(0xffffffffu, kcur, 31);
+    const uint32_t span = last + 1u - first;  // >= 0: klo of lane 0 <= its key + 1 <= last + 1
+    if (span <= (uint32_t)kWarpFillMax) {
+        const uint32_t p0 = p - lane;
+        for (uint32_t t = 0; t < span; t += 32) {
+            const uint32_t c = first + t + lane;
+            uint32_t j = 0;  // number of keys of this warp below c (keys ascend; < 32 for every c <= last)
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const uint32_t k = __shfl_sync(0xffffffffu, kcur, j + step - 1);
+                if (k < c) j += step;
+            }
+            if (c <= last) cell_start[c] = p0 + j;
+        }
+        return;
+    }
+    // a warp that spans a large run of empty cells (blob boundary, space between slabs): every lane its own gap
+    int64_t lo = klo, hi = kcur;
     const int64_t len = hi - lo + 1;
-    if (len > kGapLong) {  // a huge run of empty cells (space between clusters / slabs): hand it to k_fill_gaps
+    if (len > kGapLong) {  // a huge run of empty cells: hand it to k_fill_gaps
         const uint32_t slot = atomicAdd(&fb->n_gaps, 1u);
         if (slot < (uint32_t)kGapCap) {
             gaps[slot] = make_uint4((uint32_t)lo, (uint32_t)hi, p, 0u);
@@ -498,7 +520,6 @@ k_cell_table_permute(uint32_t n_total, const uint32_t *__restrict__ keys_a, cons
     if (!is_long)
         for (int64_t c = lo; c <= hi; ++c) cell_start[c] = p;
     uint32_t long_mask = __ballot_sync(0xffffffffu, is_long);
-    const int lane = threadIdx.x & 31;
     while (long_mask) {
         const int src = __ffs(long_mask) - 1;
         long_mask &= long_mask - 1;
