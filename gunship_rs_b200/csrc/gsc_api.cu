@@ -604,10 +604,10 @@ static int stage_enqueue(gsc_ctx *c)
         k_pairs<<<pb, kPairThreads, 0, s>>>(n_total, c->d_keys[0], c->d_keys[1], sv, c->d_cell_start, po, fb);
         if (timing) CU(c, cudaEventRecord(c->ev[5], s));
         if (c->d_contacts)
-            k_narrow<true><<<148 * 4, kNarrowThreads, 0, s>>>(c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands, c->d_rec,
+            k_narrow<true><<<148 * kNarrowCtasPerSm, kNarrowThreads, 0, s>>>(c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands, c->d_rec,
                                                             c->d_obb, c->d_pairs, c->d_contacts, c->max_pairs, fb);
         else
-            k_narrow<false><<<148 * 4, kNarrowThreads, 0, s>>>(c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands, c->d_rec,
+            k_narrow<false><<<148 * kNarrowCtasPerSm, kNarrowThreads, 0, s>>>(c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands, c->d_rec,
                                                              c->d_obb, c->d_pairs, nullptr, c->max_pairs, fb);
         k_wide_pairs<<<kGridStrideBlocks, kNarrowThreads, 0, s>>>(c->n_local, c->d_wide, c->d_rec, c->d_obb, c->d_pairs,
                                                                 c->d_contacts, c->max_pairs, fb);

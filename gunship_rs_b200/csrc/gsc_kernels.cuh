@@ -790,6 +790,10 @@ k_pairs(uint32_t n_total, const uint32_t *__restrict__ keys_a, const uint32_t *_
 constexpr int kNarrowThreads = 256;
 constexpr int kNarrowWarps = kNarrowThreads / 32;
 constexpr int kNarrowCap = 96;
+#ifndef GSC_NARROW_CTAS
+#define GSC_NARROW_CTAS 4
+#endif
+constexpr int kNarrowCtasPerSm = GSC_NARROW_CTAS;  // resident CTAs per SM the persistent grid is sized for
 
 // All three shape tests in ONE persistent kernel over a work queue of candidate chunks: box-box chunks first
 // (the long SAT tests), then sphere-box, then sphere-sphere.  Run as three kernels each of them was latency
@@ -798,7 +802,7 @@ constexpr int kNarrowCap = 96;
 constexpr int kNarrowChunk = kNarrowThreads * 2;  // candidates per ticket
 
 template <bool CONTACTS>
-__global__ void __launch_bounds__(kNarrowThreads, 4)
+__global__ void __launch_bounds__(kNarrowThreads, kNarrowCtasPerSm)
 k_narrow(const uint2 *__restrict__ cand_ss, const uint2 *__restrict__ cand_so, const uint2 *__restrict__ cand_oo,
          unsigned long long cap_cands, const float4 *__restrict__ rec, const float4 *__restrict__ obb,
          uint2 *__restrict__ pairs, float4 *__restrict__ contacts, unsigned long long cap_pairs, FrameBlock *__restrict__ fb)
