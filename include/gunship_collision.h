@@ -13,8 +13,11 @@
  * Threading: a context is owned by one caller thread (the reference's `update(&mut self, ..)`,
  * src/old/engine.rs:193); distinct contexts are independent.
  *
- * Ownership: input host arrays are borrowed for the duration of the call only.  The library owns
- * all device buffers; device pointers it hands out stay valid until the next gsc_step / gsc_destroy.
+ * Ownership: input host arrays are borrowed for the duration of the call only -- with one exception: the
+ * per-frame transform arrays of gsc_update_transforms / _packed are copied asynchronously (truly so when the
+ * memory is pinned) and must stay valid and unmodified until the gsc_step / gsc_step_end that consumes them has
+ * returned.  The library owns all device buffers; device pointers it hands out stay valid until the next
+ * gsc_step / gsc_step_begin / gsc_destroy.
  */
 #ifndef GUNSHIP_COLLISION_H
 #define GUNSHIP_COLLISION_H

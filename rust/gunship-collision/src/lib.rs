@@ -115,6 +115,55 @@ impl<S: std::hash::BuildHasher + Default> GridCollisionSystem<S> {
     }
 }
 
+impl<S: std::hash::BuildHasher + Default> GridCollisionSystem<S> {
+    /// `ColliderManager::assign` after the first `set_colliders` (struct_component_manager.rs:83-96): the new
+    /// colliders go to the end of the dense arrays; the ones already on the device are not touched.
+    pub fn append_colliders(&mut self, entities: &[Entity], kind: &[u8], offset3: &[f32], size3: &[f32]) {
+        let rc = unsafe { ffi::gsc_append_colliders(self.ctx, entities.len() as u32, entities.as_ptr(), kind.as_ptr(), offset3.as_ptr(), size3.as_ptr()) };
+        check(self.ctx, rc);
+        self.n += entities.len() as u32;
+    }
+
+    /// The cleanup loop of `CollisionSystem::update` (mod.rs:605-609): one `destroy_immediate` (swap_remove,
+    /// bounding_volume.rs:82-104) per index, in order; `indices[k]` is what `self.indices.remove(&entity)` yields
+    /// at that moment.
+    pub fn remove_colliders(&mut self, indices: &[u32]) {
+        let rc = unsafe { ffi::gsc_remove_colliders(self.ctx, indices.len() as u32, indices.as_ptr()) };
+        check(self.ctx, rc);
+        self.n -= indices.len() as u32;
+    }
+
+    /// Pipelined form of `update` for a main loop that can hand over the NEXT frame's transforms while this
+    /// frame's step runs: `begin_update(frame f)`, ..., `begin_update(frame f+1)` is legal before `end_update()`
+    /// only through `stage_transforms`, which the C side orders behind `bvh_update` of the step in flight.
+    pub fn stage_transforms(&mut self, transforms: &[DerivedTransform]) {
+        assert_eq!(transforms.len(), self.n as usize);
+        self.pos.clear(); self.quat.clear(); self.scale.clear();
+        for t in transforms {
+            self.pos.extend_from_slice(&t.position);
+            self.quat.extend_from_slice(&t.rotation);
+            self.scale.extend_from_slice(&t.scale);
+        }
+        unsafe { check(self.ctx, ffi::gsc_update_transforms(self.ctx, self.n, self.pos.as_ptr(), self.quat.as_ptr(), self.scale.as_ptr())); }
+    }
+    pub fn begin_update(&mut self) {
+        unsafe { check(self.ctx, ffi::gsc_step_begin(self.ctx)); }
+    }
+    pub fn end_update(&mut self) {
+        let mut out: ffi::gsc_step_out = unsafe { std::mem::zeroed() };
+        unsafe { check(self.ctx, ffi::gsc_step_end(self.ctx, &mut out)); }
+        self.cell_size = out.cell_size;
+        self.pairs.resize(2 * out.n_pairs as usize, 0);
+        let mut n = 0u64;
+        let rc = unsafe { ffi::gsc_download_pairs(self.ctx, self.pairs.as_mut_ptr(), out.n_pairs, 0, &mut n) };
+        check(self.ctx, rc);
+        self.collisions.clear();
+        for p in self.pairs.chunks(2) {
+            self.collisions.insert((p[0], p[1]));
+        }
+    }
+}
+
 impl<S: std::hash::BuildHasher + Default> Drop for GridCollisionSystem<S> {
     fn drop(&mut self) {
         unsafe { ffi::gsc_destroy(self.ctx) }
