@@ -143,13 +143,19 @@ class SlabDriver:
             self.trace[name] = self.trace.get(name, 0.0) + time.perf_counter() - t0
         return time.perf_counter()
 
-    def step(self):
+    def step(self, after_bounds=None):
+        """One collision step over all ranks.  `after_bounds`, if given, is called as soon as stage 0 (bvh_update) of
+        this step is done on this rank: the one reader of the frame's transform arrays has finished, so a host loop
+        hands over the NEXT frame's transforms there and the PCIe copy runs under the exchange and stages 1-5."""
         import torch
         dist, be = self.dist, self.backend
         dev = be.tensor_device
         t0 = time.perf_counter()
         longest, wmin, wmax, status, home_x_max, n_local = be.phase_bounds()
         t0 = self._t("phase_bounds", t0)
+        if after_bounds is not None:
+            after_bounds()
+            t0 = self._t("after_bounds", t0)
         # ONE all-gather carries everything the ranks must agree on: the global cell size (max longest axis) and
         # world box (they place the grid), and every rank's home x-range in world units
         # (f64 carries the f32 values exactly, and the collider counts the peer push needs)
@@ -434,7 +440,21 @@ def bench_multi_gpu(args, n, rank, world, local_rank, metric, unit, workload_nam
     ctx.update_transforms_packed_ptr(h_pos[0].data_ptr(), n_box, h_bquat[0].data_ptr(), h_bscale.data_ptr())
     for i in range(args.warmup):
         step_e2e(i)
-    span_e2e, outs_e2e = timed(lambda i: step_e2e(args.warmup + i), args.steps)
+    span_sync, _ = timed(lambda i: step_e2e(args.warmup + i), args.steps)
+
+    # the same per-step work as a host loop pipelines it: frame f+1 is handed over as soon as bvh_update of step f is
+    # done (SlabDriver.step(after_bounds=...)), so its PCIe copy runs under the exchange and stages 1-5 of step f
+    def step_e2e_pipelined(i):
+        f = (i + 1) % nframes
+        out = driver.step(after_bounds=lambda: ctx.update_transforms_packed_ptr(h_pos[f].data_ptr(), n_box, h_bquat[f].data_ptr(), 0))
+        rc = ctx._lib.gsc_download_pairs(ctx._h, h_pairs.data_ptr(), h_pairs.numel() // 2, 0, C.byref(npairs))
+        assert rc == 0, ctx._lib.gsc_last_error(ctx._h)
+        return out
+
+    ctx.update_transforms_packed_ptr(h_pos[0].data_ptr(), n_box, h_bquat[0].data_ptr(), 0)
+    for i in range(args.warmup):
+        step_e2e_pipelined(i)
+    span_e2e, outs_e2e = timed(lambda i: step_e2e_pipelined(args.warmup + i), args.steps)
 
     # aggregate counters over ranks
     def total(vals):
@@ -471,7 +491,9 @@ def bench_multi_gpu(args, n, rank, world, local_rank, metric, unit, workload_nam
                        "box_fraction": round(f_box, 3), "contact_pairs_per_step": int(sums[0]),
                        "halo_colliders_per_step": int(sums[5])},
             "e2e": {"value": n * args.steps / span_e2e, "unit": unit, "ms_per_step": 1e3 * span_e2e / args.steps,
-                    "h2d_bytes_per_step": int(n * 12 + sums[8] * 16), "d2h_bytes_per_step": int(sums[7])},
+                    "h2d_bytes_per_step": int(n * 12 + sums[8] * 16), "d2h_bytes_per_step": int(sums[7]),
+                    "mode": "pipelined host loop: every rank hands frame f+1 over right after bvh_update of step f",
+                    "sync_value": n * args.steps / span_sync, "sync_ms_per_step": 1e3 * span_sync / args.steps},
             "gpu_launches": (13 + 4) * args.steps * world,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -35,12 +35,22 @@ def _worker(rank, world, port, cfg, n, frames, ownership, out_dir):
     mine = np.nonzero(owner == rank)[0]
     be = CpuSlabBackend(s.entity[mine], s.kind[mine], s.offset[mine], s.size[mine], mine)
     drv = slabs.SlabDriver(be)
-    for f in frames:
+    # pipelined host loop: the next frame is handed over from the after_bounds hook of the step in flight (the
+    # frame's transforms have been consumed by then), as bench.py's multi-GPU e2e loop does
+    hooks = []
+
+    def hand_over(f):
+        hooks.append(f)
         pos, quat = s.frame(f)
         be.set_frame(pos[mine], quat[mine], s.scale[mine])
-        out = drv.step()
+
+    hand_over(frames[0])
+    for k, f in enumerate(frames):
+        nxt = frames[k + 1] if k + 1 < len(frames) else None
+        out = drv.step(after_bounds=(lambda: hand_over(nxt)) if nxt is not None else None)
         np.save(os.path.join(out_dir, f"p_{f}_{rank}.npy"), out.pairs)
         np.save(os.path.join(out_dir, f"h_{f}_{rank}.npy"), np.array([drv.last_halo_in, drv.last_halo_out, len(mine)]))
+    assert hooks == list(frames)
     dist.barrier()
     dist.destroy_process_group()
 
