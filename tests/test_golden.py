@@ -66,3 +66,31 @@ def test_cuda_narrowphase_reproduces_golden():
     assert np.array_equal(np.packbits(G.test_obb_obb(ob, oa)), GOLD["np_obb_obb_swapped"])
     cells = np.random.default_rng(9).integers(-32768, 32767, size=(512, 3)).astype(np.int16)
     assert np.array_equal(G.fnv1a_gridcell(cells), GOLD["fnv_gridcell"])
+
+
+TGOLD = np.load(os.path.join(HERE, "golden", "transform_golden.npz"))
+
+
+def test_oracle_transform_and_lifecycle_reproduce_golden():
+    got = O.transform_update(TGOLD["row_begin"], TGOLD["parent"], TGOLD["lpos"], TGOLD["lquat"], TGOLD["lscale"])
+    for g, name in zip(got, ("dpos", "dquat", "dscale", "dmat")):
+        assert np.array_equal(g.view(np.uint32), TGOLD[name].view(np.uint32)), name
+    after = O.swap_remove_sequence(np.arange(1, 501, dtype=np.uint32), TGOLD["remove_seq"])
+    assert np.array_equal(after, TGOLD["order_after"])
+
+
+@pytest.mark.gpu
+def test_cuda_transform_and_lifecycle_reproduce_golden():
+    from gunship_rs_b200 import _native as N
+    from gunship_rs_b200 import context as G
+    n_nodes = TGOLD["parent"].shape[0]
+    n = 500
+    with G.CollisionContext(n) as ctx:
+        ent = np.arange(1, n + 1, dtype=np.uint32)
+        ctx.upload_colliders(ent, np.zeros(n, np.uint8), np.zeros((n, 3), np.float32), np.ones((n, 3), np.float32))
+        ctx.hierarchy_upload(TGOLD["row_begin"], TGOLD["parent"], (np.arange(n) * 3 % n_nodes).astype(np.uint32))
+        ctx.hierarchy_update(TGOLD["lpos"], TGOLD["lquat"], TGOLD["lscale"])
+        for g, name in zip(ctx.hierarchy_download(), ("dpos", "dquat", "dscale", "dmat")):
+            assert np.array_equal(g.view(np.uint32), TGOLD[name].view(np.uint32)), name
+        ctx.remove_colliders(TGOLD["remove_seq"])
+        assert np.array_equal(ctx.debug(N.GSC_DBG_ENTITY), TGOLD["order_after"])
