@@ -564,12 +564,21 @@ k_fill_gaps(uint32_t *__restrict__ cell_start, const uint4 *__restrict__ gaps, c
 // index and append them -- one atomicAdd per class and CTA -- to the three global candidate lists.  The
 // shape tests run as separate, perfectly balanced kernels over those lists (stage 5).  Shared memory is
 // kept small on purpose: the candidate boxes are read through L1, which needs the carve-out.
-constexpr int kPairThreads = 64;
+#ifndef GSC_PAIR_THREADS
+#define GSC_PAIR_THREADS 64
+#endif
+#ifndef GSC_PAIR_MIN_CTAS
+#define GSC_PAIR_MIN_CTAS 20
+#endif
+#ifndef GSC_PAIR_PRIV
+#define GSC_PAIR_PRIV 12  // 8 / 12 / 16 / 24 measured: 0.942 / 0.903 / 0.913 / 0.936 ms at 16M (fewer single-lane drains vs a smaller L1)
+#endif
+constexpr int kPairThreads = GSC_PAIR_THREADS;
 constexpr int kPairWarps = kPairThreads / 32;
 constexpr int kPairRows = 5;
 constexpr int kPairTrip = 4;    // candidates per loop trip
-constexpr int kPairPriv = 8;    // private survivor slots per lane; a lane that fills them drains early
-constexpr int kPairCap = 256;   // survivors staged per CTA (4 per volume); denser CTAs spill one by one
+constexpr int kPairPriv = GSC_PAIR_PRIV;    // private survivor slots per lane; a lane that fills them drains early
+constexpr int kPairCap = 4 * kPairThreads;   // survivors staged per CTA (4 per volume); denser CTAs spill one by one
 
 struct PairOut {
     uint2 *cand_ss;
@@ -626,7 +635,7 @@ __device__ __noinline__ void pair_drain_lane(PairShared &sh, uint32_t p, uint32_
     }
 }
 
-__global__ void __launch_bounds__(kPairThreads, 20)
+__global__ void __launch_bounds__(kPairThreads, GSC_PAIR_MIN_CTAS)
 k_pairs(uint32_t n_total, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ keys_b,
         SortedVolumes sv, const uint32_t *__restrict__ cell_start, PairOut out, FrameBlock *__restrict__ fb)
 {

@@ -176,13 +176,12 @@ class SlabDriver:
         g_status = int(np.bitwise_or.reduce(allb[:, 8].astype(np.int64)))
         be.set_global_bounds(float(cell), g_min.tolist(), g_max.tolist(), g_status)
         # home x-cell = floor(fl(aabb.min.x / cell)) (grid_collision.rs:329-335): IEEE f32 divide, same as the device
-        ranges = []
-        for r in range(self.world):
-            if not (allb[r, 0] > 0) or not np.isfinite(allb[r, 1]) or not (cell > 0):
-                ranges.append((1, 0))  # no colliders on that rank
-            else:
-                with np.errstate(all="ignore"):
-                    ranges.append((int(np.floor(np.float32(allb[r, 1]) / cell)), int(np.floor(np.float32(allb[r, 7]) / cell))))
+        # (one vectorised f32 divide for all ranks: this runs on the critical path of every step)
+        with np.errstate(all="ignore"):
+            lo_x = np.floor(allb[:, 1] / cell)
+            hi_x = np.floor(allb[:, 7] / cell)
+        has = (allb[:, 0] > 0) & np.isfinite(allb[:, 1]) & bool(cell > 0)
+        ranges = [(int(lo_x[r]), int(hi_x[r])) if has[r] else (1, 0) for r in range(self.world)]  # (1, 0): no colliders
         x_min, x_max = ranges[self.rank]
         if x_min <= x_max:
             be.set_x_window(*needed_range(x_min, x_max))
