@@ -71,3 +71,11 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle_lib" not in text and "gunship_oracle" not in text, f
+
+
+def test_rust_ffi_declares_every_header_function():
+    """rust/gunship-collision/src/ffi.rs cannot be compiled here (no rustc); at least keep its extern "C" block in
+    step with the header"""
+    ffi = open(os.path.join(ROOT, "rust", "gunship-collision", "src", "ffi.rs")).read()
+    declared = set(re.findall(r"pub fn (gsc_[a-z0-9_]+)\s*\(", ffi))
+    assert sorted(declared) == _header_functions()
