@@ -18,11 +18,11 @@ from gunship_rs_b200.colliders import ColliderSet
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _build(tmp_path, name):
+def _build(tmp_path, name, src_dir=("tests", "cpp")):
     exe = tmp_path / name
     libdir = os.path.join(ROOT, "gunship_rs_b200")
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
-                           "-I", os.path.join(ROOT, "host"), os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-o", str(exe),
+                           "-I", os.path.join(ROOT, "host"), os.path.join(ROOT, *src_dir, name + ".cpp"), "-o", str(exe),
                            "-L", libdir, "-lgunship_collision", f"-Wl,-rpath,{libdir}"])
     return str(exe)
 
@@ -35,6 +35,7 @@ def _has_gpu():
 def test_host_mirror_builds_and_panics_without_a_device(tmp_path):
     kat = _build(tmp_path, "collider_kat")
     _build(tmp_path, "scene_runner")
+    _build(tmp_path, "grid_collision", ("benches",))  # the C++ counterpart of benches/grid_collision.rs
     if _has_gpu():
         pytest.skip("a CUDA device is present: the GPU tests run the binaries")
     r = subprocess.run([kat], capture_output=True, text=True)
