@@ -376,6 +376,14 @@ def main():
                      "step_alg_bytes": int(total_bytes), "step_frac": total_bytes / (np.mean(dev_ms) * 1e-3) / 1e9 / peak},
         "stages": stages,
     }
+    # a size-independent fingerprint of the pair set at FULL size: frame 0's pair count and an order-independent
+    # checksum (sum of first << 32 | second mod 2^64) -- it must not move when a kernel is rewritten
+    try:
+        step_resident(0)
+        pk = ctx.pairs_packed(sorted=False)
+        line["config"]["frame0_pair_set"] = {"pairs": int(pk.shape[0]), "checksum": f"{int(np.sum(pk, dtype=np.uint64)):016x}"}
+    except Exception as exc:  # never let the fingerprint cost the bench line
+        line["config"]["frame0_pair_set"] = {"error": str(exc)[:200]}
     ctx.close()
     del d_pos, d_quat
 
