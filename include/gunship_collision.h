@@ -86,7 +86,7 @@ typedef struct gsc_step_out {
     uint32_t n_wide;         /* volumes whose AABB spans > 2 cells on an axis (debug_assert grid_collision.rs:403-410) */
     int32_t  grid_origin[3]; /* min cell coordinate per axis */
     int32_t  grid_dims[3];   /* cells per axis */
-    uint32_t sort_passes;    /* 8-bit radix passes run on the cell keys */
+    uint32_t sort_passes;    /* radix passes run on the cell keys (digits of up to 9 bits) */
     uint32_t status_flags;   /* raw device error bits (diagnostics) */
     float    stage_ms[GSC_NUM_STAGES]; /* only with GSC_FLAG_TIMING */
     float    step_ms;        /* device time of the whole step (always) */
