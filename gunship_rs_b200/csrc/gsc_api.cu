@@ -1213,6 +1213,11 @@ int gsc_hierarchy_upload(gsc_ctx *c, uint32_t n_nodes, uint32_t n_rows, const ui
         if (collider_node[k] >= n_nodes)
             return fail(c, GSC_ERR_INVALID, "gsc_hierarchy_upload: collider %u names node %u of %u", k, collider_node[k], n_nodes);
     if (n_nodes > c->hier_cap) {
+        // (a failure below must not leave a previous hierarchy usable over half-replaced buffers)
+        c->hier_cap = 0;
+        c->hier_row_begin.clear();
+        c->hier_colliders = 0;
+        c->hier_derived = false;
         float **fbufs[] = { &c->d_lpos, &c->d_lquat, &c->d_lscale, &c->d_dpos, &c->d_dquat, &c->d_dscale, &c->d_dmat };
         const size_t per[] = { 3, 4, 3, 3, 4, 3, 16 };
         for (int i = 0; i < 7; ++i) {
