@@ -198,19 +198,19 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        # bounded sample: the reference path at 16M takes ~6 s/step on 8 threads; time it on a 2M-collider
-        # field from the same generator (same density, same mix) so K+W steps end within minutes
-        n_ref = args.cpu_sample_n or min(n, 1 << 21)
+        # SAME configuration as the CUDA arm: the full collider count of the workload (a 16M step takes ~6-10 s on 8
+        # threads, so K+W steps end within a few minutes); --cpu-sample-n only exists for quick development runs
+        n_ref = args.cpu_sample_n or n
         scene = make_scene(args.config, n_ref)
         frames = [scene.frame(f) for f in range(min(args.frames, 2))]
         value, ms, cores = run_reference(args, scene, frames)
+        sample = (f"{args.steps} full steps over all {n_ref} colliders of the workload" if n_ref == n else
+                  f"{args.steps} steps over a {n_ref}-collider field of the same generator (development run)")
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_name(args.config, n),
-                           "sample": f"{n_ref} colliders of the same generator per step"},
-                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                                 "sample": f"{args.steps} steps over {n_ref} colliders (same generator, density and mix)"},
+                "config": {"workload": workload_name(args.config, n_ref), "frames_cycled": len(frames)},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
         return 0
@@ -390,20 +390,27 @@ def main():
     if not args.no_cpu_baseline:
         import oracle_lib as O
         cores = min(8, os.cpu_count() or 1)
-        n_cpu = args.cpu_sample_n or min(n, 1 << 22)
+        n_cpu = args.cpu_sample_n or n          # the same workload, all colliders: 2 steps of ~6-10 s at 16M
         cs = scene if n_cpu == n else make_scene(args.config, n_cpu)
         sysm = O.OracleSystem(8, cores)
         ts = []
-        for i in range(3):
+        for i in range(2):
             pos, quat = (h_pos[i % nframes].numpy(), h_quat[i % nframes].numpy()) if n_cpu == n else cs.frame(i)
             t0 = time.perf_counter()
             sysm.bvh_update(cs.entity, cs.kind, cs.offset, cs.size, pos, quat, cs.scale)
             sysm.grid_update()
             ts.append(time.perf_counter() - t0)
+            if i == 0 and n_cpu == n and "pairs" in line["config"].get("frame0_pair_set", {}):
+                # the oracle's frame-0 pair set must carry the fingerprint of the CUDA path's (full-size parity, every run)
+                want = sysm.collisions_sorted()
+                fp = {"pairs": int(want.shape[0]), "checksum": f"{int(np.sum(want, dtype=np.uint64)):016x}"}
+                line["config"]["frame0_pair_set"]["oracle"] = fp
+                line["config"]["frame0_pair_set"]["match"] = (fp["pairs"] == line["config"]["frame0_pair_set"]["pairs"] and
+                                                              fp["checksum"] == line["config"]["frame0_pair_set"]["checksum"])
         sysm.close()
-        best = float(np.median(ts[1:]))
+        best = float(ts[-1])
         line["cpu_baseline"] = {"value": n_cpu / best, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"3 steps (first discarded) over {n_cpu} colliders of the same generator",
+                                "sample": f"2 full steps (first discarded) over all {n_cpu} colliders of the workload",
                                 "ms_per_step": 1e3 * best}
     emit(line)
     return 0

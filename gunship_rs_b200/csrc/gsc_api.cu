@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -68,6 +69,8 @@ struct gsc_ctx {
     uint32_t *d_w3_sorted = nullptr;
     uint32_t *d_keys[2] = { nullptr, nullptr }, *d_vals[2] = { nullptr, nullptr };
     uint32_t *d_cell_start = nullptr, *d_wide = nullptr;
+    uint32_t *d_overflow = nullptr;  // tiles of the pairs stage that did not fit its staging buffers
+    bool pairs_legacy = false;       // GSC_PAIRS_LEGACY=1: the round-1 thread-per-volume kernel on every tile (A/B measurements)
     uint4 *d_gaps = nullptr;
     bool have_window = false;
     int32_t win_lo = 0, win_hi = 0;
@@ -290,6 +293,12 @@ int gsc_create(const gsc_config *cfg, gsc_ctx **out)
     }
     CR(dmalloc(&c->d_cell_start, c->max_cells + 2));
     CR(dmalloc(&c->d_wide, M));
+    CR(dmalloc(&c->d_overflow, (M + kTileA - 1) / kTileA + 1));
+    CR(cudaFuncSetAttribute(k_pairs_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)));
+    {
+        const char *e = getenv("GSC_PAIRS_LEGACY");
+        c->pairs_legacy = e && e[0] == '1';
+    }
     CR(dmalloc(&c->d_gaps, (size_t)kGapCap));
     CR(dmalloc(&c->d_pairs, c->max_pairs));
     if (cfg->flags & GSC_FLAG_CONTACTS) CR(dmalloc(&c->d_contacts, c->max_pairs));
@@ -331,7 +340,7 @@ void gsc_destroy(gsc_ctx *c)
         }
     void *bufs[] = { c->d_entity, c->d_gidx, c->d_box_slot, c->d_kind, c->d_offset, c->d_size, c->d_pos, c->d_quat, c->d_scale, c->d_rec,
                      c->d_rec_sorted, c->d_qrec_sorted, c->d_w3_sorted, c->d_obb, c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1], c->d_cell_start,
-                     c->d_wide, c->d_gaps, c->d_pairs, c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->d_pairs_sorted, c->d_contacts, c->d_contacts_sorted, c->d_perm, c->d_adj_entity, c->d_adj_offset, c->d_adj_other, c->d_fb, c->d_sort_scratch,
+                     c->d_wide, c->d_overflow, c->d_gaps, c->d_pairs, c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->d_pairs_sorted, c->d_contacts, c->d_contacts_sorted, c->d_perm, c->d_adj_entity, c->d_adj_offset, c->d_adj_other, c->d_fb, c->d_sort_scratch,
                      c->d_halo_rec, c->d_halo_obb, c->d_halo_count, c->d_hier_parent, c->d_hier_node, c->d_lpos, c->d_lquat,
                      c->d_lscale, c->d_dpos, c->d_dquat, c->d_dscale, c->d_dmat };
     for (void *b : bufs)
@@ -599,15 +608,20 @@ static int stage_enqueue(gsc_ctx *c)
                                                          c->d_rec, sv, c->d_cell_start, c->d_gaps, fb);
         k_fill_gaps<<<148 * 2, 256, 0, s>>>(c->d_cell_start, c->d_gaps, fb);
         if (timing) CU(c, cudaEventRecord(c->ev[4], s));
-        PairOut po{ c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands };
-        const uint32_t pb = (n_total + kPairThreads - 1) / kPairThreads;
-        k_pairs<<<pb, kPairThreads, 0, s>>>(n_total, c->d_keys[0], c->d_keys[1], sv, c->d_cell_start, po, fb);
+        // sphere-sphere pairs are decided inside the pairs stage unless a contact has to be computed for them
+        PairOut po{ c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands, c->d_pairs, c->max_pairs, c->d_overflow, c->d_contacts ? 0 : 1 };
+        if (!c->pairs_legacy)
+            k_pairs_tiled<<<(n_total + kTileA - 1) / kTileA, kTileA, sizeof(TileShared), s>>>(n_total, c->d_keys[0], c->d_keys[1], sv,
+                                                                                           c->d_cell_start, po, fb);
+        // tiles too dense for the staging buffers (normally none: the kernel exits at once)
+        k_pairs<<<148 * GSC_PAIR_MIN_CTAS, kPairThreads, 0, s>>>(n_total, c->d_keys[0], c->d_keys[1], sv, c->d_cell_start, po, fb,
+                                                                 c->pairs_legacy ? 1 : 0);
         if (timing) CU(c, cudaEventRecord(c->ev[5], s));
         if (c->d_contacts)
-            k_narrow<true><<<148 * kNarrowCtasPerSm, kNarrowThreads, 0, s>>>(c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands, c->d_rec,
+            k_narrow<true><<<148 * kNarrowCtasPerSm, kNarrowThreads, 0, s>>>(c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands, c->d_rec_sorted,
                                                             c->d_obb, c->d_pairs, c->d_contacts, c->max_pairs, fb);
         else
-            k_narrow<false><<<148 * kNarrowCtasPerSm, kNarrowThreads, 0, s>>>(c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands, c->d_rec,
+            k_narrow<false><<<148 * kNarrowCtasPerSm, kNarrowThreads, 0, s>>>(c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands, c->d_rec_sorted,
                                                              c->d_obb, c->d_pairs, nullptr, c->max_pairs, fb);
         k_wide_pairs<<<kGridStrideBlocks, kNarrowThreads, 0, s>>>(c->n_local, c->d_wide, c->d_rec, c->d_obb, c->d_pairs,
                                                                 c->d_contacts, c->max_pairs, fb);
@@ -634,7 +648,7 @@ static int stage_collect(gsc_ctx *c, gsc_step_out *out)
     if (out) {
         memset(out, 0, sizeof *out);
         out->n_pairs = h.n_pairs;
-        out->n_sphere_sphere = h.n_ss;
+        out->n_sphere_sphere = c->d_contacts ? h.n_ss : h.n_ss_fused;
         out->n_sphere_obb = h.n_so;
         out->n_obb_obb = h.n_oo;
         out->n_cells = h.grid.num_cells;

@@ -88,7 +88,10 @@ struct FrameBlock {
     uint32_t n_gaps;      // long empty key gaps queued for k_fill_gaps
     uint32_t n_ghost_in;  // ghosts written into this context by peer GPUs this step (k_halo_push, system-scope atomic)
     uint32_t narrow_ticket;  // work queue of k_narrow (chunks of the three candidate lists)
+    uint32_t n_total;     // local + ghost volumes of this step (k_grid_setup); kernels launched for a capacity clamp to it
+    uint32_t n_overflow;  // tiles k_pairs_tiled could not stage (queued for k_pairs)
     uint32_t pad1;
+    unsigned long long n_ss_fused;  // AABB-overlapping sphere-sphere candidates decided inside the pairs stage
     GridParams grid;
     SortControl sort;
 };
@@ -282,6 +285,7 @@ __global__ void k_grid_setup(FrameBlock *fb, unsigned long long max_cells, uint3
     fb->sort.num_passes = 0;
     fb->sort.key_bits = 0;
     fb->sort.digit_bits = 0;
+    fb->n_total = n_total;
     uint32_t st = 0;
     if (n_total == 0 || fb->bounds[0] == 0) {  // nothing to do (no colliders): valid stays 0, not an error
         fb->grid = g;
@@ -402,10 +406,11 @@ k_cell_keys(uint32_t n_total, const float4 *__restrict__ rec, uint32_t *__restri
     tile_hist[(size_t)(2 * tid + 1) * num_tiles + tile] = c1;
 }
 
-// Cell-ordered volumes, the array k_pairs streams (one 32 B record = one DRAM sector per volume):
-//   v[2p] = (min.x, min.y, min.z, max.x)   v[2p+1] = (max.y, max.z, global index bits, meta)
+// Cell-ordered volumes (one 32 B record = one DRAM sector per volume): the volume record in the form bvh_update
+// wrote it -- sphere (cx, cy, cz, r | entity, 0, gidx, meta), box (min.xyz, max.x | max.yz, gidx, meta) -- so the pairs
+// stage can run the exact AABB test AND Sphere::test_sphere on it, and the SAT stage reads its spheres from here.
 // meta of the sorted copy additionally carries kMetaReachY / kMetaReachZ: the AABB's max corner lies in
-// the next cell along y / z (cell(max) > cell(min)), which is what lets k_pairs prune rows exactly.
+// the next cell along y / z (cell(max) > cell(min)), which is what lets the pairs stage prune rows exactly.
 constexpr uint32_t kMetaReachY = 4u, kMetaReachZ = 8u;
 
 // and, for the filter loop of k_pairs, an 8 B conservatively quantised box per volume plus its ordering word:
@@ -470,12 +475,15 @@ k_cell_table_permute(uint32_t n_total, const uint32_t *__restrict__ keys_a, cons
     const uint32_t klo = p == 0 ? 0u : (p - 1 < n_total ? min(keys[p - 1], C) : C) + 1u;
     if (p < n_total) {
         const uint32_t i = vals[p];
-        const Volume v = volume_decode(ldg_gather(rec + 2 * (size_t)i), ldg_gather(rec + 2 * (size_t)i + 1));
+        const float4 r0 = ldg_gather(rec + 2 * (size_t)i);
+        float4 r1 = ldg_gather(rec + 2 * (size_t)i + 1);
+        const Volume v = volume_decode(r0, r1);
         uint32_t meta = v.meta;
         if (cell_coord_f(v.mx[1], g.cell_size) > cell_coord_f(v.mn[1], g.cell_size)) meta |= kMetaReachY;
         if (cell_coord_f(v.mx[2], g.cell_size) > cell_coord_f(v.mn[2], g.cell_size)) meta |= kMetaReachZ;
-        sv.v[2 * (size_t)p] = make_float4(v.mn[0], v.mn[1], v.mn[2], v.mx[0]);
-        sv.v[2 * (size_t)p + 1] = make_float4(v.mx[1], v.mx[2], __uint_as_float(v.gidx), __uint_as_float(meta));
+        r1.w = __uint_as_float(meta);
+        sv.v[2 * (size_t)p] = r0;
+        sv.v[2 * (size_t)p + 1] = r1;
         const uint32_t wmin = quant_pack(quant_lo(v.mn[0], g.qorg[0], g.qscale[0], g.qmargin),
                                          quant_lo(v.mn[1], g.qorg[1], g.qscale[1], g.qmargin),
                                          quant_lo(v.mn[2], g.qorg[2], g.qscale[2], g.qmargin));
@@ -541,259 +549,11 @@ k_fill_gaps(uint32_t *__restrict__ cell_start, const uint4 *__restrict__ gaps, c
     }
 }
 
-// ---- stage 4: neighbour-cell pair enumeration + AABB filter ----------------------------------------
-// One thread per cell-sorted volume A.  Candidates B are the volumes of the 13 cells that precede A's
-// home cell in key order among its 26 neighbours plus A's own cell; a pair inside one cell is taken by
-// the member with the larger global index.  Every unordered pair is therefore visited exactly once --
-// the sort order itself is the dedupe that the reference does with a HashMap (grid_collision.rs:497-511).
-//
-// Because keys are x-major / z-minor and start[] is monotone, the candidates of A are FIVE contiguous
-// runs of the cell-sorted arrays, one per (dx, dy) row: (-1,-1) (-1,0) (-1,+1) (0,-1) (0,0), each
-// covering cells z-1 .. z+1 (z-1 .. z for the own row).  The grid carries a one-cell apron of empty
-// cells, so neighbour keys are plain offsets of A's key and never need a bounds check.  Rows / cells
-// that A's own AABB cannot reach are pruned exactly: B in row y+1 (or cell z+1) means
-// cell(B.min) > cell(A.max) there, hence B.min > A.max by monotonicity of floor(fl(p / c)), hence
-// test_ranges fails.
-//
-// The kernel is an instruction-issue-bound filter (22 AABB tests per volume on the clustered scene, 1.3
-// survive), so the loop is kept minimal and branch-free: each lane walks its runs doing only the
-// inclusive AABB overlap test on the precomputed boxes; a survivor's position is stored with a
-// predicated write into a few PRIVATE shared-memory slots of the lane (no atomics, no divergent branch).
-// When the CTA is done the private slots are compacted into one CTA list (warp scan + one shared atomic
-// per warp); then all threads classify the listed (A, B) pairs by the two kinds, orient them by global
-// index and append them -- one atomicAdd per class and CTA -- to the three global candidate lists.  The
-// shape tests run as separate, perfectly balanced kernels over those lists (stage 5).  Shared memory is
-// kept small on purpose: the candidate boxes are read through L1, which needs the carve-out.
-#ifndef GSC_PAIR_THREADS
-#define GSC_PAIR_THREADS 64
-#endif
-#ifndef GSC_PAIR_MIN_CTAS
-#define GSC_PAIR_MIN_CTAS 20
-#endif
-#ifndef GSC_PAIR_PRIV
-#define GSC_PAIR_PRIV 12  // 8 / 12 / 16 / 24 measured: 0.942 / 0.903 / 0.913 / 0.936 ms at 16M (fewer single-lane drains vs a smaller L1)
-#endif
-constexpr int kPairThreads = GSC_PAIR_THREADS;
-constexpr int kPairWarps = kPairThreads / 32;
-constexpr int kPairRows = 5;
-constexpr int kPairTrip = 4;    // candidates per loop trip
-constexpr int kPairPriv = GSC_PAIR_PRIV;    // private survivor slots per lane; a lane that fills them drains early
-constexpr int kPairCap = 4 * kPairThreads;   // survivors staged per CTA (4 per volume); denser CTAs spill one by one
+}  // namespace gsc
 
-struct PairOut {
-    uint2 *cand_ss;
-    uint2 *cand_so;
-    uint2 *cand_oo;
-    unsigned long long cap_cands;
-};
+#include "gsc_pairs.cuh"  // stage 4: neighbour-cell pair enumeration + AABB filter (k_pairs_tiled, k_pairs)
 
-struct PairShared {
-    uint32_t priv[kPairPriv * kPairThreads];  // slot-major: lane t owns priv[j * kPairThreads + t]
-    uint2 list[kPairCap];
-    uint32_t count;
-    uint32_t warp_cls[kPairWarps][3];
-    unsigned long long base[3];
-};
-
-// orient a surviving (A, B) pair: item = (local index of the later volume [| sphere flag], local index of
-// the earlier one); returns the class 0 sphere-sphere, 1 sphere-box, 2 box-box
-GSC_DEV int pair_classify(uint32_t a_gidx, uint32_t a_meta, uint32_t b_gidx, uint32_t b_meta, uint2 *item)
-{
-    const bool a_box = a_meta & kMetaBox, b_box = b_meta & kMetaBox;
-    const bool a_hi = a_gidx > b_gidx;  // tuple = (later index, earlier index), grid_collision.rs:440,497
-    uint32_t hi_l = a_hi ? a_meta >> 4 : b_meta >> 4;
-    const uint32_t lo_l = a_hi ? b_meta >> 4 : a_meta >> 4;
-    const int cls = (int)a_box + (int)b_box;
-    if (cls == 1 && (a_hi ? !a_box : !b_box)) hi_l |= 0x80000000u;  // the later volume is the sphere
-    *item = make_uint2(hi_l, lo_l);
-    return cls;
-}
-
-// slow path of a full CTA list: classify and append one pair straight to the global lists
-__device__ __noinline__ void pair_spill(uint32_t p, uint32_t q, const float4 *__restrict__ sv, PairOut out, FrameBlock *fb)
-{
-    const float4 a0 = __ldg(sv + 2 * (size_t)p), a1 = __ldg(sv + 2 * (size_t)p + 1);
-    const float4 b0 = __ldg(sv + 2 * (size_t)q), b1 = __ldg(sv + 2 * (size_t)q + 1);
-    if (a0.x > b0.w || b0.x > a0.w || a0.y > b1.x || b0.y > a1.x || a0.z > b1.y || b0.z > a1.y) return;  // exact AABB test
-    uint2 item;
-    const int cls = pair_classify(__float_as_uint(a1.z), __float_as_uint(a1.w), __float_as_uint(b1.z), __float_as_uint(b1.w), &item);
-    unsigned long long *ctr = cls == 0 ? &fb->n_ss : (cls == 1 ? &fb->n_so : &fb->n_oo);
-    uint2 *dst = cls == 0 ? out.cand_ss : (cls == 1 ? out.cand_so : out.cand_oo);
-    const unsigned long long at = atomicAdd(ctr, 1ull);
-    if (at < out.cap_cands) dst[at] = item;
-}
-
-// a lane whose private slots are (nearly) full moves them to the CTA list (rare: >= kPairPriv - 1 survivors)
-__device__ __noinline__ void pair_drain_lane(PairShared &sh, uint32_t p, uint32_t cnt, int tid, const float4 *__restrict__ sv,
-                                             PairOut out, FrameBlock *fb)
-{
-    const uint32_t at = atomicAdd(&sh.count, cnt);
-    for (uint32_t j = 0; j < cnt; ++j) {
-        const uint32_t q = sh.priv[j * kPairThreads + tid];
-        if (at + j < (uint32_t)kPairCap) sh.list[at + j] = make_uint2(p, q);
-        else pair_spill(p, q, sv, out, fb);
-    }
-}
-
-__global__ void __launch_bounds__(kPairThreads, GSC_PAIR_MIN_CTAS)
-k_pairs(uint32_t n_total, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ keys_b,
-        SortedVolumes sv, const uint32_t *__restrict__ cell_start, PairOut out, FrameBlock *__restrict__ fb)
-{
-    __shared__ PairShared sh;
-    const GridParams g = fb->grid;
-    if (!g.valid) return;
-    const uint32_t *keys = (fb->sort.num_passes & 1) ? keys_b : keys_a;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) sh.count = 0;
-    __syncthreads();
-
-    const uint32_t p = blockIdx.x * kPairThreads + tid;
-    // A's quantised box: packed min corner and guarded packed max corner (see SortedVolumes)
-    uint32_t a_min = 0, a_maxg = 0, a_w3 = 0, qsame = 0;
-    uint32_t lo[kPairRows], hi[kPairRows];
-#pragma unroll
-    for (int r = 0; r < kPairRows; ++r) lo[r] = hi[r] = 0;
-    if (p < n_total) {
-        const uint2 aq = __ldg(sv.q + p);
-        const uint32_t key = keys[p];
-        a_min = aq.x;
-        a_maxg = aq.y;
-        a_w3 = __ldg(sv.w3 + p);
-        // ghosts only serve as the earlier volume; wide volumes (key == num_cells) go to k_wide_pairs
-        const bool active = !(a_w3 & kMetaGhost) && key < g.num_cells;
-        const uint32_t dz = (uint32_t)g.dims[2], dydz = (uint32_t)g.dims[1] * dz;
-        const uint32_t zhi = (a_w3 & kMetaReachZ) ? 2u : 1u;  // end = start[kk + zhi]
-        const bool ry = a_w3 & kMetaReachY;
-#pragma unroll
-        for (int r = 0; r < kPairRows; ++r) {
-            // row base key kk = key + dx * dims.y * dims.z + dy * dims.z  (apron => always a valid cell)
-            const uint32_t kk = key - (r < 3 ? dydz : 0u) + (r == 2 ? dz : 0u) - ((r == 0 || r == 3) ? dz : 0u);
-            const bool use = active && (r != 2 || ry);
-            lo[r] = use ? ldg_gather_u32(cell_start + kk - 1) : 0u;
-            hi[r] = use ? ldg_gather_u32(cell_start + kk + (r == 4 ? 1u : zhi)) : 0u;
-        }
-        qsame = active ? ldg_gather_u32(cell_start + key) : 0u;
-    }
-
-    // The five runs are walked one after the other (row-outer): a warp then spends sum_r max_lane(len_r)
-    // iterations instead of max_lane(sum_r len_r) -- 15% more on the clustered scene -- but the loop body
-    // has no run-switching logic at all, and only the own row needs the same-cell ordering rule.
-    // next free private slot, as a shared-window byte address (st.shared with a plain register address)
-    const uint32_t pa0 = (uint32_t)__cvta_generic_to_shared(&sh.priv[tid]);
-    constexpr uint32_t kSlotStride = kPairThreads * 4u;
-    uint32_t pa = pa0;
-    // quantised AABB::test_aabb (bounding_volume.rs:338-343, 411-419; inclusive): three packed differences per
-    // subtraction, overlap on every axis iff no field went negative
-    auto test = [&](uint32_t q, uint2 b, bool take) {
-        const uint32_t t1 = a_maxg - b.x;  // A.qmax - B.qmin per axis
-        const uint32_t t2 = b.y - a_min;   // B.qmax - A.qmin per axis
-        if ((((t1 | t2) & kQSign) == 0u) && take) {
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(pa), "r"(q) : "memory");
-            pa += kSlotStride;
-        }
-    };
-    auto drain_if_full = [&]() {
-        if (pa - pa0 > (kPairPriv - kPairTrip) * kSlotStride) {  // fewer than one trip of free slots left
-            pair_drain_lane(sh, p, (pa - pa0) / kSlotStride, tid, sv.v, out, fb);
-            pa = pa0;
-        }
-    };
-    // (Measured and dropped: run starts aligned down to 2 / 4 candidates so that a trip is two 16 B loads or one
-    // 32 B load -- 0.97 / 1.03 ms against 0.94 ms for the four 8 B loads below: the extra masked slots cost more than
-    // the wider loads save.)
-    // kPairTrip candidates per trip, all their loads in flight before the first test.  Runs are short (4.4
-    // candidates on average), so a trip usually covers the whole run: indices past the end are clamped for the
-    // load and masked out of the test.
-#pragma unroll
-    for (int r = 0; r < kPairRows; ++r) {
-        const bool own = r == kPairRows - 1;  // own row (cells z-1, z): same-cell pairs go to the larger global index
-        const uint32_t qe = hi[r];
-#pragma unroll 1
-        for (uint32_t q = lo[r]; q < qe; q += kPairTrip) {
-            // (reads up to kPairTrip - 1 records past the run: always inside the array, which is padded, and
-            // masked out of the test below)
-            const uint2 *bp = sv.q + q;
-            uint2 b[kPairTrip];
-            uint32_t w[kPairTrip];
-#pragma unroll
-            for (int k = 0; k < kPairTrip; ++k) b[k] = __ldg(bp + k);
-            if (own) {
-#pragma unroll
-                for (int k = 0; k < kPairTrip; ++k) w[k] = __ldg(sv.w3 + q + k);
-            }
-#pragma unroll
-            for (int k = 0; k < kPairTrip; ++k) {
-                const uint32_t qk = q + k;
-                test(qk, b[k], qk < qe && (!own || qk < qsame || w[k] < a_w3));
-            }
-            drain_if_full();
-        }
-        __syncwarp();  // reconverge before the next run: lanes must walk each run together
-    }
-
-    // ---- compact the private slots into the CTA list: warp scan + one shared atomic per warp ----
-    {
-        const uint32_t cnt = (pa - pa0) / kSlotStride;
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        uint32_t wbase = 0;
-        if (lane == 31 && incl) wbase = atomicAdd(&sh.count, incl);
-        wbase = __shfl_sync(0xffffffffu, wbase, 31);
-        const uint32_t at = wbase + incl - cnt;
-        for (uint32_t j = 0; j < cnt; ++j) {
-            const uint32_t q = sh.priv[j * kPairThreads + tid];
-            if (at + j < (uint32_t)kPairCap) sh.list[at + j] = make_uint2(p, q);
-            else pair_spill(p, q, sv.v, out, fb);
-        }
-    }
-    __syncthreads();
-
-    // ---- classify + append the CTA's survivors to the three global lists ----
-    const uint32_t have = min(sh.count, (uint32_t)kPairCap);
-    for (uint32_t base = 0; base < have; base += kPairThreads) {
-        const uint32_t i = base + tid;
-        int cls = 3;
-        uint2 item = make_uint2(0, 0);
-        if (i < have) {
-            const uint2 e = sh.list[i];
-            const float4 a0 = __ldg(sv.v + 2 * (size_t)e.x), a1 = __ldg(sv.v + 2 * (size_t)e.x + 1);
-            const float4 c0 = __ldg(sv.v + 2 * (size_t)e.y), c1 = __ldg(sv.v + 2 * (size_t)e.y + 1);
-            // the exact AABB::test_aabb (bounding_volume.rs:338-343, 411-419), inclusive
-            const bool sep = a0.x > c0.w || c0.x > a0.w || a0.y > c1.x || c0.y > a1.x || a0.z > c1.y || c0.z > a1.y;
-            if (!sep)
-                cls = pair_classify(__float_as_uint(a1.z), __float_as_uint(a1.w), __float_as_uint(c1.z), __float_as_uint(c1.w), &item);
-        }
-        uint32_t m[3], rank = 0;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            m[c] = __ballot_sync(0xffffffffu, cls == c);
-            if (cls == c) rank = __popc(m[c] & ((1u << lane) - 1u));
-        }
-        if (lane < 3) sh.warp_cls[warp][lane] = __popc(m[lane]);
-        __syncthreads();
-        if (tid < 3) {
-            uint32_t tot = 0;
-            for (int w = 0; w < kPairWarps; ++w) {
-                const uint32_t c = sh.warp_cls[w][tid];
-                sh.warp_cls[w][tid] = tot;
-                tot += c;
-            }
-            unsigned long long *ctr = tid == 0 ? &fb->n_ss : (tid == 1 ? &fb->n_so : &fb->n_oo);
-            sh.base[tid] = tot ? atomicAdd(ctr, (unsigned long long)tot) : 0ull;
-        }
-        __syncthreads();
-        if (cls < 3) {
-            uint2 *dst = cls == 0 ? out.cand_ss : (cls == 1 ? out.cand_so : out.cand_oo);
-            const unsigned long long at = sh.base[cls] + sh.warp_cls[warp][cls] + rank;
-            if (at < out.cap_cands) dst[at] = item;
-        }
-        __syncthreads();
-    }
-}
+namespace gsc {
 
 // ---- stage 5: SAT narrowphase over the deferred candidates ------------------------------------------
 constexpr int kNarrowThreads = 256;
@@ -813,7 +573,7 @@ constexpr int kNarrowChunk = kNarrowThreads * 2;  // candidates per ticket
 template <bool CONTACTS>
 __global__ void __launch_bounds__(kNarrowThreads, kNarrowCtasPerSm)
 k_narrow(const uint2 *__restrict__ cand_ss, const uint2 *__restrict__ cand_so, const uint2 *__restrict__ cand_oo,
-         unsigned long long cap_cands, const float4 *__restrict__ rec, const float4 *__restrict__ obb,
+         unsigned long long cap_cands, const float4 *__restrict__ srec, const float4 *__restrict__ obb,
          uint2 *__restrict__ pairs, float4 *__restrict__ contacts, unsigned long long cap_pairs, FrameBlock *__restrict__ fb)
 {
     __shared__ EmitBuf<kNarrowWarps, kNarrowCap> s_out;
@@ -852,7 +612,8 @@ k_narrow(const uint2 *__restrict__ cand_ss, const uint2 *__restrict__ cand_so, c
                     const bool hi_is_sphere = c.x >> 31;
                     const uint32_t hi = c.x & 0x7fffffffu, lo = c.y;
                     const uint32_t si = hi_is_sphere ? hi : lo, oi = hi_is_sphere ? lo : hi;
-                    const float4 s0 = ldg_gather(rec + 2 * (size_t)si), s1 = ldg_gather(rec + 2 * (size_t)si + 1);
+                    // (the sphere is addressed by its cell-ordered position, pair_classify)
+                    const float4 s0 = ldg_gather(srec + 2 * (size_t)si), s1 = ldg_gather(srec + 2 * (size_t)si + 1);
                     uint32_t oe;
                     const Obb o = obb_load(obb + 4 * (size_t)oi, &oe);
                     hit = test_sphere_obb(s0.x, s0.y, s0.z, s0.w, o);
@@ -860,10 +621,10 @@ k_narrow(const uint2 *__restrict__ cand_ss, const uint2 *__restrict__ cand_so, c
                     item = hi_is_sphere ? make_uint2(se, oe) : make_uint2(oe, se);
                     if (CONTACTS && hit) ct = contact_sphere_obb(s0.x, s0.y, s0.z, s0.w, o, hi_is_sphere);
                 } else {  // Sphere::test_sphere (mod.rs:383-389)
-                    const float4 h0 = ldg_gather(rec + 2 * (size_t)c.x), l0 = ldg_gather(rec + 2 * (size_t)c.y);
+                    const float4 h0 = ldg_gather(srec + 2 * (size_t)c.x), l0 = ldg_gather(srec + 2 * (size_t)c.y);
                     hit = test_sphere_sphere(h0.x, h0.y, h0.z, h0.w, l0.x, l0.y, l0.z, l0.w);
                     if (hit) {
-                        const float4 h1 = ldg_gather(rec + 2 * (size_t)c.x + 1), l1 = ldg_gather(rec + 2 * (size_t)c.y + 1);
+                        const float4 h1 = ldg_gather(srec + 2 * (size_t)c.x + 1), l1 = ldg_gather(srec + 2 * (size_t)c.y + 1);
                         item = make_uint2(__float_as_uint(h1.x), __float_as_uint(l1.x));
                         if (CONTACTS) ct = contact_sphere_sphere(h0.x, h0.y, h0.z, h0.w, l0.x, l0.y, l0.z, l0.w);
                     }
