@@ -47,7 +47,7 @@ class GscStepOut(C.Structure):
                 ("n_cells", C.c_uint64), ("cell_size", C.c_float), ("n_wide", C.c_uint32),
                 ("grid_origin", C.c_int32 * 3), ("grid_dims", C.c_int32 * 3), ("sort_passes", C.c_uint32),
                 ("status_flags", C.c_uint32), ("stage_ms", C.c_float * GSC_NUM_STAGES), ("step_ms", C.c_float),
-                ("d_pairs", C.c_void_p), ("d_contacts", C.c_void_p)]
+                ("d_pairs", C.c_void_p), ("d_contacts", C.c_void_p), ("n_ghost", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class GscAdjacency(C.Structure):
@@ -70,7 +70,10 @@ EXPORTS = (
     "gsc_halo_sync", "gsc_halo_commit", "gsc_download_contacts", "gsc_contact_sphere_sphere", "gsc_contact_sphere_obb",
     "gsc_contact_obb_obb", "gsc_build_adjacency", "gsc_download_adjacency", "gsc_step_begin", "gsc_step_end",
     "gsc_append_colliders", "gsc_remove_colliders", "gsc_collider_count", "gsc_hierarchy_upload", "gsc_hierarchy_update",
-    "gsc_hierarchy_download",
+    "gsc_hierarchy_download", "gsc_open_peer_local", "gsc_slab_init", "gsc_slab_step", "gsc_slab_step_begin",
+    "gsc_group_create", "gsc_group_destroy", "gsc_group_last_error", "gsc_group_upload_colliders",
+    "gsc_group_update_transforms", "gsc_group_step", "gsc_group_download_pairs", "gsc_group_rebalance", "gsc_group_member",
+    "gsc_map_transform_staging", "gsc_commit_transform_staging", "gsc_box_slots",
 )
 
 _lib = None
@@ -131,9 +134,27 @@ def load():
     L.gsc_halo_push.argtypes = [vp, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32]
     L.gsc_halo_sync.argtypes = [vp]
     L.gsc_halo_commit.argtypes = [vp, C.POINTER(C.c_uint32)]
+    L.gsc_open_peer_local.argtypes = [vp, C.c_uint32, vp]
+    L.gsc_slab_init.argtypes = [vp, C.c_uint32, C.c_uint32]
+    L.gsc_slab_step.argtypes = [vp, C.POINTER(GscStepOut)]
+    L.gsc_slab_step_begin.argtypes = [vp]
+    L.gsc_group_create.argtypes = [C.c_uint32, C.POINTER(C.c_int32), C.POINTER(GscConfig), C.POINTER(vp)]
+    L.gsc_group_destroy.argtypes = [vp]
+    L.gsc_group_destroy.restype = None
+    L.gsc_group_last_error.argtypes = [vp]
+    L.gsc_group_last_error.restype = C.c_char_p
+    L.gsc_group_upload_colliders.argtypes = [vp, C.c_uint32, u32p, u8p, f32p, f32p, f32p]
+    L.gsc_group_update_transforms.argtypes = [vp, C.c_uint32, f32p, f32p, f32p]
+    L.gsc_group_step.argtypes = [vp, C.POINTER(GscStepOut)]
+    L.gsc_group_download_pairs.argtypes = [vp, u32p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
+    L.gsc_group_rebalance.argtypes = [vp]
+    L.gsc_group_member.argtypes = [vp, C.c_uint32, C.POINTER(vp), C.POINTER(C.c_uint32), u32p]
+    L.gsc_map_transform_staging.argtypes = [vp, C.c_uint32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.gsc_commit_transform_staging.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int]
+    L.gsc_box_slots.argtypes = [vp, u32p, C.c_uint32, C.POINTER(C.c_uint32)]
     for name in EXPORTS:
         fn = getattr(L, name)  # raises AttributeError if the .so does not export it
-        if name not in ("gsc_destroy", "gsc_last_error"):
+        if name not in ("gsc_destroy", "gsc_last_error", "gsc_group_destroy", "gsc_group_last_error"):
             fn.restype = C.c_int
     _lib = L
     return L

@@ -22,10 +22,12 @@ class CollisionContext:
     """gsc_ctx: device buffers + the per-frame step for up to `max_colliders` colliders on one GPU."""
 
     def __init__(self, max_colliders: int, device: int = 0, max_pairs: int = 0, max_candidates: int = 0,
-                 max_cells: int = 0, timing: bool = False, contacts: bool = False):
+                 max_cells: int = 0, timing: bool = False, contacts: bool = False, graph: bool = False):
         self._lib = N.load()
         cfg = N.GscConfig(device, max_colliders, max_pairs, max_candidates, max_cells,
-                          (N.GSC_FLAG_TIMING if timing else 0) | (N.GSC_FLAG_CONTACTS if contacts else 0), 0)
+                          (N.GSC_FLAG_TIMING if timing else 0) | (N.GSC_FLAG_CONTACTS if contacts else 0) |
+                          (N.GSC_FLAG_GRAPH if graph else 0), 0)
+        self.cap = max_colliders
         h = C.c_void_p()
         rc = self._lib.gsc_create(C.byref(cfg), C.byref(h))
         if rc != N.GSC_OK:
@@ -254,6 +256,124 @@ class CollisionContext:
         rc = self._lib.gsc_phase_finish(self._h, C.byref(out))
         self.last = out
         self._check(rc)
+        return out
+
+    # the same exchange driven from the device: one call per step and rank, one host wait (gsc_slab_*)
+    def open_peer_local(self, peer: int, other: "CollisionContext"):
+        self._check(self._lib.gsc_open_peer_local(self._h, peer, other._h))
+
+    def slab_init(self, rank: int, world: int):
+        self._check(self._lib.gsc_slab_init(self._h, rank, world))
+
+    def slab_step(self) -> N.GscStepOut:
+        out = N.GscStepOut()
+        rc = self._lib.gsc_slab_step(self._h, C.byref(out))
+        self.last = out
+        self._check(rc)
+        return out
+
+    def slab_step_begin(self):
+        self._check(self._lib.gsc_slab_step_begin(self._h))
+
+    # pinned transform staging (gsc_map_transform_staging): numpy views of the library's pinned banks
+    def map_transform_staging(self, bank: int, cap: int):
+        """(pos[cap,3], box_quat[cap,4], box_scale[cap,3]) float32 views of pinned bank `bank`; cap = max_colliders"""
+        ptrs = [C.c_void_p() for _ in range(3)]
+        self._check(self._lib.gsc_map_transform_staging(self._h, bank, *[C.byref(p) for p in ptrs]))
+        out = []
+        for p, w in zip(ptrs, (3, 4, 3)):
+            buf = (C.c_float * (cap * w)).from_address(p.value)
+            out.append(np.frombuffer(buf, dtype=np.float32).reshape(cap, w))
+        return tuple(out)
+
+    def commit_transform_staging(self, bank: int, n_box: int, with_rotation: bool = True, with_scale: bool = True):
+        self._check(self._lib.gsc_commit_transform_staging(self._h, bank, self.n, n_box, int(with_rotation), int(with_scale)))
+
+    def box_slots(self) -> np.ndarray:
+        out = np.zeros(max(self.n, 1), dtype=np.uint32)
+        nb = C.c_uint32(0)
+        self._check(self._lib.gsc_box_slots(self._h, _ptr(out), out.shape[0], C.byref(nb)))
+        return out[: self.n]
+
+
+class CollisionGroup:
+    """gsc_group: all GPUs of a box behind one handle (one context per device, x-slab partition, device-driven halo
+    exchange).  Colliders and transforms are given in the engine's dense order; pairs() is the union of the members'
+    lists == the single-GPU pair set."""
+
+    def __init__(self, devices, max_colliders_per_member: int, max_pairs: int = 0, max_candidates: int = 0, max_cells: int = 0,
+                 timing: bool = False):
+        self._lib = N.load()
+        cfg = N.GscConfig(0, max_colliders_per_member, max_pairs, max_candidates, max_cells, N.GSC_FLAG_TIMING if timing else 0, 0)
+        dev = (C.c_int32 * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self._lib.gsc_group_create(len(devices), dev, C.byref(cfg), C.byref(h))
+        if rc != N.GSC_OK:
+            raise GscError(rc, self._lib.gsc_last_error(None).decode())
+        self._h = h
+        self.world = len(devices)
+        self.n = 0
+        self.last = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gsc_group_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != N.GSC_OK:
+            raise GscError(rc, self._lib.gsc_group_last_error(self._h).decode())
+
+    def upload_colliders(self, entity, kind, offset, size, pos):
+        e, k = _c(entity, np.uint32), _c(kind, np.uint8)
+        o, s, p = _c(offset, np.float32), _c(size, np.float32), _c(pos, np.float32)
+        self.n = int(e.shape[0])
+        self._check(self._lib.gsc_group_upload_colliders(self._h, self.n, _ptr(e), _ptr(k), _ptr(o), _ptr(s), _ptr(p)))
+
+    def update_transforms(self, pos, quat=None, scale=None):
+        p, q, s = _c(pos, np.float32), _c(quat, np.float32), _c(scale, np.float32)
+        self._check(self._lib.gsc_group_update_transforms(self._h, self.n, _ptr(p), _ptr(q), _ptr(s)))
+
+    def step(self) -> N.GscStepOut:
+        out = N.GscStepOut()
+        rc = self._lib.gsc_group_step(self._h, C.byref(out))
+        self.last = out
+        self._check(rc)
+        return out
+
+    def pairs(self, sorted: bool = True) -> np.ndarray:
+        n = C.c_uint64(0)
+        self._check(self._lib.gsc_group_download_pairs(self._h, None, 0, 0, C.byref(n)))
+        out = np.zeros((int(n.value), 2), dtype=np.uint32)
+        if n.value:
+            self._check(self._lib.gsc_group_download_pairs(self._h, _ptr(out), n.value, 1 if sorted else 0, C.byref(n)))
+        return out
+
+    def pairs_packed(self, sorted: bool = True) -> np.ndarray:
+        p = self.pairs(sorted).astype(np.uint64)
+        return (p[:, 0] << np.uint64(32)) | p[:, 1]
+
+    def rebalance(self):
+        self._check(self._lib.gsc_group_rebalance(self._h))
+
+    def member_counts(self):
+        out = []
+        for i in range(self.world):
+            n = C.c_uint32(0)
+            self._check(self._lib.gsc_group_member(self._h, i, None, C.byref(n), None))
+            out.append(int(n.value))
         return out
 
 

@@ -37,6 +37,9 @@ struct Scratch {
 
 }  // namespace
 
+static_assert(kMaxPeers == GSC_MAX_PEERS, "kMaxPeers");
+constexpr size_t kMailOffset = (sizeof(FrameBlock) + 255) & ~size_t(255);  // the mailbox lives behind the control block
+
 struct gsc_ctx {
     gsc_config cfg{};
     int device = 0;
@@ -53,6 +56,17 @@ struct gsc_ctx {
     uint32_t *d_entity = nullptr, *d_gidx = nullptr, *d_box_slot = nullptr;
     uint32_t n_box = 0;
     bool packed = false;  // d_quat / d_scale hold boxes only (gsc_update_transforms_packed)
+    // d_quat / d_scale match the CURRENT collider set and layout: cleared by upload / append / remove (the arrays then
+    // hold another set's values, packed or in pre-swap_remove order), so "NULL keeps the previous values" is refused
+    // until rotation and scale were sent again (a set without boxes never needs them)
+    bool rot_scale_valid = false;
+    // pinned transform staging (gsc_map_transform_staging), allocated on first use
+    float *h_stage[2][3] = { { nullptr, nullptr, nullptr }, { nullptr, nullptr, nullptr } };
+    // GSC_FLAG_GRAPH: stages 1-5 captured once per launch geometry
+    cudaGraphExec_t graph_exec = nullptr;
+    uint32_t graph_n = 0;
+    bool graph_window = false;
+    int32_t graph_win[2] = { 0, 0 };
     // host -> device transform copies are cut into chunks; bvh_update starts on a chunk as soon as it has landed
     static constexpr int kChunks = 8;
     uint32_t chunk_begin[kChunks + 1] = {}, chunk_box[kChunks + 1] = {};
@@ -70,7 +84,8 @@ struct gsc_ctx {
     uint32_t *d_keys[2] = { nullptr, nullptr }, *d_vals[2] = { nullptr, nullptr };
     uint32_t *d_cell_start = nullptr, *d_wide = nullptr;
     uint32_t *d_overflow = nullptr;  // tiles of the pairs stage that did not fit its staging buffers
-    bool pairs_legacy = false;       // GSC_PAIRS_LEGACY=1: the round-1 thread-per-volume kernel on every tile (A/B measurements)
+    bool pairs_tiled = false;        // GSC_PAIRS_TILED=1: the tile-staged, work-flattened pairs kernel (measured slower, see DESIGN)
+    bool fuse_ss = true;             // GSC_FUSE_SS=0: sphere-sphere candidates go through the SAT stage's queue as in round 1
     uint4 *d_gaps = nullptr;
     bool have_window = false;
     int32_t win_lo = 0, win_hi = 0;
@@ -97,8 +112,17 @@ struct gsc_ctx {
         float4 *rec = nullptr, *obb = nullptr;
         FrameBlock *fb = nullptr;
         uint32_t cap = 0;
-        bool self = false;
+        bool self = false;   // this context itself
+        bool local = false;  // another context of this process (gsc_open_peer_local): nothing to unmap
+        SlabMail *mail() const { return fb ? reinterpret_cast<SlabMail *>(reinterpret_cast<char *>(fb) + kMailOffset) : nullptr; }
     } peers[GSC_MAX_PEERS];
+
+    // device-driven slab exchange (gsc_slab_*): mailbox behind the FrameBlock in the same allocation
+    SlabMail *d_mail = nullptr;
+    uint32_t slab_rank = 0, slab_world = 0, slab_seq = 0;
+    bool slab_ready = false, slab_step = false;  // slab_step: the step in flight / last collected ran the device-driven exchange
+    unsigned long long peer_timeout_ns = 5000000000ull;
+    cudaEvent_t ev_slab[2] = { nullptr, nullptr };  // behind the publish / behind the done flags (in-process groups order on them)
 
     uint64_t max_pairs = 0, max_cands = 0, max_cells = 0;
     uint64_t last_pairs = 0;
@@ -172,8 +196,10 @@ inline uint32_t tiles_for(uint32_t n) { return (n + kSortTile - 1) / kSortTile; 
 // Runs the radix passes on `n` (key, value) pairs.  Passes beyond ctl->num_passes exit on the device.
 // scratch = [kRadix * tiles] tile histogram + [kRadix] digit totals
 // `have_pass0_hist`: the producer of the keys (k_cell_keys) already filled the tile histogram of pass 0
+// `n_dev`: optional device-side element count (<= n); the launches are then sized for n and clamp to *n_dev
 void launch_sort(cudaStream_t s, uint32_t n, uint32_t *keys[2], uint32_t *vals[2], bool first_vals_identity,
-                 int max_passes, const SortControl *ctl, uint32_t *scratch, bool have_pass0_hist = false)
+                 int max_passes, const SortControl *ctl, uint32_t *scratch, bool have_pass0_hist = false,
+                 const uint32_t *n_dev = nullptr)
 {
     const uint32_t tiles = tiles_for(n);
     if (tiles == 0) return;
@@ -181,10 +207,10 @@ void launch_sort(cudaStream_t s, uint32_t n, uint32_t *keys[2], uint32_t *vals[2
     for (int pass = 0; pass < max_passes; ++pass) {
         const int in = pass & 1, out = in ^ 1;
         const uint32_t *vin = (pass == 0 && first_vals_identity) ? nullptr : vals[in];
-        if (pass > 0 || !have_pass0_hist) k_radix_upsweep<<<tiles, kSortThreads, 0, s>>>(keys[in], n, pass, ctl, tile_hist, tiles);
-        k_radix_scan<<<kRadix, 256, 0, s>>>(tile_hist, tiles, pass, ctl, digit_total);
+        if (pass > 0 || !have_pass0_hist) k_radix_upsweep<<<tiles, kSortThreads, 0, s>>>(keys[in], n, pass, ctl, tile_hist, tiles, n_dev);
+        k_radix_scan<<<kRadix, 256, 0, s>>>(tile_hist, tiles, pass, ctl, digit_total, n_dev);
         k_radix_downsweep<<<tiles, kSortThreads, 0, s>>>(keys[in], vin, keys[out], vals[out], n, pass, ctl, tile_hist,
-                                                        digit_total, tiles);
+                                                        digit_total, tiles, n_dev);
     }
 }
 
@@ -206,6 +232,12 @@ int status_to_error(gsc_ctx *c, const FrameBlock &fb)
     if (st & kStCellSize) return fail(c, GSC_ERR_RANGE, "cell size (longest AABB axis) is not positive: %g", (double)fb.grid.cell_size);
     if (st & kStRange) return fail(c, GSC_ERR_RANGE, "a grid coordinate leaves the i16 range of GridCoord (grid_collision.rs:535)");
     if (st & kStWindow) return fail(c, GSC_ERR_INVALID, "gsc_set_x_window does not cover the home cell of a local collider");
+    if (st & kStPeerTimeout)
+        return fail(c, GSC_ERR_NCCL, "slab exchange: a peer GPU did not publish its bounds / finish its halo push within %llu ms "
+                                     "(a rank failed, or the ranks are not stepping together)", c->peer_timeout_ns / 1000000ull);
+    if (st & kStGhostCap)
+        return fail(c, GSC_ERR_CAPACITY, "slab exchange: %u local + %u pushed ghost colliders > max_colliders %u", c->n_local,
+                    fb.n_ghost_in, c->cap);
     if (st & kStCells) return fail(c, GSC_ERR_CAPACITY, "dense cell table too small: raise gsc_config.max_cells (have %llu)", (unsigned long long)c->max_cells);
     return GSC_OK;
 }
@@ -296,8 +328,10 @@ int gsc_create(const gsc_config *cfg, gsc_ctx **out)
     CR(dmalloc(&c->d_overflow, (M + kTileA - 1) / kTileA + 1));
     CR(cudaFuncSetAttribute(k_pairs_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)));
     {
-        const char *e = getenv("GSC_PAIRS_LEGACY");
-        c->pairs_legacy = e && e[0] == '1';
+        const char *e = getenv("GSC_PAIRS_TILED");
+        c->pairs_tiled = e && e[0] == '1';
+        e = getenv("GSC_FUSE_SS");
+        c->fuse_ss = !(e && e[0] == '0');
     }
     CR(dmalloc(&c->d_gaps, (size_t)kGapCap));
     CR(dmalloc(&c->d_pairs, c->max_pairs));
@@ -305,7 +339,15 @@ int gsc_create(const gsc_config *cfg, gsc_ctx **out)
     CR(dmalloc(&c->d_cand_ss, c->max_cands));
     CR(dmalloc(&c->d_cand_so, c->max_cands));
     CR(dmalloc(&c->d_cand_oo, c->max_cands));
-    CR(dmalloc(&c->d_fb, 1));
+    {   // FrameBlock (zeroed every step) + SlabMail (never zeroed after this) in ONE allocation: one IPC handle maps both
+        void *blk = nullptr;
+        CR(cudaMalloc(&blk, kMailOffset + sizeof(SlabMail)));
+        CR(cudaMemset(blk, 0, kMailOffset + sizeof(SlabMail)));
+        c->d_fb = reinterpret_cast<FrameBlock *>(blk);
+        c->d_mail = reinterpret_cast<SlabMail *>(reinterpret_cast<char *>(blk) + kMailOffset);
+    }
+    for (auto &ev : c->ev_slab) CR(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    if (const char *e = getenv("GSC_PEER_TIMEOUT_MS")) c->peer_timeout_ns = strtoull(e, nullptr, 10) * 1000000ull;
     CR(dmalloc(&c->d_sort_scratch, sort_scratch_words(c->cap)));
     CR(dmalloc(&c->d_halo_count, 1));
     CR(cudaHostAlloc((void **)&c->h_fb, sizeof(FrameBlock), cudaHostAllocDefault));
@@ -332,8 +374,10 @@ void gsc_destroy(gsc_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto &ev : c->ev_slab)
+        if (ev) cudaEventDestroy(ev);
     for (auto &p : c->peers)
-        if (p.rec && !p.self) {
+        if (p.rec && !p.self && !p.local) {
             cudaIpcCloseMemHandle(p.rec);
             cudaIpcCloseMemHandle(p.obb);
             cudaIpcCloseMemHandle(p.fb);
@@ -345,6 +389,10 @@ void gsc_destroy(gsc_ctx *c)
                      c->d_lscale, c->d_dpos, c->d_dquat, c->d_dscale, c->d_dmat };
     for (void *b : bufs)
         if (b) cudaFree(b);
+    for (auto &bank : c->h_stage)
+        for (float *&b : bank)
+            if (b) cudaFreeHost(b);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->h_fb) cudaFreeHost(c->h_fb);
     if (c->h_enc) cudaFreeHost(c->h_enc);
     for (auto &ev : c->ev)
@@ -383,6 +431,7 @@ int gsc_upload_colliders(gsc_ctx *c, uint32_t n, const uint32_t *entity, const u
     c->have_gidx = global_index != nullptr;
     c->have_colliders = true;
     c->have_transforms = false;
+    c->rot_scale_valid = false;
     c->packed = false;
     c->chunked = false;
     c->hier_colliders = 0;
@@ -424,6 +473,7 @@ int gsc_append_colliders(gsc_ctx *c, uint32_t n_new, const uint32_t *entity, con
     c->n_local = n0 + n_new;
     if (int rc = rebuild_box_slots(c)) return rc;
     c->have_transforms = false;
+    c->rot_scale_valid = false;
     c->packed = false;
     c->chunked = false;
     c->hier_colliders = 0;
@@ -475,6 +525,7 @@ int gsc_remove_colliders(gsc_ctx *c, uint32_t n_remove, const uint32_t *index)
     c->n_local = len;
     if (int rc = rebuild_box_slots(c)) return rc;
     c->have_transforms = false;
+    c->rot_scale_valid = false;
     c->packed = false;
     c->chunked = false;
     c->hier_colliders = 0;
@@ -509,9 +560,11 @@ int gsc_update_transforms(gsc_ctx *c, uint32_t n, const float *pos3, const float
     if (!c->have_colliders || n != c->n_local)
         return fail(c, GSC_ERR_INVALID, "gsc_update_transforms: n=%u does not match the %u uploaded colliders", n, c->n_local);
     if (n && !pos3) return fail(c, GSC_ERR_INVALID, "gsc_update_transforms: null positions");
-    if (c->packed && (!quat4 || !scale3) && c->n_box)
-        return fail(c, GSC_ERR_INVALID, "gsc_update_transforms: after a packed update, pass rotation and scale again");
+    if ((c->packed || !c->rot_scale_valid) && (!quat4 || !scale3) && c->n_box)
+        return fail(c, GSC_ERR_INVALID, c->packed ? "gsc_update_transforms: after a packed update, pass rotation and scale again"
+                                                  : "gsc_update_transforms: the collider set changed (upload / append / remove): pass rotation and scale again");
     if (int rc = copy_transforms(c, n, pos3, quat4, scale3, false)) return rc;
+    c->rot_scale_valid = true;
     c->packed = false;
     c->b_pos = c->d_pos;
     c->b_quat = c->d_quat;
@@ -528,14 +581,52 @@ int gsc_update_transforms_packed(gsc_ctx *c, uint32_t n, const float *pos3, uint
         return fail(c, GSC_ERR_INVALID, "gsc_update_transforms_packed: n=%u / n_box=%u do not match the uploaded %u colliders / %u boxes",
                     n, n_box, c->n_local, c->n_box);
     if (n && !pos3) return fail(c, GSC_ERR_INVALID, "gsc_update_transforms_packed: null positions");
-    if (n_box && !c->packed && (!box_quat4 || !box_scale3))
-        return fail(c, GSC_ERR_INVALID, "gsc_update_transforms_packed: the first packed update needs rotation and scale");
+    if (n_box && (!c->packed || !c->rot_scale_valid) && (!box_quat4 || !box_scale3))
+        return fail(c, GSC_ERR_INVALID, "gsc_update_transforms_packed: the first packed update (also after upload / append / remove) needs rotation and scale");
     if (int rc = copy_transforms(c, n, pos3, box_quat4, box_scale3, true)) return rc;
+    c->rot_scale_valid = true;
     c->packed = true;
     c->b_pos = c->d_pos;
     c->b_quat = c->d_quat;
     c->b_scale = c->d_scale;
     c->have_transforms = true;
+    return GSC_OK;
+}
+
+// ---- pinned transform staging -----------------------------------------------------------------------------------
+int gsc_map_transform_staging(gsc_ctx *c, uint32_t bank, float **pos3, float **box_quat4, float **box_scale3)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (bank > 1 || !pos3 || !box_quat4 || !box_scale3) return fail(c, GSC_ERR_INVALID, "gsc_map_transform_staging: bad argument");
+    const size_t per[3] = { 12, 16, 12 };
+    for (int k = 0; k < 3; ++k)
+        if (!c->h_stage[bank][k]) CU(c, cudaHostAlloc((void **)&c->h_stage[bank][k], std::max<size_t>(c->cap, 1) * per[k], cudaHostAllocDefault));
+    *pos3 = c->h_stage[bank][0];
+    *box_quat4 = c->h_stage[bank][1];
+    *box_scale3 = c->h_stage[bank][2];
+    return GSC_OK;
+}
+
+int gsc_commit_transform_staging(gsc_ctx *c, uint32_t bank, uint32_t n, uint32_t n_box, int with_rotation, int with_scale)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (bank > 1 || !c->h_stage[bank][0]) return fail(c, GSC_ERR_INVALID, "gsc_commit_transform_staging: bank %u was not mapped", bank);
+    return gsc_update_transforms_packed(c, n, c->h_stage[bank][0], n_box, with_rotation ? c->h_stage[bank][1] : nullptr,
+                                        with_scale ? c->h_stage[bank][2] : nullptr);
+}
+
+int gsc_box_slots(gsc_ctx *c, uint32_t *box_slot, uint32_t cap, uint32_t *n_box)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!c->have_colliders) return fail(c, GSC_ERR_INVALID, "gsc_box_slots before gsc_upload_colliders");
+    if (n_box) *n_box = c->n_box;
+    if (!box_slot) return GSC_OK;
+    if (cap < c->n_local) return fail(c, GSC_ERR_CAPACITY, "gsc_box_slots: need room for %u entries", c->n_local);
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < c->n_local; ++i) {
+        box_slot[i] = k;
+        k += c->h_kind[i] == GSC_BOX;
+    }
     return GSC_OK;
 }
 
@@ -547,9 +638,12 @@ int gsc_bind_device_transforms(gsc_ctx *c, uint32_t n, const float *d_pos3, cons
     if (n && !d_pos3) return fail(c, GSC_ERR_INVALID, "gsc_bind_device_transforms: null positions");
     if (d_quat4 && (reinterpret_cast<uintptr_t>(d_quat4) & 15))
         return fail(c, GSC_ERR_INVALID, "gsc_bind_device_transforms: quaternions must be 16-byte aligned");
-    if (c->packed && (!d_quat4 || !d_scale3) && c->n_box)
-        return fail(c, GSC_ERR_INVALID, "gsc_bind_device_transforms: after a packed update, pass rotation and scale again");
-    c->packed = false;
+    if (!c->rot_scale_valid && (!d_quat4 || !d_scale3) && c->n_box)
+        return fail(c, GSC_ERR_INVALID, "gsc_bind_device_transforms: no rotation / scale on the device for the current collider set: pass them");
+    // (`packed` describes the layout of the OWNED rotation / scale arrays; a NULL here keeps using them as they are,
+    // caller arrays are always dense -- so the two cannot be mixed while the owned ones are packed)
+    if (c->packed && c->n_box && ((d_quat4 == nullptr) != (d_scale3 == nullptr)))
+        return fail(c, GSC_ERR_INVALID, "gsc_bind_device_transforms: after a packed update pass rotation AND scale, or neither");
     c->chunked = false;
     c->b_pos = d_pos3;
     c->b_quat = d_quat4 ? d_quat4 : c->d_quat;
@@ -577,7 +671,7 @@ static int stage_bounds(gsc_ctx *c)
         if (e > b)
             k_bvh_update<<<(e - b + kBvhThreads - 1) / kBvhThreads, kBvhThreads, 0, s>>>(
                 b, e, c->d_kind, c->d_offset, c->d_size, c->b_pos, c->b_quat, c->b_scale, c->d_entity,
-                c->have_gidx ? c->d_gidx : nullptr, c->packed ? c->d_box_slot : nullptr, c->d_rec, c->d_obb, c->d_fb);
+                c->have_gidx ? c->d_gidx : nullptr, (c->packed && c->b_quat == c->d_quat) ? c->d_box_slot : nullptr, c->d_rec, c->d_obb, c->d_fb);
         if (!c->chunked) break;
     }
     CU(c, cudaGetLastError());
@@ -589,18 +683,21 @@ static int stage_bounds(gsc_ctx *c)
     return GSC_OK;
 }
 
-static int stage_enqueue(gsc_ctx *c)
+// The launches of stages 1-5 and the read-back of the control block.
+// `slab`: the step's volume count (local + pushed ghosts) and the windowed grid were produced on the device by
+// k_slab_gather / k_slab_wait: launches are sized for the capacity and clamp to FrameBlock::n_total
+static int stage_launches(gsc_ctx *c, bool slab, bool timing)
 {
     cudaStream_t s = c->stream;
-    const bool timing = c->cfg.flags & GSC_FLAG_TIMING;
-    const uint32_t n_total = c->n_local + c->n_ghost;
+    const uint32_t n_total = slab ? c->cap : c->n_local + c->n_ghost;
+    const uint32_t n_launch = n_total;
+    const uint32_t *n_dev = slab ? &c->d_fb->n_total : nullptr;
     FrameBlock *fb = c->d_fb;
-    k_grid_setup<<<1, 32, 0, s>>>(fb, c->max_cells, n_total, c->have_window ? 1 : 0, c->win_lo, c->win_hi);
+    if (!slab) k_grid_setup<<<1, 32, 0, s>>>(fb, c->max_cells, n_total, c->have_window ? 1 : 0, c->win_lo, c->win_hi);
     if (n_total) {
-        k_cell_keys<<<tiles_for(n_total), kKeyThreads, 0, s>>>(n_total, c->d_rec, c->d_keys[0], c->d_wide, c->d_sort_scratch,
-                                                              tiles_for(n_total), fb);
+        k_cell_keys<<<tiles_for(n_total), kKeyThreads, 0, s>>>(n_total, c->d_rec, c->d_keys[0], c->d_wide, c->d_sort_scratch, fb);
         if (timing) CU(c, cudaEventRecord(c->ev[2], s));
-        launch_sort(s, n_total, c->d_keys, c->d_vals, true, kMaxPasses, &fb->sort, c->d_sort_scratch, true);
+        launch_sort(s, n_total, c->d_keys, c->d_vals, true, kMaxPasses, &fb->sort, c->d_sort_scratch, true, n_dev);
         if (timing) CU(c, cudaEventRecord(c->ev[3], s));
         const uint32_t tb = (n_total + 1 + kTableThreads - 1) / kTableThreads;
         SortedVolumes sv{ c->d_rec_sorted, c->d_qrec_sorted, c->d_w3_sorted };
@@ -609,13 +706,17 @@ static int stage_enqueue(gsc_ctx *c)
         k_fill_gaps<<<148 * 2, 256, 0, s>>>(c->d_cell_start, c->d_gaps, fb);
         if (timing) CU(c, cudaEventRecord(c->ev[4], s));
         // sphere-sphere pairs are decided inside the pairs stage unless a contact has to be computed for them
-        PairOut po{ c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands, c->d_pairs, c->max_pairs, c->d_overflow, c->d_contacts ? 0 : 1 };
-        if (!c->pairs_legacy)
-            k_pairs_tiled<<<(n_total + kTileA - 1) / kTileA, kTileA, sizeof(TileShared), s>>>(n_total, c->d_keys[0], c->d_keys[1], sv,
-                                                                                           c->d_cell_start, po, fb);
-        // tiles too dense for the staging buffers (normally none: the kernel exits at once)
-        k_pairs<<<148 * GSC_PAIR_MIN_CTAS, kPairThreads, 0, s>>>(n_total, c->d_keys[0], c->d_keys[1], sv, c->d_cell_start, po, fb,
-                                                                 c->pairs_legacy ? 1 : 0);
+        PairOut po{ c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands, c->d_pairs, c->max_pairs, c->d_overflow,
+                    (c->d_contacts || !c->fuse_ss) ? 0 : 1 };
+        if (c->pairs_tiled) {
+            k_pairs_tiled<<<(n_launch + kTileA - 1) / kTileA, kTileA, sizeof(TileShared), s>>>(n_launch, c->d_keys[0], c->d_keys[1], sv,
+                                                                                            c->d_cell_start, po, fb);
+            // tiles too dense for the staging buffers (normally none: the kernel exits at once)
+            k_pairs<true><<<148 * 16, kPairThreads, 0, s>>>(n_launch, c->d_keys[0], c->d_keys[1], sv, c->d_cell_start, po, fb);
+        } else {
+            k_pairs<false><<<(n_launch + kPairThreads - 1) / kPairThreads, kPairThreads, 0, s>>>(n_launch, c->d_keys[0], c->d_keys[1], sv,
+                                                                                              c->d_cell_start, po, fb);
+        }
         if (timing) CU(c, cudaEventRecord(c->ev[5], s));
         if (c->d_contacts)
             k_narrow<true><<<148 * kNarrowCtasPerSm, kNarrowThreads, 0, s>>>(c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands, c->d_rec_sorted,
@@ -631,6 +732,40 @@ static int stage_enqueue(gsc_ctx *c)
     }
     CU(c, cudaGetLastError());
     CU(c, cudaMemcpyAsync(c->h_fb, fb, sizeof(FrameBlock), cudaMemcpyDeviceToHost, s));
+    return GSC_OK;
+}
+
+static int stage_enqueue(gsc_ctx *c, bool slab = false)
+{
+    cudaStream_t s = c->stream;
+    const bool timing = c->cfg.flags & GSC_FLAG_TIMING;
+    // GSC_FLAG_GRAPH: the launch sequence has no host round trip and its geometry only depends on the collider count
+    // (and the slab window), so it is captured once and replayed with ONE graph launch per step
+    if ((c->cfg.flags & GSC_FLAG_GRAPH) && !timing && !slab) {
+        const uint32_t n_total = c->n_local + c->n_ghost;
+        const bool same = c->graph_exec && c->graph_n == n_total && c->graph_window == c->have_window &&
+                          (!c->have_window || (c->graph_win[0] == c->win_lo && c->graph_win[1] == c->win_hi));
+        if (!same) {
+            if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+            c->graph_exec = nullptr;
+            cudaGraph_t graph = nullptr;
+            CU(c, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            const int rc = stage_launches(c, false, false);
+            const cudaError_t e = cudaStreamEndCapture(s, &graph);
+            if (rc != GSC_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess) return fail(c, GSC_ERR_CUDA, "graph capture: %s", cudaGetErrorString(e));
+            const cudaError_t e2 = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e2 != cudaSuccess) { c->graph_exec = nullptr; return fail(c, GSC_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e2)); }
+            c->graph_n = n_total;
+            c->graph_window = c->have_window;
+            c->graph_win[0] = c->win_lo;
+            c->graph_win[1] = c->win_hi;
+        }
+        CU(c, cudaGraphLaunch(c->graph_exec, s));
+    } else if (int rc = stage_launches(c, slab, timing)) {
+        return rc;
+    }
     CU(c, cudaEventRecord(c->ev_end, s));
     c->bounds_done = false;
     c->perm_valid = false;
@@ -645,10 +780,11 @@ static int stage_collect(gsc_ctx *c, gsc_step_out *out)
     CU(c, cudaStreamSynchronize(c->stream));
     const FrameBlock &h = *c->h_fb;
     c->last_pairs = std::min<uint64_t>(h.n_pairs, c->max_pairs);
+    if (c->slab_step) c->n_ghost = h.slab.n_ghost;
     if (out) {
         memset(out, 0, sizeof *out);
         out->n_pairs = h.n_pairs;
-        out->n_sphere_sphere = c->d_contacts ? h.n_ss : h.n_ss_fused;
+        out->n_sphere_sphere = (c->d_contacts || !c->fuse_ss) ? h.n_ss : h.n_ss_fused;
         out->n_sphere_obb = h.n_so;
         out->n_obb_obb = h.n_oo;
         out->n_cells = h.grid.num_cells;
@@ -662,6 +798,7 @@ static int stage_collect(gsc_ctx *c, gsc_step_out *out)
         out->status_flags = h.status;
         out->d_pairs = reinterpret_cast<const uint32_t *>(c->d_pairs);
         out->d_contacts = reinterpret_cast<const float *>(c->d_contacts);
+        out->n_ghost = c->slab_step ? h.slab.n_ghost : c->n_ghost;
         cudaEventElapsedTime(&out->step_ms, c->ev_begin, c->ev_end);
         if (timing)
             for (int i = 0; i < GSC_NUM_STAGES; ++i) cudaEventElapsedTime(&out->stage_ms[i], c->ev[i], c->ev[i + 1]);
@@ -687,6 +824,7 @@ int gsc_step(gsc_ctx *c, gsc_step_out *out)
 {
     if (int rc = check_ctx(c)) return rc;
     NOT_IN_FLIGHT(c, "gsc_step");
+    c->slab_step = false;
     if (int rc = stage_bounds(c)) return rc;
     return stage_finish(c, out);
 }
@@ -695,6 +833,7 @@ int gsc_step_begin(gsc_ctx *c)
 {
     if (int rc = check_ctx(c)) return rc;
     NOT_IN_FLIGHT(c, "gsc_step_begin");
+    c->slab_step = false;
     if (int rc = stage_bounds(c)) return rc;
     if (int rc = stage_enqueue(c)) return rc;
     c->in_flight = true;
@@ -714,6 +853,7 @@ int gsc_phase_bounds(gsc_ctx *c, gsc_bounds *local)
     if (int rc = check_ctx(c)) return rc;
     NOT_IN_FLIGHT(c, "gsc_phase_bounds");
     if (!local) return fail(c, GSC_ERR_INVALID, "gsc_phase_bounds: null output");
+    c->slab_step = false;
     if (int rc = stage_bounds(c)) return rc;
     CU(c, cudaMemcpyAsync(c->h_fb, c->d_fb, sizeof(FrameBlock), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
@@ -794,7 +934,7 @@ int gsc_ipc_open_peer(gsc_ctx *c, uint32_t peer, const void *blob, size_t blob_b
     IpcBlob b;
     memcpy(&b, blob, sizeof b);
     gsc_ctx::Peer &p = c->peers[peer];
-    if (p.rec && !p.self) {  // re-open: drop the old mapping
+    if (p.rec && !p.self && !p.local) {  // re-open: drop the old mapping
         cudaIpcCloseMemHandle(p.rec);
         cudaIpcCloseMemHandle(p.obb);
         cudaIpcCloseMemHandle(p.fb);
@@ -848,6 +988,125 @@ int gsc_halo_commit(gsc_ctx *c, uint32_t *n_ghost)
         return fail(c, GSC_ERR_CAPACITY, "gsc_halo_commit: %u local + %u pushed ghosts > max_colliders %u", c->n_local, pushed, c->cap);
     c->n_ghost += pushed;
     return GSC_OK;
+}
+
+// ---- slab exchange driven from the device (k_slab_*) -----------------------------------------------------------
+static SlabPeers slab_peers(const gsc_ctx *c)
+{
+    SlabPeers sp;
+    memset(&sp, 0, sizeof sp);
+    for (uint32_t s = 0; s < c->slab_world; ++s) {
+        const gsc_ctx::Peer &p = c->peers[s];
+        sp.rec[s] = p.rec;
+        sp.obb[s] = p.obb;
+        sp.fb[s] = p.fb;
+        sp.mail[s] = p.mail();
+        sp.cap[s] = p.cap;
+    }
+    return sp;
+}
+
+// phase A: bvh_update over the local colliders, then my bounds go into every rank's mailbox
+static int slab_phase_a(gsc_ctx *c)
+{
+    if (!c->slab_ready) return fail(c, GSC_ERR_INVALID, "slab step: call gsc_slab_init first");
+    if (int rc = stage_bounds(c)) return rc;
+    c->slab_step = true;
+    ++c->slab_seq;
+    k_slab_publish<<<1, 32, 0, c->stream>>>(c->d_fb, slab_peers(c), c->slab_rank, c->slab_world, c->n_local, c->slab_seq);
+    CU(c, cudaGetLastError());
+    CU(c, cudaEventRecord(c->ev_slab[0], c->stream));
+    return GSC_OK;
+}
+
+// phase B: wait for every rank's bounds, place my grid, push my boundary volumes into the peers that need them
+static int slab_phase_b(gsc_ctx *c)
+{
+    cudaStream_t s = c->stream;
+    k_slab_gather<<<1, 32, 0, s>>>(c->d_fb, c->d_mail, c->slab_rank, c->slab_world, c->slab_seq, c->max_cells, c->n_local + 1,
+                                   c->peer_timeout_ns);
+    if (c->n_local && c->slab_world > 1)
+        k_slab_push<<<dim3(148 * 2, c->slab_world), kPushThreads, 0, s>>>(c->n_local, c->d_rec, c->d_obb, slab_peers(c), c->slab_rank, c->d_fb);
+    k_slab_done<<<1, 32, 0, s>>>(slab_peers(c), c->slab_rank, c->slab_world, c->slab_seq);
+    CU(c, cudaGetLastError());
+    CU(c, cudaEventRecord(c->ev_slab[1], s));
+    return GSC_OK;
+}
+
+// phase C: wait for the peers' pushes, adopt the ghosts, stages 1-5
+static int slab_phase_c(gsc_ctx *c)
+{
+    k_slab_wait<<<1, 32, 0, c->stream>>>(c->d_fb, c->d_mail, c->slab_rank, c->slab_world, c->slab_seq, c->n_local, c->cap,
+                                         c->peer_timeout_ns);
+    CU(c, cudaGetLastError());
+    return stage_enqueue(c, true);
+}
+
+int gsc_slab_init(gsc_ctx *c, uint32_t rank, uint32_t world)
+{
+    if (int rc = check_ctx(c)) return rc;
+    NOT_IN_FLIGHT(c, "gsc_slab_init");
+    if (world == 0 || world > GSC_MAX_PEERS || rank >= world) return fail(c, GSC_ERR_INVALID, "gsc_slab_init: rank %u of %u", rank, world);
+    gsc_ctx::Peer &me = c->peers[rank];
+    if (!me.rec) {  // a rank is its own peer `rank`
+        me = gsc_ctx::Peer();
+        me.rec = c->d_rec;
+        me.obb = c->d_obb;
+        me.fb = c->d_fb;
+        me.cap = c->cap;
+        me.self = true;
+    }
+    for (uint32_t s = 0; s < world; ++s)
+        if (!c->peers[s].rec) return fail(c, GSC_ERR_INVALID, "gsc_slab_init: peer %u was not opened (gsc_ipc_open_peer / gsc_open_peer_local)", s);
+    c->slab_rank = rank;
+    c->slab_world = world;
+    c->slab_ready = true;
+    return GSC_OK;
+}
+
+int gsc_open_peer_local(gsc_ctx *c, uint32_t peer, gsc_ctx *other)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (peer >= GSC_MAX_PEERS || !other) return fail(c, GSC_ERR_INVALID, "gsc_open_peer_local: bad argument");
+    gsc_ctx::Peer &p = c->peers[peer];
+    if (p.rec && !p.self && !p.local) {
+        cudaIpcCloseMemHandle(p.rec);
+        cudaIpcCloseMemHandle(p.obb);
+        cudaIpcCloseMemHandle(p.fb);
+    }
+    p = gsc_ctx::Peer();
+    if (other->device != c->device) {
+        int can = 0;
+        CU(c, cudaDeviceCanAccessPeer(&can, c->device, other->device));
+        if (!can) return fail(c, GSC_ERR_CUDA, "gsc_open_peer_local: device %d cannot access device %d", c->device, other->device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(other->device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (e != cudaSuccess) return fail(c, GSC_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", other->device, cudaGetErrorString(e));
+    }
+    p.rec = other->d_rec;
+    p.obb = other->d_obb;
+    p.fb = other->d_fb;
+    p.cap = other->cap;
+    p.self = other == c;
+    p.local = other != c;
+    return GSC_OK;
+}
+
+int gsc_slab_step_begin(gsc_ctx *c)
+{
+    if (int rc = check_ctx(c)) return rc;
+    NOT_IN_FLIGHT(c, "gsc_slab_step_begin");
+    if (int rc = slab_phase_a(c)) return rc;
+    if (int rc = slab_phase_b(c)) return rc;
+    if (int rc = slab_phase_c(c)) return rc;
+    c->in_flight = true;
+    return GSC_OK;
+}
+
+int gsc_slab_step(gsc_ctx *c, gsc_step_out *out)
+{
+    if (int rc = gsc_slab_step_begin(c)) return rc;
+    return gsc_step_end(c, out);
 }
 
 int gsc_set_x_window(gsc_ctx *c, int32_t x_lo, int32_t x_hi)
@@ -1253,6 +1512,9 @@ int gsc_hierarchy_upload(gsc_ctx *c, uint32_t n_nodes, uint32_t n_rows, const ui
     c->hier_row_begin.assign(row_begin, row_begin + n_rows + 1);
     c->hier_colliders = n_colliders;
     c->hier_derived = false;
+    // a new hierarchy: the local transforms on the device belong to the previous one ("NULL keeps the previous
+    // values" must not reuse them)
+    c->hier_local[0] = c->hier_local[1] = c->hier_local[2] = false;
     return GSC_OK;
 }
 
@@ -1291,6 +1553,7 @@ int gsc_hierarchy_update(gsc_ctx *c, const float *local_pos3, const float *local
     CU(c, cudaGetLastError());
     CU(c, cudaStreamSynchronize(s));  // the caller's host arrays are borrowed for the call only
     c->hier_derived = true;
+    c->rot_scale_valid = true;  // k_hier_bind wrote rotation and scale of every collider
     c->packed = false;
     c->chunked = false;
     c->b_pos = c->d_pos;
@@ -1470,3 +1733,5 @@ int gsc_sort_pairs_u32(int device, size_t n, uint32_t *keys, uint32_t *vals, int
 }
 
 }  // extern "C"
+
+#include "gsc_group.cuh"

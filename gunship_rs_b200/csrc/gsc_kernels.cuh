@@ -34,6 +34,8 @@ enum : uint32_t {
     kStPairs = 1u << 5,
     kStCands = 1u << 6,
     kStWindow = 1u << 7,
+    kStPeerTimeout = 1u << 8,  // a peer GPU did not publish its bounds / finish its halo push in time
+    kStGhostCap = 1u << 9,     // local + pushed ghost volumes exceed the context's capacity
 };
 
 // ---- volume record: 32 B = 2 x float4, the unit the broadphase streams ----
@@ -78,6 +80,40 @@ struct GridParams {
     float qorg[3], qscale[3], qmargin;  // conservative box quantisation of k_pairs: t = (v - qorg) * qscale, qscale = 128 / cell (x, y), 64 / cell (z)
 };
 
+// ---- multi-GPU slab exchange without the host (k_slab_*) ----
+constexpr int kMaxPeers = 16;  // == GSC_MAX_PEERS
+
+// what k_slab_gather works out for this rank from all ranks' bounds (absolute home x-cells)
+struct SlabState {
+    int32_t push_lo[kMaxPeers], push_hi[kMaxPeers];  // my volumes with home x-cell in [lo, hi] go to peer s (lo > hi: none)
+    uint32_t peer_n_local[kMaxPeers];                // where peer s's ghost region starts
+    int32_t x_lo[kMaxPeers], x_hi[kMaxPeers];        // every rank's home x-range (lo > hi: no colliders)
+    uint32_t n_ghost;                                // ghosts adopted this step (k_slab_wait)
+    uint32_t pad;
+};
+
+// Mailbox of a context, written by the PEERS over NVLink / NVSwitch peer memory (one slot per sender), never zeroed:
+// `seq` / `done_seq` carry the step number, so a slot is valid exactly when its sequence equals the current step.
+struct SlabMailSlot {
+    uint32_t bounds[8];  // the sender's FrameBlock::bounds after its bvh_update
+    uint32_t n_local;
+    uint32_t status;
+    uint32_t pad[5];
+    uint32_t seq;        // written last (release)
+};
+struct SlabMail {
+    SlabMailSlot from[kMaxPeers];
+    uint32_t done_seq[kMaxPeers];  // sender s has finished pushing its halo into this context for step done_seq[s]
+};
+struct FrameBlock;
+struct SlabPeers {  // kernel parameter: the mapped arrays of every rank (own entry included)
+    float4 *rec[kMaxPeers];
+    float4 *obb[kMaxPeers];
+    FrameBlock *fb[kMaxPeers];
+    SlabMail *mail[kMaxPeers];
+    uint32_t cap[kMaxPeers];
+};
+
 // Per-step device control block.  Zeroed at the start of every step.
 struct FrameBlock {
     uint32_t bounds[8];  // [0] ord(longest axis); [1..3] ~ord(world min xyz); [4..6] ord(world max xyz); [7] ord(max aabb.min.x)
@@ -94,6 +130,7 @@ struct FrameBlock {
     unsigned long long n_ss_fused;  // AABB-overlapping sphere-sphere candidates decided inside the pairs stage
     GridParams grid;
     SortControl sort;
+    SlabState slab;
 };
 
 // ---- block-aggregated stream compaction ------------------------------------------------------
@@ -273,9 +310,8 @@ k_bvh_update(uint32_t first, uint32_t n, const uint8_t *__restrict__ kind, const
 // cell size = longest axis (grid_collision.rs:238-240); dense grid covers floor(world min / cell) ..
 // floor(world max / cell), which bounds every home cell because floor(fl(p / c)) is monotone in p.
 // `has_window`: the caller (multi-GPU slab layer) restricts the grid to home x-cells [x_lo, x_hi] (absolute).
-__global__ void k_grid_setup(FrameBlock *fb, unsigned long long max_cells, uint32_t n_total, int has_window, int x_lo, int x_hi)
+GSC_DEV void grid_setup(FrameBlock *fb, unsigned long long max_cells, uint32_t n_total, int has_window, int x_lo, int x_hi)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
     GridParams g;
     g.valid = 0;
     g.num_cells = 0;
@@ -337,6 +373,12 @@ __global__ void k_grid_setup(FrameBlock *fb, unsigned long long max_cells, uint3
     fb->grid = g;
 }
 
+__global__ void k_grid_setup(FrameBlock *fb, unsigned long long max_cells, uint32_t n_total, int has_window, int x_lo, int x_hi)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    grid_setup(fb, max_cells, n_total, has_window, x_lo, x_hi);
+}
+
 GSC_DEV bool home_cell(const Volume &v, const GridParams &g, int c_mn[3], int c_mx[3])
 {
     bool wide = false;
@@ -357,14 +399,17 @@ constexpr int kKeyThreads = 256;
 // One CTA per sort tile (kSortTile volumes), so that the digit counts of the FIRST radix pass come for free:
 // tile_hist[d * num_tiles + tile] is what k_radix_upsweep would compute for pass 0.
 __global__ void __launch_bounds__(kKeyThreads)
-k_cell_keys(uint32_t n_total, const float4 *__restrict__ rec, uint32_t *__restrict__ keys,
-            uint32_t *__restrict__ wide_list, uint32_t *__restrict__ tile_hist, uint32_t num_tiles,
-            FrameBlock *__restrict__ fb)
+k_cell_keys(uint32_t n_cap, const float4 *__restrict__ rec, uint32_t *__restrict__ keys,
+            uint32_t *__restrict__ wide_list, uint32_t *__restrict__ tile_hist, FrameBlock *__restrict__ fb)
 {
     constexpr int WARPS = kKeyThreads / 32;
     __shared__ __align__(16) uint16_t s_hist[WARPS][kRadix];
     const GridParams g = fb->grid;
     if (!g.valid) return;
+    // (the grid may be sized for a capacity: the step's volume count -- local + ghosts -- lives on the device)
+    const uint32_t n_total = min(fb->n_total, n_cap);
+    const uint32_t num_tiles = (n_total + kSortTile - 1) / kSortTile;
+    if (blockIdx.x >= num_tiles) return;
     const int tid = threadIdx.x, warp = tid >> 5;
     const uint32_t mask = (1u << fb->sort.digit_bits) - 1u;
 #pragma unroll
@@ -457,13 +502,15 @@ constexpr int kGapCap = 4096;
 constexpr int kWarpFillMax = 4096;  // cells a warp fills transposed; wider spans (rare) go gap by gap
 
 __global__ void __launch_bounds__(kTableThreads)
-k_cell_table_permute(uint32_t n_total, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ vals_a,
+k_cell_table_permute(uint32_t n_cap, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ vals_a,
                      const uint32_t *__restrict__ keys_b, const uint32_t *__restrict__ vals_b,
                      const float4 *__restrict__ rec, SortedVolumes sv,
                      uint32_t *__restrict__ cell_start, uint4 *__restrict__ gaps, FrameBlock *__restrict__ fb)
 {
     const GridParams g = fb->grid;
     if (!g.valid) return;
+    const uint32_t n_total = min(fb->n_total, n_cap);
+    if (blockIdx.x * (uint32_t)kTableThreads > n_total) return;  // (position n_total itself closes the table)
     const bool in_b = fb->sort.num_passes & 1;  // ping-pong parity of the sort
     const uint32_t *keys = in_b ? keys_b : keys_a;
     const uint32_t *vals = in_b ? vals_b : vals_a;
@@ -792,19 +839,16 @@ k_halo_select(uint32_t n_local, const float4 *__restrict__ rec, const float4 *__
 constexpr int kPushThreads = 256;
 constexpr int kPushList = 3072;  // selected indices staged per CTA and round
 
-__global__ void __launch_bounds__(kPushThreads)
-k_halo_push(uint32_t n_local, const float4 *__restrict__ rec, const float4 *__restrict__ obb, int x_lo, int x_hi,
-            float4 *__restrict__ peer_rec, float4 *__restrict__ peer_obb, FrameBlock *peer_fb, uint32_t peer_first,
-            uint32_t peer_cap, const FrameBlock *__restrict__ fb)
+GSC_DEV void halo_push_cta(uint32_t n_local, const float4 *__restrict__ rec, const float4 *__restrict__ obb, int x_lo, int x_hi,
+                           float4 *__restrict__ peer_rec, float4 *__restrict__ peer_obb, FrameBlock *peer_fb, uint32_t peer_first,
+                           uint32_t peer_cap, const GridParams &g, uint32_t cta, uint32_t n_ctas)
 {
     __shared__ uint32_t s_list[kPushList];
     __shared__ uint32_t s_count, s_base;
-    const GridParams g = fb->grid;
-    if (!g.valid) return;
     const int lane = threadIdx.x & 31;
     // contiguous share of the records per CTA, walked in rounds that cannot overflow the list
-    const uint32_t per_cta = (n_local + gridDim.x - 1) / gridDim.x;
-    const uint32_t begin = min(n_local, blockIdx.x * per_cta), end = min(n_local, begin + per_cta);
+    const uint32_t per_cta = (n_local + n_ctas - 1) / n_ctas;
+    const uint32_t begin = min(n_local, cta * per_cta), end = min(n_local, begin + per_cta);
     for (uint32_t r0 = begin; r0 < end; r0 += kPushList) {
         const uint32_t r1 = min(end, r0 + (uint32_t)kPushList);
         if (threadIdx.x == 0) s_count = 0;
@@ -845,6 +889,171 @@ k_halo_push(uint32_t n_local, const float4 *__restrict__ rec, const float4 *__re
         }
         __syncthreads();
     }
+    __threadfence_system();  // the pushed records are visible to the peer before this rank's done flag can be
+}
+
+// host-driven exchange: the caller worked out the range (gsc_halo_push)
+__global__ void __launch_bounds__(kPushThreads)
+k_halo_push(uint32_t n_local, const float4 *__restrict__ rec, const float4 *__restrict__ obb, int x_lo, int x_hi,
+            float4 *__restrict__ peer_rec, float4 *__restrict__ peer_obb, FrameBlock *peer_fb, uint32_t peer_first,
+            uint32_t peer_cap, const FrameBlock *__restrict__ fb)
+{
+    const GridParams g = fb->grid;
+    if (!g.valid) return;
+    halo_push_cta(n_local, rec, obb, x_lo, x_hi, peer_rec, peer_obb, peer_fb, peer_first, peer_cap, g, blockIdx.x, gridDim.x);
+}
+
+// device-driven exchange: blockIdx.y = peer; the range comes from k_slab_gather (most peers need nothing: those CTAs
+// leave at once)
+__global__ void __launch_bounds__(kPushThreads)
+k_slab_push(uint32_t n_local, const float4 *__restrict__ rec, const float4 *__restrict__ obb, SlabPeers peers, uint32_t rank,
+            const FrameBlock *__restrict__ fb)
+{
+    const uint32_t s = blockIdx.y;
+    const int x_lo = fb->slab.push_lo[s], x_hi = fb->slab.push_hi[s];
+    if (s == rank || x_lo > x_hi || !(fb->bounds[0] != 0)) return;
+    GridParams g = fb->grid;  // (only the cell size is used)
+    halo_push_cta(n_local, rec, obb, x_lo, x_hi, peers.rec[s], peers.obb[s], peers.fb[s], fb->slab.peer_n_local[s], peers.cap[s], g,
+                  blockIdx.x, gridDim.x);
+}
+
+// ---- multi-GPU slab exchange driven from the device ---------------------------------------------------------------
+// Round 1 ran the exchange from the host: D2H of the bounds + stream sync, a host all-gather, an H2D of the global
+// bounds, the push launches, a second sync, a host barrier, a third sync to read the ghost count -- 0.26 ms per
+// step whatever the number of GPUs.  Here the ranks talk through each other's mapped memory and every wait is a
+// one-warp kernel on the rank's own stream:
+//   k_slab_publish  my bounds -> slot `rank` of every rank's mailbox (system-scope release)
+//   k_slab_gather   wait for all slots of my mailbox; reduce the global bounds; every rank's home x-range; what each
+//                   peer needs of mine; place my (windowed) grid
+//   k_halo_push     (one launch per peer, range read from the control block) select + write into the peer's arrays
+//   k_slab_done     my pushes are complete -> done flag in every peer's mailbox
+//   k_slab_wait     wait for every peer's done flag; adopt the ghosts: n_total = n_local + n_ghost_in
+// The host enqueues all of it plus stages 1-5 and waits ONCE, at the end of the step.
+GSC_DEV uint32_t ld_acquire_sys(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+GSC_DEV void st_release_sys(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+GSC_DEV unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// spin until *flag == seq; false on timeout
+GSC_DEV bool slab_wait_flag(const uint32_t *flag, uint32_t seq, unsigned long long timeout_ns)
+{
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys(flag) != seq) {
+        if (global_timer_ns() - t0 > timeout_ns) return false;
+        __nanosleep(64);
+    }
+    return true;
+}
+
+__global__ void k_slab_publish(const FrameBlock *__restrict__ fb, SlabPeers peers, uint32_t rank, uint32_t world, uint32_t n_local,
+                               uint32_t seq)
+{
+    const uint32_t s = threadIdx.x;
+    if (s >= world) return;
+    SlabMailSlot *dst = &peers.mail[s]->from[rank];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst->bounds[i] = fb->bounds[i];
+    dst->n_local = n_local;
+    dst->status = fb->status;
+    __threadfence_system();
+    st_release_sys(&dst->seq, seq);
+}
+
+__global__ void k_slab_gather(FrameBlock *fb, const SlabMail *mail, uint32_t rank, uint32_t world, uint32_t seq,
+                              unsigned long long max_cells, uint32_t n_hint, unsigned long long timeout_ns)
+{
+    const uint32_t s = threadIdx.x;
+    bool ok = true;
+    if (s < world) ok = slab_wait_flag(&mail->from[s].seq, seq, timeout_ns);
+    const bool all_ok = __all_sync(0xffffffffu, ok);
+    if (threadIdx.x != 0) return;
+    if (!all_ok) {
+        atomicOr(&fb->status, kStPeerTimeout);
+        fb->grid.valid = 0;
+        return;
+    }
+    // global bounds: bounds[] are ordered-uint encodings, every one of them reduces with max
+    uint32_t gb[7] = { 0, 0, 0, 0, 0, 0, 0 }, st = 0;
+    for (uint32_t r = 0; r < world; ++r) {
+        const SlabMailSlot &m = mail->from[r];
+        (void)ld_acquire_sys(&m.seq);  // (the slot arrived: lane r saw it; this orders lane 0's reads behind it)
+        for (int i = 0; i < 7; ++i) gb[i] = max(gb[i], m.bounds[i]);
+        st |= m.status;
+    }
+    for (int i = 0; i < 7; ++i) fb->bounds[i] = gb[i];
+    if (st) atomicOr(&fb->status, st);
+    const float cell = ord2f(gb[0]);
+    SlabState &sl = fb->slab;
+    for (uint32_t r = 0; r < world; ++r) {
+        const SlabMailSlot &m = mail->from[r];
+        // home x-cell = floor(fl(aabb.min.x / cell)) (grid_collision.rs:329-335): range of rank r from its smallest / largest aabb.min.x
+        const bool has = m.n_local != 0 && m.bounds[0] != 0 && gb[0] != 0 && cell > 0.0f && m.bounds[1] != 0 && m.bounds[7] != 0;
+        float lo = 1.0f, hi = 0.0f;
+        if (has) {
+            lo = cell_coord_f(ord2f(~m.bounds[1]), cell);
+            hi = cell_coord_f(ord2f(m.bounds[7]), cell);
+            if (!(lo >= -32768.0f) || !(hi <= 32767.0f)) { lo = 1.0f; hi = 0.0f; }  // (grid_setup reports the range error)
+        }
+        sl.x_lo[r] = (int32_t)lo;
+        sl.x_hi[r] = (int32_t)hi;
+        sl.peer_n_local[r] = m.n_local;
+    }
+    const int32_t my_lo = sl.x_lo[rank], my_hi = sl.x_hi[rank];
+    for (uint32_t r = 0; r < world; ++r) {
+        // rank r's takers look at home x-cells {x - 1, x}: it needs the foreign volumes in [x_lo_r - 1, x_hi_r]
+        int32_t lo = 1, hi = 0;
+        if (r != rank && my_lo <= my_hi && sl.x_lo[r] <= sl.x_hi[r]) {
+            lo = max(sl.x_lo[r] - 1, my_lo);
+            hi = min(sl.x_hi[r], my_hi);
+        }
+        sl.push_lo[r] = lo;
+        sl.push_hi[r] = hi;
+    }
+    // my grid covers my slab (+ the one column of ghosts below it), not the world
+    grid_setup(fb, max_cells, n_hint, my_lo <= my_hi ? 1 : 0, my_lo - 1, my_hi);
+    if (my_lo > my_hi) fb->grid.valid = 0;  // no local colliders: nothing to do on this rank (ghosts never take)
+}
+
+__global__ void k_slab_done(SlabPeers peers, uint32_t rank, uint32_t world, uint32_t seq)
+{
+    const uint32_t s = threadIdx.x;
+    if (s >= world || s == rank) return;
+    __threadfence_system();
+    st_release_sys(&peers.mail[s]->done_seq[rank], seq);
+}
+
+__global__ void k_slab_wait(FrameBlock *fb, const SlabMail *mail, uint32_t rank, uint32_t world, uint32_t seq, uint32_t n_local,
+                            uint32_t cap, unsigned long long timeout_ns)
+{
+    const uint32_t s = threadIdx.x;
+    bool ok = true;
+    if (s < world && s != rank) ok = slab_wait_flag(&mail->done_seq[s], seq, timeout_ns);
+    const bool all_ok = __all_sync(0xffffffffu, ok);
+    if (threadIdx.x != 0) return;
+    if (!all_ok) {
+        atomicOr(&fb->status, kStPeerTimeout);
+        fb->grid.valid = 0;
+        return;
+    }
+    uint32_t ghosts = atomicAdd_system(&fb->n_ghost_in, 0u);  // (the peers' reservations were system-scope atomics on this word)
+    if ((unsigned long long)n_local + ghosts > cap) {
+        atomicOr(&fb->status, kStGhostCap);
+        fb->grid.valid = 0;  // the pushed records beyond the capacity were dropped: no partial result
+        ghosts = cap - n_local;
+    }
+    fb->slab.n_ghost = ghosts;
+    fb->n_total = n_local + ghosts;
 }
 
 // Appends ghosts received from another slab behind the local volumes: new local index, ghost flag.

@@ -77,7 +77,7 @@ GSC_DEV int pair_classify(uint32_t a_pos, uint32_t a_gidx, uint32_t a_meta, uint
 // exact test + classification of one filtered (A at sorted position p, B at q) pair.
 //   returns 0 sphere-sphere HIT when fuse_ss (item = entities), else sphere-sphere candidate; 1; 2; 3 = nothing to emit.
 //   *was_ss: the pair was an AABB-overlapping sphere-sphere candidate (statistics)
-GSC_DEV int pair_decide(uint32_t p, uint32_t q, const float4 *__restrict__ sv, int fuse_ss, uint2 *item, bool *was_ss)
+__device__ __noinline__ int pair_decide(uint32_t p, uint32_t q, const float4 *__restrict__ sv, int fuse_ss, uint2 *item, bool *was_ss)
 {
     const float4 a0 = __ldg(sv + 2 * (size_t)p), a1 = __ldg(sv + 2 * (size_t)p + 1);
     const float4 c0 = __ldg(sv + 2 * (size_t)q), c1 = __ldg(sv + 2 * (size_t)q + 1);
@@ -102,7 +102,7 @@ GSC_DEV int pair_decide(uint32_t p, uint32_t q, const float4 *__restrict__ sv, i
 }
 
 // slow path of a full CTA list: decide and append one pair straight to the global lists
-__device__ __noinline__ void pair_spill(uint32_t p, uint32_t q, const float4 *__restrict__ sv, PairOut out, FrameBlock *fb)
+__device__ __noinline__ void pair_spill(uint32_t p, uint32_t q, const float4 *__restrict__ sv, const PairOut &out, FrameBlock *fb)
 {
     uint2 item;
     bool was_ss;
@@ -129,7 +129,7 @@ struct TailShared {
 
 // `fetch(i)` yields the i-th listed pair as (p, q) sorted positions.  All threads of the CTA call.
 template <int THREADS, class Fetch>
-GSC_DEV void pairs_tail(uint32_t have, Fetch fetch, const float4 *__restrict__ sv, PairOut out, FrameBlock *__restrict__ fb,
+GSC_DEV void pairs_tail(uint32_t have, Fetch fetch, const float4 *__restrict__ sv, const PairOut &out, FrameBlock *__restrict__ fb,
                         TailShared<THREADS / 32> &ts)
 {
     constexpr int WARPS = THREADS / 32;
@@ -496,7 +496,7 @@ k_pairs_tiled(uint32_t n_cap, const uint32_t *__restrict__ keys_a, const uint32_
 #define GSC_PAIR_THREADS 64
 #endif
 #ifndef GSC_PAIR_MIN_CTAS
-#define GSC_PAIR_MIN_CTAS 16  // (round 1 ran 20 x 64 threads at 48 registers; the persistent loop needs a few more)
+#define GSC_PAIR_MIN_CTAS 20
 #endif
 #ifndef GSC_PAIR_PRIV
 #define GSC_PAIR_PRIV 12  // 8 / 12 / 16 / 24 measured: 0.942 / 0.903 / 0.913 / 0.936 ms at 16M
@@ -517,7 +517,7 @@ struct PairShared {
 
 // a lane whose private slots are (nearly) full moves them to the CTA list (rare: >= kPairPriv - 1 survivors)
 __device__ __noinline__ void pair_drain_lane(PairShared &sh, uint32_t p, uint32_t cnt, int tid, const float4 *__restrict__ sv,
-                                             PairOut out, FrameBlock *fb)
+                                             const PairOut &out, FrameBlock *fb)
 {
     const uint32_t at = atomicAdd(&sh.count, cnt);
     for (uint32_t j = 0; j < cnt; ++j) {
@@ -527,11 +527,12 @@ __device__ __noinline__ void pair_drain_lane(PairShared &sh, uint32_t p, uint32_
     }
 }
 
-// all_tiles != 0: every tile of the sorted array (the round-1 form of the stage; A/B runs and tests);
-// otherwise only the tiles queued in out.overflow_tiles
-__global__ void __launch_bounds__(kPairThreads, GSC_PAIR_MIN_CTAS)
+// QUEUE == false: one CTA per kPairThreads volumes over the whole sorted array (the round-1 form of the stage);
+// QUEUE == true: persistent CTAs over the tiles queued in out.overflow_tiles by k_pairs_tiled
+template <bool QUEUE>
+__global__ void __launch_bounds__(kPairThreads, QUEUE ? 16 : GSC_PAIR_MIN_CTAS)
 k_pairs(uint32_t n_cap, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ keys_b, SortedVolumes sv,
-        const uint32_t *__restrict__ cell_start, PairOut out, FrameBlock *__restrict__ fb, int all_tiles)
+        const uint32_t *__restrict__ cell_start, PairOut out, FrameBlock *__restrict__ fb)
 {
     __shared__ PairShared sh;
     const GridParams g = fb->grid;
@@ -540,10 +541,11 @@ k_pairs(uint32_t n_cap, const uint32_t *__restrict__ keys_a, const uint32_t *__r
     const uint32_t *keys = (fb->sort.num_passes & 1) ? keys_b : keys_a;
     const int tid = threadIdx.x, lane = tid & 31;
     constexpr uint32_t kSlices = kTileA / kPairThreads;  // slices of kPairThreads volumes per tile
-    const uint32_t n_tiles = all_tiles ? (n_total + kTileA - 1) / kTileA : fb->n_overflow;
-    for (uint32_t e = blockIdx.x; e < n_tiles * kSlices; e += gridDim.x) {
-        const uint32_t tile = all_tiles ? e / kSlices : out.overflow_tiles[e / kSlices];
-        const uint32_t p = tile * (uint32_t)kTileA + (e % kSlices) * kPairThreads + tid;
+    const uint32_t n_slices = QUEUE ? fb->n_overflow * kSlices : gridDim.x;
+    for (uint32_t e = blockIdx.x; e < n_slices; e += gridDim.x) {
+        const uint32_t p = QUEUE ? out.overflow_tiles[e / kSlices] * (uint32_t)kTileA + (e % kSlices) * kPairThreads + tid
+                                 : e * (uint32_t)kPairThreads + tid;
+        if (!QUEUE && e * (uint32_t)kPairThreads >= n_total) return;
         if (tid == 0) sh.count = 0;
         __syncthreads();
 
@@ -639,6 +641,7 @@ k_pairs(uint32_t n_cap, const uint32_t *__restrict__ keys_a, const uint32_t *__r
         }
         __syncthreads();
         pairs_tail<kPairThreads>(min(sh.count, (uint32_t)kPairCap), [&](uint32_t i) { return sh.list[i]; }, sv.v, out, fb, sh.tail);
+        if (!QUEUE) return;
         __syncthreads();
     }
 }

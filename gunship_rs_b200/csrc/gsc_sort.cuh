@@ -76,11 +76,16 @@ __device__ __forceinline__ void hist_add(uint16_t *h, uint32_t d) { atomicAdd(re
 
 __global__ void __launch_bounds__(kSortThreads)
 k_radix_upsweep(const uint32_t *__restrict__ keys_in, uint32_t n, int pass, const SortControl *__restrict__ ctl,
-                uint32_t *__restrict__ tile_hist, uint32_t num_tiles)
+                uint32_t *__restrict__ tile_hist, uint32_t num_tiles, const uint32_t *__restrict__ n_dev)
 {
     constexpr int WARPS = kSortThreads / 32;
     __shared__ __align__(16) uint16_t s_hist[WARPS][kRadix];  // a warp counts at most 512 items: u16 is plenty
     if (pass >= ctl->num_passes) return;
+    if (n_dev) {  // launched for a capacity: the real count lives on the device (multi-GPU steps: local + ghosts)
+        n = min(n, *n_dev);
+        num_tiles = (n + kSortTile - 1) / kSortTile;
+        if (blockIdx.x >= num_tiles) return;
+    }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int shift = pass * ctl->digit_bits;
     const uint32_t mask = (1u << ctl->digit_bits) - 1u;
@@ -118,12 +123,13 @@ constexpr int kScanChunk = 4096;  // tiles per round (16 KB of shared memory)
 
 __global__ void __launch_bounds__(256)
 k_radix_scan(uint32_t *__restrict__ tile_hist, uint32_t num_tiles, int pass, const SortControl *__restrict__ ctl,
-             uint32_t *__restrict__ digit_total)
+             uint32_t *__restrict__ digit_total, const uint32_t *__restrict__ n_dev)
 {
     constexpr int PER = kScanChunk / 256;                 // entries per thread
     __shared__ uint32_t s_row[kScanChunk + kScanChunk / PER];  // padded: entry i lives at i + i / PER (no bank conflicts)
     __shared__ uint32_t s_warp[8];
     if (pass >= ctl->num_passes) return;
+    if (n_dev) num_tiles = min(num_tiles, (*n_dev + kSortTile - 1) / kSortTile);
     if (blockIdx.x >= (1u << ctl->digit_bits)) {  // digits this sort does not use
         if (threadIdx.x == 0) digit_total[blockIdx.x] = 0;
         return;
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(kSortThreads, 4)
 k_radix_downsweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                   uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n, int pass,
                   const SortControl *__restrict__ ctl, const uint32_t *__restrict__ tile_hist,
-                  const uint32_t *__restrict__ digit_total, uint32_t num_tiles)
+                  const uint32_t *__restrict__ digit_total, uint32_t num_tiles, const uint32_t *__restrict__ n_dev)
 {
     constexpr int WARPS = kSortThreads / 32;
     constexpr int WTILE = 32 * kSortIpt;
@@ -180,6 +186,11 @@ k_radix_downsweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
     __shared__ uint32_t s_warp[8];
 
     if (pass >= ctl->num_passes) return;
+    if (n_dev) {
+        n = min(n, *n_dev);
+        num_tiles = (n + kSortTile - 1) / kSortTile;
+        if (blockIdx.x >= num_tiles) return;
+    }
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int shift = pass * ctl->digit_bits;

@@ -31,8 +31,9 @@ from . import _native as N
 RECORD_BYTES = N.GSC_HALO_RECORD_BYTES
 
 
-def partition_x_slabs(x: np.ndarray, world: int) -> np.ndarray:
-    """Count-balanced x-slabs: owner rank of every collider from the quantiles of its x position.
+def partition_x_slabs(x: np.ndarray, world: int, weight: np.ndarray | None = None) -> np.ndarray:
+    """x-slabs: owner rank of every collider from the quantiles of its x position -- count-balanced, or balanced
+    by `weight` (an estimate of every collider's cost, see pair_work_estimate) when given.
 
     Returns int32[N].  Ties at a cut go to the lower rank.  (The cut need not fall on a cell boundary:
     ownership only decides who reports a pair, the ghost range is derived from the home cells.)"""
@@ -41,10 +42,27 @@ def partition_x_slabs(x: np.ndarray, world: int) -> np.ndarray:
         return np.zeros(n, dtype=np.int32)
     order = np.argsort(x, kind="stable")
     owner = np.empty(n, dtype=np.int32)
-    bounds = [(n * r) // world for r in range(world + 1)]
+    if weight is None:
+        bounds = [(n * r) // world for r in range(world + 1)]
+    else:
+        cum = np.cumsum(weight[order], dtype=np.float64)
+        bounds = [0] + [int(np.searchsorted(cum, cum[-1] * r / world, side="left")) for r in range(1, world)] + [n]
     for r in range(world):
         owner[order[bounds[r]:bounds[r + 1]]] = r
     return owner
+
+
+def pair_work_estimate(pos: np.ndarray, cell: float) -> np.ndarray:
+    """Relative cost of every collider in a step: the per-collider stages (bvh_update, keys, sort, table) cost about as
+    much as 26 quantised AABB tests, and a collider in a cell with c occupants meets ~9 c candidates in its half shell
+    (13 neighbour cells + its own, after the reach pruning).  Slabs cut by this weight even out the pairs stage on
+    clustered scenes, where count-balanced slabs leave the ranks that hold a blob 30% longer in k_pairs."""
+    c = np.floor(pos.astype(np.float64) / float(cell)).astype(np.int64)
+    c -= c.min(axis=0)
+    dims = c.max(axis=0) + 1
+    key = (c[:, 0] * dims[1] + c[:, 1]) * dims[2] + c[:, 2]
+    _, inv, cnt = np.unique(key, return_inverse=True, return_counts=True)
+    return 26.0 + 9.0 * cnt[inv].astype(np.float64)
 
 
 def needed_range(x_min: int, x_max: int):
@@ -79,20 +97,36 @@ class ShmControl:
         if rank == 0:
             os.unlink(box[0])  # stays alive while mapped; nothing is left behind
 
+    TIMEOUT_S = float(os.environ.get("GSC_CONTROL_TIMEOUT_S", "60"))
+
     def all_gather(self, values):
+        """(x86 only: the sequence number is published after the payload and relies on the store order of the
+        platform; the default exchange -- GSC_EXCHANGE=device -- does not use this class at all)"""
         self.seq += 1
         bank = self.mem[self.seq & 1]
         n = len(values)
         if n:
             bank[self.rank, 1:1 + n] = values
-        bank[self.rank, 0] = self.seq          # publish after the payload (x86 store order)
-        seqs = bank[:, 0]
-        while (seqs < self.seq).any():
-            pass
+        bank[self.rank, 0] = self.seq          # publish after the payload
+        seqs = self.mem[:, :, 0]
+        deadline = time.monotonic() + self.TIMEOUT_S
+        spins = 0
+        while (seqs[self.seq & 1] < self.seq).any():
+            if (seqs < 0).any():               # a peer left its step with an error: fail together instead of spinning
+                raise RuntimeError("slab control: a peer rank aborted its step")
+            spins += 1
+            if spins & 0xFFF == 0 and time.monotonic() > deadline:
+                self.abort()
+                raise TimeoutError(f"slab control: a peer rank did not arrive within {self.TIMEOUT_S:.0f} s")
         return np.array(bank[:, 1:1 + n])
 
     def barrier(self):
         self.all_gather(())
+
+    def abort(self):
+        """Poison both banks: every rank spinning in (or entering) a gather raises instead of waiting forever."""
+        self.mem[0, self.rank, 0] = -1.0
+        self.mem[1, self.rank, 0] = -1.0
 
 
 class SlabDriver:
@@ -119,6 +153,7 @@ class SlabDriver:
         self.last_halo_out = 0
         self.push = False
         self.shm = None
+        self.device_exchange = False
         self.trace = {} if os.environ.get("GSC_SLAB_TRACE") else None  # host seconds per phase, summed over steps
 
     def enable_peer_push(self):
@@ -135,7 +170,17 @@ class SlabDriver:
             if s_ != self.rank:
                 be.ipc_open_peer(s_, bytes(b.cpu().numpy().tobytes()))
         self.push = True
-        if os.environ.get("GSC_CONTROL", "shm") == "shm":
+        # default: the whole exchange runs on the device (bounds, halo and flags through peer memory, ONE host wait per
+        # step, gsc_slab_step); GSC_EXCHANGE=host keeps the round-1 host-driven sequence (three syncs + two rendezvous)
+        # Ranks that share a GPU must NOT wait for each other inside kernels (nothing guarantees that the kernels of two
+        # processes on one GPU run at the same time): they keep the host-driven sequence.
+        devs = [None] * self.world
+        dist.all_gather_object(devs, getattr(be, "device_id", lambda: self.rank)(), group=self.group)
+        distinct = len(set(devs)) == self.world
+        if os.environ.get("GSC_EXCHANGE", "device") == "device" and hasattr(be, "slab_init") and distinct:
+            be.slab_init(self.rank, self.world)
+            self.device_exchange = True
+        elif os.environ.get("GSC_CONTROL", "shm") == "shm":
             self.shm = ShmControl(dist, self.group, self.rank, self.world)  # same box: host control plane
 
     def _t(self, name, t0):
@@ -151,6 +196,27 @@ class SlabDriver:
         dist, be = self.dist, self.backend
         dev = be.tensor_device
         t0 = time.perf_counter()
+        if self.device_exchange:
+            be.slab_step_begin()                 # bvh_update, exchange and stages 1-5: all enqueued, no host wait
+            t0 = self._t("enqueue", t0)
+            if after_bounds is not None:
+                after_bounds()                   # (the copy is ordered behind bvh_update of the step in flight)
+                t0 = self._t("after_bounds", t0)
+            out = be.step_end()
+            self._t("wait", t0)
+            self.last_halo_in = int(out.n_ghost)
+            return out
+        try:
+            return self._step_host(after_bounds, t0)
+        except Exception:
+            if self.shm is not None:
+                self.shm.abort()                 # the other ranks must not wait for this one
+            raise
+
+    def _step_host(self, after_bounds, t0):
+        import torch
+        dist, be = self.dist, self.backend
+        dev = be.tensor_device
         longest, wmin, wmax, status, home_x_max, n_local = be.phase_bounds()
         t0 = self._t("phase_bounds", t0)
         if after_bounds is not None:
@@ -342,6 +408,23 @@ class GpuSlabBackend:
     def phase_finish(self):
         return self.ctx.phase_finish()
 
+    # device-driven exchange
+    def device_id(self):
+        """identifies the physical GPU of this rank (ranks that share one keep the host-driven exchange)"""
+        try:
+            return str(self.torch.cuda.get_device_properties(self.cuda).uuid)
+        except Exception:
+            return f"{os.uname().nodename}:{self.cuda.index}"
+
+    def slab_init(self, rank, world):
+        self.ctx.slab_init(rank, world)
+
+    def slab_step_begin(self):
+        self.ctx.slab_step_begin()
+
+    def step_end(self):
+        return self.ctx.step_end()
+
 
 # ------------------------------------------------------------------------------------------------------
 # bench.py --gpus N  (launched under torchrun, one rank per GPU)
@@ -358,7 +441,9 @@ def bench_multi_gpu(args, n, rank, world, local_rank, metric, unit, workload_nam
     dev = torch.device("cuda", local_rank)
     scene = scenes.by_config(args.config, n)
     n = scene.n
-    owner = partition_x_slabs(scene.pos[:, 0], world)
+    balance = os.environ.get("GSC_SLAB_BALANCE", "work")
+    weight = pair_work_estimate(scene.pos, scene.cell_hint) if balance == "work" and world > 1 else None
+    owner = partition_x_slabs(scene.pos[:, 0], world, weight)
     mine = np.nonzero(owner == rank)[0]
     n_local = int(mine.shape[0])
     nframes = max(1, args.frames)
@@ -470,6 +555,14 @@ def bench_multi_gpu(args, n, rank, world, local_rank, metric, unit, workload_nam
                   np.mean([o.n_cells for o in outs]), float(driver.last_halo_in), float(n_local),
                   np.mean([o.n_pairs for o in outs_e2e]) * 8.0, float(n_box)])
     passes = int(outs[-1].sort_passes)
+    # a fingerprint of frame 0's pair set over ALL ranks (count, order-independent checksum mod 2^64): it must equal the
+    # 1-GPU line's config.frame0_pair_set -- the union of the ranks' lists is the single-GPU set
+    step_resident(0)
+    pk = ctx.pairs_packed(sorted=False)
+    fp = torch.tensor([int(pk.shape[0]), int(np.sum(pk, dtype=np.uint64).astype(np.int64))], dtype=torch.int64, device=dev)
+    dist.all_reduce(fp, op=dist.ReduceOp.SUM)
+    fp = fp.cpu().numpy()
+    fingerprint = {"pairs": int(fp[0]), "checksum": f"{int(fp[1].astype(np.uint64)):016x}"}
     if rank == 0:
         peak, peak_kind = measured_peak_gbs()
         n_tot = sums[6] + sums[5]  # volumes processed including ghosts
@@ -483,17 +576,19 @@ def bench_multi_gpu(args, n, rank, world, local_rank, metric, unit, workload_nam
             "ms_per_step": 1e3 * span / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.config, n), "frames_cycled": nframes,
-                       "partition": f"{world} count-balanced x-slabs, one-cell halo (+x direction), " +
-                                    ("pushed into peer HBM over NVLink (CUDA IPC), NCCL for the bounds all-gather and the barrier"
+                       "partition": f"{world} {'work' if weight is not None else 'count'}-balanced x-slabs, one-cell halo (+x direction), " +
+                                    (("pushed into peer HBM over NVLink (CUDA IPC); bounds, flags and ghost counts also travel through "
+                                      "peer memory, one host wait per step" if driver.device_exchange else
+                                      "pushed into peer HBM over NVLink (CUDA IPC); host-driven control (shared-memory file)")
                                      if driver.push else "NCCL send/recv"),
                        "l2": "inputs larger than L2 (no flush needed)" if n_local * 100 > 126e6 else "per-rank inputs near L2 size",
                        "box_fraction": round(f_box, 3), "contact_pairs_per_step": int(sums[0]),
-                       "halo_colliders_per_step": int(sums[5])},
+                       "halo_colliders_per_step": int(sums[5]), "frame0_pair_set": fingerprint},
             "e2e": {"value": n * args.steps / span_e2e, "unit": unit, "ms_per_step": 1e3 * span_e2e / args.steps,
                     "h2d_bytes_per_step": int(n * 12 + sums[8] * 16), "d2h_bytes_per_step": int(sums[7]),
                     "mode": "pipelined host loop: every rank hands frame f+1 over right after bvh_update of step f",
                     "sync_value": n * args.steps / span_sync, "sync_ms_per_step": 1e3 * span_sync / args.steps},
-            "gpu_launches": (13 + 4) * args.steps * world,
+            "gpu_launches": (23 if driver.device_exchange else 13 + 4 + 4) * args.steps * world,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,

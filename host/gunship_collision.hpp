@@ -302,19 +302,28 @@ public:
         // bvh_update meets entities it has not seen yet and pushes their volumes (bounding_volume.rs:394-407)
         push_assigned(ctx, cm);
         // bvh_update reads every collider's transform (bounding_volume.rs:358-362); a missing one is an unwrap() panic
+        // The ONE pass over the frame's transforms goes straight into the library's pinned staging bank (positions in
+        // dense order; rotation / scale packed over the boxes -- spheres ignore them, mod.rs:313-317): no pageable
+        // intermediate vectors, no second (staged) copy inside the driver.
         const size_t n = cm.entities_.size();
-        pos_.resize(3 * n); quat_.resize(4 * n); scale_.resize(3 * n);
+        float *pos = nullptr, *quat = nullptr, *scale = nullptr;
+        detail::check(ctx, gsc_map_transform_staging(ctx, bank_, &pos, &quat, &scale));
+        size_t k = 0;  // box slot
         for (size_t i = 0; i < n; ++i) {
             const Transform *t = tm.get(cm.entities_[i]);
             if (!t) throw Panic("called `Option::unwrap()` on a `None` value: entity " + std::to_string(cm.entities_[i]) + " has a collider but no transform");
             const Point p = t->position_derived();
-            const Quaternion q = t->rotation_derived();
-            const Vector3 s = t->scale_derived();
-            pos_[3 * i] = p.x; pos_[3 * i + 1] = p.y; pos_[3 * i + 2] = p.z;
-            quat_[4 * i] = q.x; quat_[4 * i + 1] = q.y; quat_[4 * i + 2] = q.z; quat_[4 * i + 3] = q.w;
-            scale_[3 * i] = s.x; scale_[3 * i + 1] = s.y; scale_[3 * i + 2] = s.z;
+            pos[3 * i] = p.x; pos[3 * i + 1] = p.y; pos[3 * i + 2] = p.z;
+            if (cm.colliders_[i].kind == Collider::kBox) {
+                const Quaternion q = t->rotation_derived();
+                const Vector3 s = t->scale_derived();
+                quat[4 * k] = q.x; quat[4 * k + 1] = q.y; quat[4 * k + 2] = q.z; quat[4 * k + 3] = q.w;
+                scale[3 * k] = s.x; scale[3 * k + 1] = s.y; scale[3 * k + 2] = s.z;
+                ++k;
+            }
         }
-        detail::check(ctx, gsc_update_transforms(ctx, (uint32_t)n, pos_.data(), quat_.data(), scale_.data()));
+        detail::check(ctx, gsc_commit_transform_staging(ctx, bank_, (uint32_t)n, (uint32_t)k, 1, 1));
+        bank_ ^= 1u;
         grid_system.update();  // :596-599
 
         // callback_manager.process_collisions(scene, &self.grid_system.collisions) (:601): the per-entity lists
@@ -359,7 +368,7 @@ private:
             detail::check(ctx, gsc_append_colliders(ctx, (uint32_t)(hi - lo), cm.entities_.data() + lo, kind.data(), off.data(), size.data()));
         cm.on_device_ = hi;
     }
-    std::vector<float> pos_, quat_, scale_;
+    uint32_t bank_ = 0;  // pinned staging bank of the next frame (two alternate)
     std::vector<uint32_t> adj_entity_, adj_offset_, adj_other_;
 };
 

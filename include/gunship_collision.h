@@ -29,14 +29,15 @@
 extern "C" {
 #endif
 
-#define GSC_ABI_VERSION 1
+#define GSC_ABI_VERSION 2
 
 /* status codes */
 enum {
     GSC_OK           = 0,
     GSC_ERR_INVALID  = 1, /* bad argument / call order */
     GSC_ERR_CUDA     = 2, /* CUDA runtime failure (message in gsc_last_error) */
-    GSC_ERR_NCCL     = 3, /* reserved: collective failure in the multi-GPU host layer */
+    GSC_ERR_NCCL     = 3, /* multi-GPU exchange failure: a peer GPU did not arrive within the time limit
+                             (gsc_slab_step / gsc_group_step; GSC_PEER_TIMEOUT_MS, default 5000) */
     GSC_ERR_CAPACITY = 4, /* pair / candidate / cell-table capacity exceeded; needed sizes are in gsc_step_out */
     GSC_ERR_RANGE    = 5, /* a grid coordinate leaves i16 (grid_collision.rs:530-535), cell size is not
                              positive, or an input is NaN/Inf -- the reference's behaviour is undefined there */
@@ -49,7 +50,8 @@ enum { GSC_SPHERE = 0, GSC_BOX = 1, GSC_MESH = 2 };
 /* gsc_config.flags */
 enum {
     GSC_FLAG_TIMING = 1u << 0, /* record per-stage CUDA-event times in gsc_step_out.stage_ms */
-    GSC_FLAG_GRAPH  = 1u << 1, /* reserved */
+    GSC_FLAG_GRAPH  = 1u << 1, /* replay stages 1-5 of gsc_step from a captured CUDA graph (one graph launch instead of ~18
+                                  kernel launches; matters for small scenes, where the step is launch bound) */
     GSC_FLAG_CONTACTS = 1u << 2 /* also produce a contact (unit normal, depth) per pair -- see gsc_download_contacts */
 };
 
@@ -92,6 +94,8 @@ typedef struct gsc_step_out {
     float    step_ms;        /* device time of the whole step (always) */
     const uint32_t *d_pairs; /* DEVICE pointer: n_pairs x (entity of higher index, entity of lower index) */
     const float *d_contacts; /* DEVICE pointer: n_pairs x (normal.xyz, depth), same order; NULL without GSC_FLAG_CONTACTS */
+    uint32_t n_ghost;        /* ghost colliders other slabs pushed into this context this step (gsc_slab_step) */
+    uint32_t reserved;
 } gsc_step_out;
 
 /* ---- lifetime ---- */
@@ -120,6 +124,18 @@ int gsc_update_transforms(gsc_ctx *ctx, uint32_t n, const float *pos3, const flo
  * instead of 40 B per collider.  box_quat4 / box_scale3 may be NULL to keep the previous packed values. */
 int gsc_update_transforms_packed(gsc_ctx *ctx, uint32_t n, const float *pos3, uint32_t n_box, const float *box_quat4,
                                  const float *box_scale3);
+
+/* ---- pinned transform staging: the host layer marshals the frame's derived transforms straight into library-owned
+ *      PINNED buffers (bounding_volume.rs:358-362 reads every collider's transform once per frame; a host that fills
+ *      pageable vectors instead pays a second, staged copy inside the driver).  Two banks alternate, so frame f+1 can be
+ *      written while frame f's copy is still in flight.  pos3[3 * max_colliders] is in dense collider order;
+ *      box_quat4 / box_scale3 are packed over the boxes (entry k = the k-th collider of kind GSC_BOX), exactly the
+ *      arrays of gsc_update_transforms_packed.  gsc_commit_transform_staging hands bank `bank` over (asynchronous,
+ *      same ordering rules as gsc_update_transforms_packed); with_rotation / with_scale == 0 keep the previous values. */
+int gsc_map_transform_staging(gsc_ctx *ctx, uint32_t bank, float **pos3, float **box_quat4, float **box_scale3);
+int gsc_commit_transform_staging(gsc_ctx *ctx, uint32_t bank, uint32_t n, uint32_t n_box, int with_rotation, int with_scale);
+/* box_slot[i] = number of boxes before collider i (where collider i's rotation / scale go in the packed arrays) */
+int gsc_box_slots(gsc_ctx *ctx, uint32_t *box_slot, uint32_t cap, uint32_t *n_box);
 
 /* same, from DEVICE memory that the caller keeps alive until the next bind (no copy is made) */
 int gsc_bind_device_transforms(gsc_ctx *ctx, uint32_t n, const float *d_pos3, const float *d_quat4, const float *d_scale3);
@@ -308,6 +324,44 @@ int gsc_halo_commit(gsc_ctx *ctx, uint32_t *n_ghost);
 
 /* stages 1..5 on local + ghost colliders */
 int gsc_phase_finish(gsc_ctx *ctx, gsc_step_out *out);
+
+/* -- the same exchange driven from the DEVICE (round 2): no host round trip inside a step --
+ * After the one-time peer setup (gsc_ipc_open_peer for ranks in other processes, gsc_open_peer_local for contexts of
+ * this process) and gsc_slab_init, ONE call enqueues the whole multi-GPU step on the rank's own stream:
+ *   bvh_update -> k_slab_publish (my bounds into every rank's mailbox, in peer memory) -> k_slab_gather (wait for all
+ *   bounds; global cell size / world box; every rank's home x-range; what each peer needs of mine; my windowed grid)
+ *   -> k_slab_push (select + write my boundary volumes into the peers' arrays) -> k_slab_done (flag) -> k_slab_wait
+ *   (wait for the peers' flags, adopt the ghosts) -> stages 1..5 over local + ghost volumes
+ * and the host waits once, at the end.  Every rank of the group must call it once per step (they step together);
+ * a rank that does not arrive makes the others fail with GSC_ERR_NCCL after the time limit instead of hanging.
+ * Ranks must run on DIFFERENT GPUs unless their steps are ordered by stream events (gsc_group_step does that):
+ * two kernels of one GPU that wait for each other are not guaranteed to run at the same time. */
+int gsc_open_peer_local(gsc_ctx *ctx, uint32_t peer, gsc_ctx *other);
+int gsc_slab_init(gsc_ctx *ctx, uint32_t rank, uint32_t world);
+int gsc_slab_step(gsc_ctx *ctx, gsc_step_out *out);
+/* in two halves, as gsc_step_begin / gsc_step_end: finish with gsc_step_end */
+int gsc_slab_step_begin(gsc_ctx *ctx);
+
+/* ---- a whole box behind ONE handle: one process, one context per GPU (what a Rust / C++ engine links against) ----
+ * The group owns the x-slab partition.  Colliders are registered and transforms handed over in the engine's dense
+ * order; the group scatters them to the slabs (pinned staging per member), steps all members with the device-driven
+ * exchange above (ordered by stream events, so members may even share a GPU) and returns the union of the members'
+ * pair lists, which IS the single-GPU pair set (no cross-rank dedupe).  gsc_group_rebalance re-cuts the slabs from
+ * the last frame's positions and the per-slab work of the last step (colliders + candidate pairs; migrants change owner; SURVEY 8e collectives 2 and 3). */
+typedef struct gsc_group gsc_group;
+int  gsc_group_create(uint32_t n_devices, const int32_t *devices, const gsc_config *cfg, gsc_group **out);
+void gsc_group_destroy(gsc_group *group);
+const char *gsc_group_last_error(const gsc_group *group);
+/* pos3: positions used to cut the slabs (normally the first frame's); cfg.max_colliders is the capacity PER MEMBER */
+int gsc_group_upload_colliders(gsc_group *group, uint32_t n, const uint32_t *entity, const uint8_t *kind,
+                               const float *offset3, const float *size3, const float *pos3);
+int gsc_group_update_transforms(gsc_group *group, uint32_t n, const float *pos3, const float *quat4, const float *scale3);
+/* total: sums over the members (stage_ms / step_ms: max over members; d_pairs / d_contacts NULL) */
+int gsc_group_step(gsc_group *group, gsc_step_out *total);
+int gsc_group_download_pairs(gsc_group *group, uint32_t *dst, uint64_t cap_pairs, int sorted, uint64_t *n_out);
+int gsc_group_rebalance(gsc_group *group);
+/* inspection: member i's context, its collider count and the global indices it owns (owned[n_local], may be NULL) */
+int gsc_group_member(gsc_group *group, uint32_t i, gsc_ctx **ctx, uint32_t *n_local, uint32_t *owned);
 
 #ifdef __cplusplus
 }

@@ -1,4 +1,4 @@
-//! `extern "C"` declarations -- one to one with include/gunship_collision.h (GSC_ABI_VERSION 1).
+//! `extern "C"` declarations -- one to one with include/gunship_collision.h (GSC_ABI_VERSION 2).
 #![allow(non_camel_case_types, dead_code)]
 use std::os::raw::{c_char, c_int, c_void};
 
@@ -7,7 +7,9 @@ pub const GSC_ERR_CAPACITY: c_int = 4;
 pub const GSC_SPHERE: u8 = 0;
 pub const GSC_BOX: u8 = 1;
 pub const GSC_MESH: u8 = 2;
+pub const GSC_ERR_NCCL: c_int = 3;
 pub const GSC_FLAG_TIMING: u32 = 1;
+pub const GSC_FLAG_GRAPH: u32 = 2;
 pub const GSC_FLAG_CONTACTS: u32 = 4;
 pub const GSC_MAX_PEERS: usize = 16;
 pub const GSC_IPC_EXPORT_BYTES: usize = 256;
@@ -15,6 +17,7 @@ pub const GSC_NUM_STAGES: usize = 6;
 pub const GSC_HALO_RECORD_BYTES: usize = 96;
 
 pub enum gsc_ctx {}
+pub enum gsc_group {}
 
 #[repr(C)]
 pub struct gsc_config {
@@ -44,6 +47,8 @@ pub struct gsc_step_out {
     pub step_ms: f32,
     pub d_pairs: *const u32,
     pub d_contacts: *const f32,
+    pub n_ghost: u32,
+    pub reserved: u32,
 }
 
 #[repr(C)]
@@ -118,4 +123,27 @@ extern "C" {
     pub fn gsc_halo_sync(ctx: *mut gsc_ctx) -> c_int;
     pub fn gsc_halo_commit(ctx: *mut gsc_ctx, n_ghost: *mut u32) -> c_int;
     pub fn gsc_phase_finish(ctx: *mut gsc_ctx, out: *mut gsc_step_out) -> c_int;
+    // device-driven slab exchange
+    pub fn gsc_open_peer_local(ctx: *mut gsc_ctx, peer: u32, other: *mut gsc_ctx) -> c_int;
+    pub fn gsc_slab_init(ctx: *mut gsc_ctx, rank: u32, world: u32) -> c_int;
+    pub fn gsc_slab_step(ctx: *mut gsc_ctx, out: *mut gsc_step_out) -> c_int;
+    pub fn gsc_slab_step_begin(ctx: *mut gsc_ctx) -> c_int;
+    // one handle for all GPUs of a box
+    pub fn gsc_group_create(n_devices: u32, devices: *const i32, cfg: *const gsc_config, out: *mut *mut gsc_group) -> c_int;
+    pub fn gsc_group_destroy(group: *mut gsc_group);
+    pub fn gsc_group_last_error(group: *const gsc_group) -> *const c_char;
+    pub fn gsc_group_upload_colliders(group: *mut gsc_group, n: u32, entity: *const u32, kind: *const u8, offset3: *const f32,
+                                      size3: *const f32, pos3: *const f32) -> c_int;
+    pub fn gsc_group_update_transforms(group: *mut gsc_group, n: u32, pos3: *const f32, quat4: *const f32,
+                                       scale3: *const f32) -> c_int;
+    pub fn gsc_group_step(group: *mut gsc_group, total: *mut gsc_step_out) -> c_int;
+    pub fn gsc_group_download_pairs(group: *mut gsc_group, dst: *mut u32, cap_pairs: u64, sorted: c_int, n_out: *mut u64) -> c_int;
+    pub fn gsc_group_rebalance(group: *mut gsc_group) -> c_int;
+    pub fn gsc_group_member(group: *mut gsc_group, i: u32, ctx: *mut *mut gsc_ctx, n_local: *mut u32, owned: *mut u32) -> c_int;
+    // pinned transform staging
+    pub fn gsc_map_transform_staging(ctx: *mut gsc_ctx, bank: u32, pos3: *mut *mut f32, box_quat4: *mut *mut f32,
+                                     box_scale3: *mut *mut f32) -> c_int;
+    pub fn gsc_commit_transform_staging(ctx: *mut gsc_ctx, bank: u32, n: u32, n_box: u32, with_rotation: c_int,
+                                        with_scale: c_int) -> c_int;
+    pub fn gsc_box_slots(ctx: *mut gsc_ctx, box_slot: *mut u32, cap: u32, n_box: *mut u32) -> c_int;
 }

@@ -42,9 +42,12 @@ pub struct DerivedTransform {
 pub struct GridCollisionSystem<S: std::hash::BuildHasher + Default = BuildHasherDefault<std::collections::hash_map::DefaultHasher>> {
     ctx: *mut ffi::gsc_ctx,
     n: u32,
-    pos: Vec<f32>,
-    quat: Vec<f32>,
-    scale: Vec<f32>,
+    /// `box_slot[i]` = number of boxes before collider i: where its rotation / scale go in the packed staging arrays
+    box_slot: Vec<u32>,
+    is_box: Vec<bool>,
+    n_box: u32,
+    /// pinned staging bank the next frame is marshalled into (two banks alternate, include/gunship_collision.h)
+    bank: u32,
     pairs: Vec<u32>,
     /// Same name, type shape and tuple order as grid_collision.rs:119: (later volume, earlier volume).
     pub collisions: PairSet<S>,
@@ -66,7 +69,7 @@ impl<S: std::hash::BuildHasher + Default> GridCollisionSystem<S> {
         let mut ctx = ptr::null_mut();
         let rc = unsafe { ffi::gsc_create(&cfg, &mut ctx) };
         check(ptr::null(), rc);
-        GridCollisionSystem { ctx, n: 0, pos: vec![], quat: vec![], scale: vec![], pairs: vec![],
+        GridCollisionSystem { ctx, n: 0, box_slot: vec![], is_box: vec![], n_box: 0, bank: 0, pairs: vec![],
                               collisions: HashSet::with_hasher(S::default()), cell_size: 0.0 }
     }
 
@@ -86,21 +89,50 @@ impl<S: std::hash::BuildHasher + Default> GridCollisionSystem<S> {
         let rc = unsafe { ffi::gsc_upload_colliders(self.ctx, n as u32, entities.as_ptr(), kind.as_ptr(), off.as_ptr(), size.as_ptr(), ptr::null()) };
         check(self.ctx, rc);
         self.n = n as u32;
+        self.refresh_box_slots();
+    }
+
+    /// after the collider set changed: where every box finds its rotation / scale in the packed staging arrays
+    fn refresh_box_slots(&mut self) {
+        self.box_slot.resize(self.n as usize, 0);
+        let mut n_box = 0u32;
+        let rc = unsafe { ffi::gsc_box_slots(self.ctx, self.box_slot.as_mut_ptr(), self.n, &mut n_box) };
+        check(self.ctx, rc);
+        self.n_box = n_box;
+        self.is_box.clear();
+        for i in 0..self.n as usize {
+            let next = if i + 1 < self.n as usize { self.box_slot[i + 1] } else { n_box };
+            self.is_box.push(next > self.box_slot[i]);
+        }
+    }
+
+    /// The one pass over the frame's transforms `bvh_update` makes (bounding_volume.rs:358-362), writing straight
+    /// into the library's PINNED staging bank -- positions in dense order, rotation / scale packed over the boxes
+    /// (spheres ignore them, mod.rs:313-317) -- then the bank is handed over (asynchronous copy).
+    fn marshal(&mut self, transforms: &[DerivedTransform]) {
+        assert_eq!(transforms.len(), self.n as usize);
+        let (mut pos, mut quat, mut scale) = (ptr::null_mut::<f32>(), ptr::null_mut::<f32>(), ptr::null_mut::<f32>());
+        unsafe {
+            check(self.ctx, ffi::gsc_map_transform_staging(self.ctx, self.bank, &mut pos, &mut quat, &mut scale));
+            for (i, t) in transforms.iter().enumerate() {
+                ptr::copy_nonoverlapping(t.position.as_ptr(), pos.add(3 * i), 3);
+                if self.is_box[i] {
+                    let k = self.box_slot[i] as usize;
+                    ptr::copy_nonoverlapping(t.rotation.as_ptr(), quat.add(4 * k), 4);
+                    ptr::copy_nonoverlapping(t.scale.as_ptr(), scale.add(3 * k), 3);
+                }
+            }
+            check(self.ctx, ffi::gsc_commit_transform_staging(self.ctx, self.bank, self.n, self.n_box, 1, 1));
+        }
+        self.bank ^= 1;
     }
 
     /// `bvh_update` + `GridCollisionSystem::update(&mut self, &BoundingVolumeManager)` (grid_collision.rs:218):
     /// fills `self.collisions`.  `transforms[i]` belongs to `entities[i]` of `set_colliders`.
     pub fn update(&mut self, transforms: &[DerivedTransform]) {
-        assert_eq!(transforms.len(), self.n as usize);
-        self.pos.clear(); self.quat.clear(); self.scale.clear();
-        for t in transforms {
-            self.pos.extend_from_slice(&t.position);
-            self.quat.extend_from_slice(&t.rotation);
-            self.scale.extend_from_slice(&t.scale);
-        }
+        self.marshal(transforms);
         let mut out: ffi::gsc_step_out = unsafe { std::mem::zeroed() };
         unsafe {
-            check(self.ctx, ffi::gsc_update_transforms(self.ctx, self.n, self.pos.as_ptr(), self.quat.as_ptr(), self.scale.as_ptr()));
             check(self.ctx, ffi::gsc_step(self.ctx, &mut out));
         }
         self.cell_size = out.cell_size;
@@ -122,6 +154,7 @@ impl<S: std::hash::BuildHasher + Default> GridCollisionSystem<S> {
         let rc = unsafe { ffi::gsc_append_colliders(self.ctx, entities.len() as u32, entities.as_ptr(), kind.as_ptr(), offset3.as_ptr(), size3.as_ptr()) };
         check(self.ctx, rc);
         self.n += entities.len() as u32;
+        self.refresh_box_slots();
     }
 
     /// The cleanup loop of `CollisionSystem::update` (mod.rs:605-609): one `destroy_immediate` (swap_remove,
@@ -131,20 +164,14 @@ impl<S: std::hash::BuildHasher + Default> GridCollisionSystem<S> {
         let rc = unsafe { ffi::gsc_remove_colliders(self.ctx, indices.len() as u32, indices.as_ptr()) };
         check(self.ctx, rc);
         self.n -= indices.len() as u32;
+        self.refresh_box_slots();
     }
 
     /// Pipelined form of `update` for a main loop that can hand over the NEXT frame's transforms while this
     /// frame's step runs: `begin_update(frame f)`, ..., `begin_update(frame f+1)` is legal before `end_update()`
     /// only through `stage_transforms`, which the C side orders behind `bvh_update` of the step in flight.
     pub fn stage_transforms(&mut self, transforms: &[DerivedTransform]) {
-        assert_eq!(transforms.len(), self.n as usize);
-        self.pos.clear(); self.quat.clear(); self.scale.clear();
-        for t in transforms {
-            self.pos.extend_from_slice(&t.position);
-            self.quat.extend_from_slice(&t.rotation);
-            self.scale.extend_from_slice(&t.scale);
-        }
-        unsafe { check(self.ctx, ffi::gsc_update_transforms(self.ctx, self.n, self.pos.as_ptr(), self.quat.as_ptr(), self.scale.as_ptr())); }
+        self.marshal(transforms);
     }
     pub fn begin_update(&mut self) {
         unsafe { check(self.ctx, ffi::gsc_step_begin(self.ctx)); }

@@ -28,7 +28,7 @@ def test_library_exports_every_header_symbol():
     lib = C.CDLL(N.LIB_PATH)
     for name in _header_functions():
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
-    assert N.load().gsc_abi_version() == 1
+    assert N.load().gsc_abi_version() == 2
 
 
 def test_struct_layouts_match_header(tmp_path):
