@@ -73,7 +73,7 @@ EXPORTS = (
     "gsc_hierarchy_download", "gsc_open_peer_local", "gsc_slab_init", "gsc_slab_step", "gsc_slab_step_begin",
     "gsc_group_create", "gsc_group_destroy", "gsc_group_last_error", "gsc_group_upload_colliders",
     "gsc_group_update_transforms", "gsc_group_step", "gsc_group_download_pairs", "gsc_group_rebalance", "gsc_group_member",
-    "gsc_map_transform_staging", "gsc_commit_transform_staging", "gsc_box_slots",
+    "gsc_map_transform_staging", "gsc_commit_transform_staging", "gsc_box_slots", "gsc_reorder_colliders",
 )
 
 _lib = None
@@ -152,6 +152,7 @@ def load():
     L.gsc_map_transform_staging.argtypes = [vp, C.c_uint32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.gsc_commit_transform_staging.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int]
     L.gsc_box_slots.argtypes = [vp, u32p, C.c_uint32, C.POINTER(C.c_uint32)]
+    L.gsc_reorder_colliders.argtypes = [vp, u32p, C.c_uint32]
     for name in EXPORTS:
         fn = getattr(L, name)  # raises AttributeError if the .so does not export it
         if name not in ("gsc_destroy", "gsc_last_error", "gsc_group_destroy", "gsc_group_last_error"):

@@ -289,6 +289,13 @@ class CollisionContext:
     def commit_transform_staging(self, bank: int, n_box: int, with_rotation: bool = True, with_scale: bool = True):
         self._check(self._lib.gsc_commit_transform_staging(self._h, bank, self.n, n_box, int(with_rotation), int(with_scale)))
 
+    def reorder_colliders(self) -> np.ndarray:
+        """Permute the dense arrays into the cell order of the last step (gsc_reorder_colliders); returns order[slot] =
+        previous dense index: hand over transforms[order] from now on."""
+        order = np.zeros(max(self.n, 1), dtype=np.uint32)
+        self._check(self._lib.gsc_reorder_colliders(self._h, _ptr(order), order.shape[0]))
+        return order[: self.n]
+
     def box_slots(self) -> np.ndarray:
         out = np.zeros(max(self.n, 1), dtype=np.uint32)
         nb = C.c_uint32(0)

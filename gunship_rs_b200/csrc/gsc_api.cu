@@ -60,6 +60,7 @@ struct gsc_ctx {
     // hold another set's values, packed or in pre-swap_remove order), so "NULL keeps the previous values" is refused
     // until rotation and scale were sent again (a set without boxes never needs them)
     bool rot_scale_valid = false;
+    bool sorted_valid = false;  // d_vals of the last step is the cell order of the CURRENT local collider set (gsc_reorder_colliders)
     // pinned transform staging (gsc_map_transform_staging), allocated on first use
     float *h_stage[2][3] = { { nullptr, nullptr, nullptr }, { nullptr, nullptr, nullptr } };
     // GSC_FLAG_GRAPH: stages 1-5 captured once per launch geometry
@@ -85,7 +86,7 @@ struct gsc_ctx {
     uint32_t *d_cell_start = nullptr, *d_wide = nullptr;
     uint32_t *d_overflow = nullptr;  // tiles of the pairs stage that did not fit its staging buffers
     bool pairs_tiled = false;        // GSC_PAIRS_TILED=1: the tile-staged, work-flattened pairs kernel (measured slower, see DESIGN)
-    bool fuse_ss = true;             // GSC_FUSE_SS=0: sphere-sphere candidates go through the SAT stage's queue as in round 1
+    bool fuse_ss = false;            // GSC_FUSE_SS=1 (with GSC_PAIRS_TILED=1): sphere-sphere pairs decided in the pairs tail (measured slower)
     uint4 *d_gaps = nullptr;
     bool have_window = false;
     int32_t win_lo = 0, win_hi = 0;
@@ -331,7 +332,7 @@ int gsc_create(const gsc_config *cfg, gsc_ctx **out)
         const char *e = getenv("GSC_PAIRS_TILED");
         c->pairs_tiled = e && e[0] == '1';
         e = getenv("GSC_FUSE_SS");
-        c->fuse_ss = !(e && e[0] == '0');
+        c->fuse_ss = c->pairs_tiled && e && e[0] == '1';
     }
     CR(dmalloc(&c->d_gaps, (size_t)kGapCap));
     CR(dmalloc(&c->d_pairs, c->max_pairs));
@@ -432,6 +433,7 @@ int gsc_upload_colliders(gsc_ctx *c, uint32_t n, const uint32_t *entity, const u
     c->have_colliders = true;
     c->have_transforms = false;
     c->rot_scale_valid = false;
+    c->sorted_valid = false;
     c->packed = false;
     c->chunked = false;
     c->hier_colliders = 0;
@@ -474,6 +476,7 @@ int gsc_append_colliders(gsc_ctx *c, uint32_t n_new, const uint32_t *entity, con
     if (int rc = rebuild_box_slots(c)) return rc;
     c->have_transforms = false;
     c->rot_scale_valid = false;
+    c->sorted_valid = false;
     c->packed = false;
     c->chunked = false;
     c->hier_colliders = 0;
@@ -526,6 +529,7 @@ int gsc_remove_colliders(gsc_ctx *c, uint32_t n_remove, const uint32_t *index)
     if (int rc = rebuild_box_slots(c)) return rc;
     c->have_transforms = false;
     c->rot_scale_valid = false;
+    c->sorted_valid = false;
     c->packed = false;
     c->chunked = false;
     c->hier_colliders = 0;
@@ -706,16 +710,18 @@ static int stage_launches(gsc_ctx *c, bool slab, bool timing)
         k_fill_gaps<<<148 * 2, 256, 0, s>>>(c->d_cell_start, c->d_gaps, fb);
         if (timing) CU(c, cudaEventRecord(c->ev[4], s));
         // sphere-sphere pairs are decided inside the pairs stage unless a contact has to be computed for them
-        PairOut po{ c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands, c->d_pairs, c->max_pairs, c->d_overflow,
-                    (c->d_contacts || !c->fuse_ss) ? 0 : 1 };
+        PairOut po{ c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands };
         if (c->pairs_tiled) {
+            // (experimental, measured slower than k_pairs: DESIGN section 4) sphere-sphere pairs may be decided in its tail
+            PairFuse pf{ c->d_pairs, c->max_pairs };
+            const int fuse = (c->fuse_ss && !c->d_contacts) ? 1 : 0;
             k_pairs_tiled<<<(n_launch + kTileA - 1) / kTileA, kTileA, sizeof(TileShared), s>>>(n_launch, c->d_keys[0], c->d_keys[1], sv,
-                                                                                            c->d_cell_start, po, fb);
+                                                                                            c->d_cell_start, po, pf, fuse, c->d_overflow, fb);
             // tiles too dense for the staging buffers (normally none: the kernel exits at once)
-            k_pairs<true><<<148 * 16, kPairThreads, 0, s>>>(n_launch, c->d_keys[0], c->d_keys[1], sv, c->d_cell_start, po, fb);
+            k_pairs<true><<<148 * 16, kPairThreads, 0, s>>>(n_launch, c->d_keys[0], c->d_keys[1], sv, c->d_cell_start, po, c->d_overflow, fb);
         } else {
             k_pairs<false><<<(n_launch + kPairThreads - 1) / kPairThreads, kPairThreads, 0, s>>>(n_launch, c->d_keys[0], c->d_keys[1], sv,
-                                                                                              c->d_cell_start, po, fb);
+                                                                                              c->d_cell_start, po, nullptr, fb);
         }
         if (timing) CU(c, cudaEventRecord(c->ev[5], s));
         if (c->d_contacts)
@@ -781,10 +787,11 @@ static int stage_collect(gsc_ctx *c, gsc_step_out *out)
     const FrameBlock &h = *c->h_fb;
     c->last_pairs = std::min<uint64_t>(h.n_pairs, c->max_pairs);
     if (c->slab_step) c->n_ghost = h.slab.n_ghost;
+    c->sorted_valid = h.status == 0 && h.grid.valid && !c->slab_step && c->n_ghost == 0;
     if (out) {
         memset(out, 0, sizeof *out);
         out->n_pairs = h.n_pairs;
-        out->n_sphere_sphere = (c->d_contacts || !c->fuse_ss) ? h.n_ss : h.n_ss_fused;
+        out->n_sphere_sphere = (c->d_contacts || !c->fuse_ss) ? h.n_ss : h.n_ss_fused;  // (fuse_ss implies pairs_tiled)
         out->n_sphere_obb = h.n_so;
         out->n_obb_obb = h.n_oo;
         out->n_cells = h.grid.num_cells;
@@ -1459,6 +1466,68 @@ int gsc_download_adjacency(gsc_ctx *c, uint32_t *entity, uint32_t *offset, uint3
     CU(c, cudaMemcpy(entity, a.d_entity, a.n_entities * 4, cudaMemcpyDeviceToHost));
     CU(c, cudaMemcpy(offset, a.d_offset, (a.n_entities + 1) * 4, cudaMemcpyDeviceToHost));
     CU(c, cudaMemcpy(other, a.d_other, a.n_entries * 4, cudaMemcpyDeviceToHost));
+    return GSC_OK;
+}
+
+// ---- temporal coherence: keep the colliders in the cell order of the last step ----------------------
+}  // extern "C"
+namespace {
+__global__ void k_reorder_static(uint32_t n, const uint32_t *__restrict__ order, const uint8_t *__restrict__ kind,
+                                 const float *__restrict__ offset3, const float *__restrict__ size3, const uint32_t *__restrict__ entity,
+                                 const uint32_t *__restrict__ gidx, uint8_t *__restrict__ kind_o, float *__restrict__ offset_o,
+                                 float *__restrict__ size_o, uint32_t *__restrict__ entity_o, uint32_t *__restrict__ gidx_o)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t i = order[s];
+    kind_o[s] = kind[i];
+    for (int a = 0; a < 3; ++a) { offset_o[3 * (size_t)s + a] = offset3[3 * (size_t)i + a]; size_o[3 * (size_t)s + a] = size3[3 * (size_t)i + a]; }
+    entity_o[s] = entity[i];
+    gidx_o[s] = gidx ? gidx[i] : i;  // the position in the reference's dense array keeps orienting every tuple
+}
+}  // namespace
+extern "C" {
+
+int gsc_reorder_colliders(gsc_ctx *c, uint32_t *order, uint32_t cap)
+{
+    if (int rc = check_ctx(c)) return rc;
+    NOT_IN_FLIGHT(c, "gsc_reorder_colliders");
+    if (!c->sorted_valid) return fail(c, GSC_ERR_INVALID, "gsc_reorder_colliders: needs a completed single-context step on the current collider set");
+    const uint32_t n = c->n_local;
+    if (!order || cap < n) return fail(c, GSC_ERR_CAPACITY, "gsc_reorder_colliders: need room for %u entries", n);
+    if (n == 0) return GSC_OK;
+    cudaStream_t s = c->stream;
+    const uint32_t *vals = c->d_vals[c->h_fb->sort.num_passes & 1];
+    Scratch tmp[2];
+    uint8_t *kind_o = nullptr;
+    float *off_o = nullptr, *size_o = nullptr;
+    uint32_t *ent_o = nullptr, *gidx_o = nullptr;
+    CU(c, cudaMalloc(&tmp[0].p[0], n)); kind_o = (uint8_t *)tmp[0].p[0];
+    CU(c, cudaMalloc(&tmp[0].p[1], (size_t)n * 12)); off_o = (float *)tmp[0].p[1];
+    CU(c, cudaMalloc(&tmp[0].p[2], (size_t)n * 12)); size_o = (float *)tmp[0].p[2];
+    CU(c, cudaMalloc(&tmp[0].p[3], (size_t)n * 4)); ent_o = (uint32_t *)tmp[0].p[3];
+    CU(c, cudaMalloc(&tmp[1].p[0], (size_t)n * 4)); gidx_o = (uint32_t *)tmp[1].p[0];
+    k_reorder_static<<<(n + 255) / 256, 256, 0, s>>>(n, vals, c->d_kind, c->d_offset, c->d_size, c->d_entity, c->have_gidx ? c->d_gidx : nullptr,
+                                                   kind_o, off_o, size_o, ent_o, gidx_o);
+    CU(c, cudaGetLastError());
+    CU(c, cudaMemcpyAsync(order, vals, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    CU(c, cudaMemcpyAsync(c->d_kind, kind_o, n, cudaMemcpyDeviceToDevice, s));
+    CU(c, cudaMemcpyAsync(c->d_offset, off_o, (size_t)n * 12, cudaMemcpyDeviceToDevice, s));
+    CU(c, cudaMemcpyAsync(c->d_size, size_o, (size_t)n * 12, cudaMemcpyDeviceToDevice, s));
+    CU(c, cudaMemcpyAsync(c->d_entity, ent_o, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    CU(c, cudaMemcpyAsync(c->d_gidx, gidx_o, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    CU(c, cudaStreamSynchronize(s));
+    std::vector<uint8_t> hk(n);
+    for (uint32_t k = 0; k < n; ++k) hk[k] = c->h_kind[order[k]];
+    c->h_kind.swap(hk);
+    c->have_gidx = true;
+    if (int rc = rebuild_box_slots(c)) return rc;
+    c->have_transforms = false;
+    c->rot_scale_valid = false;
+    c->sorted_valid = false;
+    c->packed = false;
+    c->chunked = false;
+    c->hier_colliders = 0;
     return GSC_OK;
 }
 

@@ -33,14 +33,15 @@
 namespace gsc {
 
 struct PairOut {
-    uint2 *cand_ss;   // sphere-sphere candidates (only when they are not decided here: GSC_FLAG_CONTACTS)
+    uint2 *cand_ss;   // sphere-sphere candidates
     uint2 *cand_so;
     uint2 *cand_oo;
     unsigned long long cap_cands;
-    uint2 *pairs;     // contact pairs (sphere-sphere hits are appended here when fuse_ss)
+};
+// k_pairs_tiled only: sphere-sphere pairs decided in the tail (GSC_FUSE_SS=1) are appended to the contact pairs directly
+struct PairFuse {
+    uint2 *pairs;
     unsigned long long cap_pairs;
-    uint32_t *overflow_tiles;  // tiles k_pairs_tiled hands to k_pairs
-    int fuse_ss;
 };
 
 // AABB of a cell-ordered record.  sphere: centre -+ (r,r,r) exactly as AABB::from_collider computes it
@@ -77,7 +78,8 @@ GSC_DEV int pair_classify(uint32_t a_pos, uint32_t a_gidx, uint32_t a_meta, uint
 // exact test + classification of one filtered (A at sorted position p, B at q) pair.
 //   returns 0 sphere-sphere HIT when fuse_ss (item = entities), else sphere-sphere candidate; 1; 2; 3 = nothing to emit.
 //   *was_ss: the pair was an AABB-overlapping sphere-sphere candidate (statistics)
-__device__ __noinline__ int pair_decide(uint32_t p, uint32_t q, const float4 *__restrict__ sv, int fuse_ss, uint2 *item, bool *was_ss)
+template <bool FUSE>
+GSC_DEV int pair_decide(uint32_t p, uint32_t q, const float4 *__restrict__ sv, uint2 *item, bool *was_ss)
 {
     const float4 a0 = __ldg(sv + 2 * (size_t)p), a1 = __ldg(sv + 2 * (size_t)p + 1);
     const float4 c0 = __ldg(sv + 2 * (size_t)q), c1 = __ldg(sv + 2 * (size_t)q + 1);
@@ -91,7 +93,7 @@ __device__ __noinline__ int pair_decide(uint32_t p, uint32_t q, const float4 *__
     const int cls = pair_classify(p, ag, __float_as_uint(a1.w), q, cg, __float_as_uint(c1.w), item);
     if (cls == 0) {
         *was_ss = true;
-        if (fuse_ss) {
+        if (FUSE) {
             const bool a_hi = ag > cg;
             const float4 h = a_hi ? a0 : c0, l = a_hi ? c0 : a0;
             if (!test_sphere_sphere(h.x, h.y, h.z, h.w, l.x, l.y, l.z, l.w)) return 3;
@@ -102,16 +104,17 @@ __device__ __noinline__ int pair_decide(uint32_t p, uint32_t q, const float4 *__
 }
 
 // slow path of a full CTA list: decide and append one pair straight to the global lists
-__device__ __noinline__ void pair_spill(uint32_t p, uint32_t q, const float4 *__restrict__ sv, const PairOut &out, FrameBlock *fb)
+template <bool FUSE>
+__device__ __noinline__ void pair_spill(uint32_t p, uint32_t q, const float4 *__restrict__ sv, PairOut out, PairFuse fuse, FrameBlock *fb)
 {
     uint2 item;
     bool was_ss;
-    const int cls = pair_decide(p, q, sv, out.fuse_ss, &item, &was_ss);
-    if (was_ss && out.fuse_ss) atomicAdd(&fb->n_ss_fused, 1ull);
+    const int cls = pair_decide<FUSE>(p, q, sv, &item, &was_ss);
+    if (FUSE && was_ss) atomicAdd(&fb->n_ss_fused, 1ull);
     if (cls == 3) return;
-    if (cls == 0 && out.fuse_ss) {
+    if (FUSE && cls == 0) {
         const unsigned long long at = atomicAdd(&fb->n_pairs, 1ull);
-        if (at < out.cap_pairs) out.pairs[at] = item;
+        if (at < fuse.cap_pairs) fuse.pairs[at] = item;
         return;
     }
     unsigned long long *ctr = cls == 0 ? &fb->n_ss : (cls == 1 ? &fb->n_so : &fb->n_oo);
@@ -128,9 +131,9 @@ struct TailShared {
 };
 
 // `fetch(i)` yields the i-th listed pair as (p, q) sorted positions.  All threads of the CTA call.
-template <int THREADS, class Fetch>
-GSC_DEV void pairs_tail(uint32_t have, Fetch fetch, const float4 *__restrict__ sv, const PairOut &out, FrameBlock *__restrict__ fb,
-                        TailShared<THREADS / 32> &ts)
+template <int THREADS, bool FUSE, class Fetch>
+GSC_DEV void pairs_tail(uint32_t have, Fetch fetch, const float4 *__restrict__ sv, const PairOut &out, const PairFuse &fuse,
+                        FrameBlock *__restrict__ fb, TailShared<THREADS / 32> &ts)
 {
     constexpr int WARPS = THREADS / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -141,7 +144,7 @@ GSC_DEV void pairs_tail(uint32_t have, Fetch fetch, const float4 *__restrict__ s
         uint2 item = make_uint2(0, 0);
         if (i < have) {
             const uint2 e = fetch(i);
-            cls = pair_decide(e.x, e.y, sv, out.fuse_ss, &item, &was_ss);
+            cls = pair_decide<FUSE>(e.x, e.y, sv, &item, &was_ss);
         }
         uint32_t m[4], rank = 0;
 #pragma unroll
@@ -149,10 +152,10 @@ GSC_DEV void pairs_tail(uint32_t have, Fetch fetch, const float4 *__restrict__ s
             m[c] = __ballot_sync(0xffffffffu, cls == c);
             if (cls == c) rank = __popc(m[c] & ((1u << lane) - 1u));
         }
-        m[3] = __ballot_sync(0xffffffffu, was_ss);
-        if (lane < 4) ts.warp_cls[warp][lane] = __popc(m[lane]);
+        if (FUSE) m[3] = __ballot_sync(0xffffffffu, was_ss);
+        if (lane < (FUSE ? 4 : 3)) ts.warp_cls[warp][lane] = __popc(m[lane]);
         __syncthreads();
-        if (tid < 4) {
+        if (tid < (FUSE ? 4 : 3)) {
             uint32_t tot = 0;
             for (int w = 0; w < WARPS; ++w) {
                 const uint32_t c = ts.warp_cls[w][tid];
@@ -160,18 +163,18 @@ GSC_DEV void pairs_tail(uint32_t have, Fetch fetch, const float4 *__restrict__ s
                 tot += c;
             }
             if (tid == 3) {
-                if (tot && out.fuse_ss) atomicAdd(&fb->n_ss_fused, (unsigned long long)tot);
+                if (tot) atomicAdd(&fb->n_ss_fused, (unsigned long long)tot);
             } else {
-                unsigned long long *ctr = tid == 0 ? (out.fuse_ss ? &fb->n_pairs : &fb->n_ss) : (tid == 1 ? &fb->n_so : &fb->n_oo);
+                unsigned long long *ctr = tid == 0 ? (FUSE ? &fb->n_pairs : &fb->n_ss) : (tid == 1 ? &fb->n_so : &fb->n_oo);
                 ts.base[tid] = tot ? atomicAdd(ctr, (unsigned long long)tot) : 0ull;
             }
         }
         __syncthreads();
         if (cls < 3) {
-            const bool to_pairs = cls == 0 && out.fuse_ss;
-            uint2 *dst = cls == 0 ? (out.fuse_ss ? out.pairs : out.cand_ss) : (cls == 1 ? out.cand_so : out.cand_oo);
+            const bool to_pairs = cls == 0 && FUSE;
+            uint2 *dst = cls == 0 ? (FUSE ? fuse.pairs : out.cand_ss) : (cls == 1 ? out.cand_so : out.cand_oo);
             const unsigned long long at = ts.base[cls] + ts.warp_cls[warp][cls] + rank;
-            if (at < (to_pairs ? out.cap_pairs : out.cap_cands)) dst[at] = item;
+            if (at < (to_pairs ? fuse.cap_pairs : out.cap_cands)) dst[at] = item;
         }
         __syncthreads();
     }
@@ -262,7 +265,8 @@ GSC_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory
 
 __global__ void __launch_bounds__(kTileA, GSC_TILE_CTAS)
 k_pairs_tiled(uint32_t n_cap, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ keys_b,
-              SortedVolumes sv, const uint32_t *__restrict__ cell_start, PairOut out, FrameBlock *__restrict__ fb)
+              SortedVolumes sv, const uint32_t *__restrict__ cell_start, PairOut out, PairFuse fuse, int fuse_ss,
+              uint32_t *__restrict__ overflow_tiles, FrameBlock *__restrict__ fb)
 {
     extern __shared__ __align__(16) unsigned char tile_smem[];
     TileShared &sh = *reinterpret_cast<TileShared *>(tile_smem);
@@ -363,7 +367,7 @@ k_pairs_tiled(uint32_t n_cap, const uint32_t *__restrict__ keys_a, const uint32_
         overflow = (total >> 20) > (uint32_t)kTileRuns;
     }
     if (overflow) {
-        if (tid == 0) out.overflow_tiles[atomicAdd(&fb->n_overflow, 1u)] = blockIdx.x;
+        if (tid == 0) overflow_tiles[atomicAdd(&fb->n_overflow, 1u)] = blockIdx.x;
         return;
     }
     const uint32_t R = total >> 20, W = total & 0xfffffu;
@@ -446,7 +450,8 @@ k_pairs_tiled(uint32_t n_cap, const uint32_t *__restrict__ keys_a, const uint32_
                 for (uint32_t j = 0; j < have; ++j) {
                     const uint32_t w = sh.priv[j * kTileA + tid];
                     if (at + j < (uint32_t)kTileList) sh.list[at + j] = w;
-                    else pair_spill(p0 + (w >> 16), global_pos(w & 0xffffu), sv.v, out, fb);
+                    else if (fuse_ss) pair_spill<true>(p0 + (w >> 16), global_pos(w & 0xffffu), sv.v, out, fuse, fb);
+                    else pair_spill<false>(p0 + (w >> 16), global_pos(w & 0xffffu), sv.v, out, fuse, fb);
                 }
                 pa = pa0;
             }
@@ -469,20 +474,20 @@ k_pairs_tiled(uint32_t n_cap, const uint32_t *__restrict__ keys_a, const uint32_
         for (uint32_t j = 0; j < have; ++j) {
             const uint32_t w = sh.priv[j * kTileA + tid];
             if (at + j < (uint32_t)kTileList) sh.list[at + j] = w;
-            else pair_spill(p0 + (w >> 16), global_pos(w & 0xffffu), sv.v, out, fb);
+            else if (fuse_ss) pair_spill<true>(p0 + (w >> 16), global_pos(w & 0xffffu), sv.v, out, fuse, fb);
+            else pair_spill<false>(p0 + (w >> 16), global_pos(w & 0xffffu), sv.v, out, fuse, fb);
         }
     }
     __syncthreads();
 
     // ---- decide + append the tile's survivors ----
     const uint32_t listed = min(sh.count, (uint32_t)kTileList);
-    pairs_tail<kTileA>(
-        listed,
-        [&](uint32_t i) {
-            const uint32_t w = sh.list[i];
-            return make_uint2(p0 + (w >> 16), global_pos(w & 0xffffu));
-        },
-        sv.v, out, fb, sh.tail);
+    auto fetch = [&](uint32_t i) {
+        const uint32_t w = sh.list[i];
+        return make_uint2(p0 + (w >> 16), global_pos(w & 0xffffu));
+    };
+    if (fuse_ss) pairs_tail<kTileA, true>(listed, fetch, sv.v, out, fuse, fb, sh.tail);
+    else pairs_tail<kTileA, false>(listed, fetch, sv.v, out, fuse, fb, sh.tail);
 }
 
 // =================================================================================================================
@@ -517,13 +522,13 @@ struct PairShared {
 
 // a lane whose private slots are (nearly) full moves them to the CTA list (rare: >= kPairPriv - 1 survivors)
 __device__ __noinline__ void pair_drain_lane(PairShared &sh, uint32_t p, uint32_t cnt, int tid, const float4 *__restrict__ sv,
-                                             const PairOut &out, FrameBlock *fb)
+                                             PairOut out, FrameBlock *fb)
 {
     const uint32_t at = atomicAdd(&sh.count, cnt);
     for (uint32_t j = 0; j < cnt; ++j) {
         const uint32_t q = sh.priv[j * kPairThreads + tid];
         if (at + j < (uint32_t)kPairCap) sh.list[at + j] = make_uint2(p, q);
-        else pair_spill(p, q, sv, out, fb);
+        else pair_spill<false>(p, q, sv, out, PairFuse{ nullptr, 0 }, fb);
     }
 }
 
@@ -532,7 +537,7 @@ __device__ __noinline__ void pair_drain_lane(PairShared &sh, uint32_t p, uint32_
 template <bool QUEUE>
 __global__ void __launch_bounds__(kPairThreads, QUEUE ? 16 : GSC_PAIR_MIN_CTAS)
 k_pairs(uint32_t n_cap, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ keys_b, SortedVolumes sv,
-        const uint32_t *__restrict__ cell_start, PairOut out, FrameBlock *__restrict__ fb)
+        const uint32_t *__restrict__ cell_start, PairOut out, const uint32_t *__restrict__ overflow_tiles, FrameBlock *__restrict__ fb)
 {
     __shared__ PairShared sh;
     const GridParams g = fb->grid;
@@ -543,7 +548,7 @@ k_pairs(uint32_t n_cap, const uint32_t *__restrict__ keys_a, const uint32_t *__r
     constexpr uint32_t kSlices = kTileA / kPairThreads;  // slices of kPairThreads volumes per tile
     const uint32_t n_slices = QUEUE ? fb->n_overflow * kSlices : gridDim.x;
     for (uint32_t e = blockIdx.x; e < n_slices; e += gridDim.x) {
-        const uint32_t p = QUEUE ? out.overflow_tiles[e / kSlices] * (uint32_t)kTileA + (e % kSlices) * kPairThreads + tid
+        const uint32_t p = QUEUE ? overflow_tiles[e / kSlices] * (uint32_t)kTileA + (e % kSlices) * kPairThreads + tid
                                  : e * (uint32_t)kPairThreads + tid;
         if (!QUEUE && e * (uint32_t)kPairThreads >= n_total) return;
         if (tid == 0) sh.count = 0;
@@ -636,11 +641,14 @@ k_pairs(uint32_t n_cap, const uint32_t *__restrict__ keys_a, const uint32_t *__r
             for (uint32_t j = 0; j < cnt; ++j) {
                 const uint32_t q = sh.priv[j * kPairThreads + tid];
                 if (at + j < (uint32_t)kPairCap) sh.list[at + j] = make_uint2(p, q);
-                else pair_spill(p, q, sv.v, out, fb);
+                else pair_spill<false>(p, q, sv.v, out, PairFuse{ nullptr, 0 }, fb);
             }
         }
         __syncthreads();
-        pairs_tail<kPairThreads>(min(sh.count, (uint32_t)kPairCap), [&](uint32_t i) { return sh.list[i]; }, sv.v, out, fb, sh.tail);
+        // (sphere-sphere pairs stay with the SAT stage here: deciding them in this tail was measured 0.13 ms slower at 16M
+        // for 0.01 ms saved in k_narrow)
+        pairs_tail<kPairThreads, false>(min(sh.count, (uint32_t)kPairCap), [&](uint32_t i) { return sh.list[i]; }, sv.v, out,
+                                        PairFuse{ nullptr, 0 }, fb, sh.tail);
         if (!QUEUE) return;
         __syncthreads();
     }

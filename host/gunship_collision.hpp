@@ -289,6 +289,69 @@ private:
     std::vector<uint32_t> pairs_;
 };
 
+// ---- the same GridCollisionSystem over ALL GPUs of a box (gsc_group_*): x-slab partition, one context per device ----
+// The reference's own decomposition is 8 octant work units on 8 threads merged into one set (grid_collision.rs:60-86,
+// 161-193, 262-272); here the units are slabs on GPUs and `collisions` is the union of their lists.  Dense-array
+// interface: colliders and derived transforms in BoundingVolumeManager.components order.
+class GroupGridCollisionSystem {
+public:
+    GridCollisionSystem::CollisionSet collisions;
+    float cell_size = 0;
+    uint32_t ghosts = 0;  // halo colliders exchanged in the last update
+
+    GroupGridCollisionSystem(const std::vector<int32_t> &devices, uint32_t max_colliders_per_device, uint32_t flags = 0)
+    {
+        gsc_config cfg{};
+        cfg.max_colliders = max_colliders_per_device;
+        cfg.flags = flags;
+        const int rc = gsc_group_create((uint32_t)devices.size(), devices.data(), &cfg, &group_);
+        if (rc != GSC_OK) throw Panic(std::string("gsc_group_create: ") + gsc_last_error(nullptr));
+    }
+    ~GroupGridCollisionSystem() { gsc_group_destroy(group_); }
+    GroupGridCollisionSystem(const GroupGridCollisionSystem &) = delete;
+    GroupGridCollisionSystem &operator=(const GroupGridCollisionSystem &) = delete;
+
+    // the dense collider arrays (ColliderManager order) and the positions the slabs are cut from
+    void set_colliders(const std::vector<Entity> &entities, const std::vector<Collider> &colliders, const std::vector<float> &pos3)
+    {
+        std::vector<uint8_t> kind;
+        std::vector<float> off, size;
+        for (const Collider &c : colliders) {
+            kind.push_back((uint8_t)c.kind);
+            off.insert(off.end(), { c.offset.x, c.offset.y, c.offset.z });
+            if (c.kind == Collider::kSphere) size.insert(size.end(), { c.radius, 0.0f, 0.0f });
+            else size.insert(size.end(), { c.widths.x, c.widths.y, c.widths.z });
+        }
+        n_ = (uint32_t)entities.size();
+        check(gsc_group_upload_colliders(group_, n_, entities.data(), kind.data(), off.data(), size.data(), pos3.data()));
+    }
+    // bvh_update + update over the frame's derived transforms (dense order)
+    void update(const std::vector<float> &pos3, const std::vector<float> &quat4, const std::vector<float> &scale3)
+    {
+        check(gsc_group_update_transforms(group_, n_, pos3.data(), quat4.data(), scale3.data()));
+        gsc_step_out out{};
+        check(gsc_group_step(group_, &out));
+        cell_size = out.cell_size;
+        ghosts = out.n_ghost;
+        pairs_.resize(2 * (size_t)out.n_pairs);
+        uint64_t n = 0;
+        check(gsc_group_download_pairs(group_, pairs_.data(), out.n_pairs, 0, &n));
+        collisions.clear();
+        for (size_t i = 0; i < (size_t)n; ++i) collisions.insert({ pairs_[2 * i], pairs_[2 * i + 1] });
+    }
+    // migrants: re-cut the slabs from the last frame's positions and the last step's work
+    void rebalance() { check(gsc_group_rebalance(group_)); }
+
+private:
+    void check(int rc) const
+    {
+        if (rc != GSC_OK) throw Panic(std::string("gunship_collision group: ") + gsc_group_last_error(group_));
+    }
+    gsc_group *group_ = nullptr;
+    uint32_t n_ = 0;
+    std::vector<uint32_t> pairs_;
+};
+
 // ---- CollisionSystem (mod.rs:577-611) -----------------------------------------------------------------------------
 class CollisionSystem {
 public:

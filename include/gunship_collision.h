@@ -169,6 +169,20 @@ int gsc_remove_colliders(gsc_ctx *ctx, uint32_t n_remove, const uint32_t *index)
 /* colliders currently registered on the device */
 int gsc_collider_count(gsc_ctx *ctx, uint32_t *n_out);
 
+/* ---- temporal coherence (second half) ----
+ * The reference rebuilds its grid from scratch every frame (grid_collision.rs:484-485) and keeps its volumes in
+ * assign order.  Colliders move little from frame to frame, so the CELL ORDER of one frame is a good memory order for
+ * the next ones: gsc_reorder_colliders permutes the context's dense arrays into the cell order of the step that
+ * just completed.  order[slot] receives the collider's previous dense index: from now on the host hands over
+ * transforms in SLOT order (transform of collider order[slot] at position slot -- the reference's bvh_update looks
+ * every transform up by entity anyway, bounding_volume.rs:358-362).  Nothing observable changes: every collider keeps
+ * its global index (its position in the reference's dense array), which is what orients the output tuples and fixes
+ * the OBB-OBB argument order.  Afterwards the cell-order gather of the volume records and the record gathers of the
+ * SAT stage run over nearly sequential memory instead of random indices.  Call it again whenever the scene has
+ * drifted (every few hundred frames).  Like a context with explicit global indices, a reordered context does not
+ * take gsc_append_colliders / gsc_remove_colliders (upload the new set instead). */
+int gsc_reorder_colliders(gsc_ctx *ctx, uint32_t *order, uint32_t cap);
+
 /* ---- the step BEFORE the path: transform derivation ----
  * TransformManager::update_transforms walks the rows of the hierarchy (row = depth; "the transforms in a row can be
  * processed independently so they should be done in parallel", component/transform.rs:243-251) and

@@ -146,4 +146,5 @@ extern "C" {
     pub fn gsc_commit_transform_staging(ctx: *mut gsc_ctx, bank: u32, n: u32, n_box: u32, with_rotation: c_int,
                                         with_scale: c_int) -> c_int;
     pub fn gsc_box_slots(ctx: *mut gsc_ctx, box_slot: *mut u32, cap: u32, n_box: *mut u32) -> c_int;
+    pub fn gsc_reorder_colliders(ctx: *mut gsc_ctx, order: *mut u32, cap: u32) -> c_int;
 }

@@ -35,6 +35,7 @@ def _has_gpu():
 def test_host_mirror_builds_and_panics_without_a_device(tmp_path):
     kat = _build(tmp_path, "collider_kat")
     _build(tmp_path, "scene_runner")
+    _build(tmp_path, "group_runner")
     _build(tmp_path, "grid_collision", ("benches",))  # the C++ counterpart of benches/grid_collision.rs
     if _has_gpu():
         pytest.skip("a CUDA device is present: the GPU tests run the binaries")
@@ -113,3 +114,36 @@ def test_scene_through_the_cpp_host_matches_the_oracle(tmp_path):
         assert np.array_equal(got, want_pairs[fr]), f"frame {fr}"
     got_calls, got_others, got_sum = struct.unpack_from("<3Q", raw, at)
     assert (got_calls, got_others, got_sum) == (calls, others, checksum)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
+def test_group_of_gpus_through_the_cpp_host_matches_the_oracle(tmp_path, world):
+    """gunship::GroupGridCollisionSystem (gsc_group_* behind the compiled host mirror): the union of the slabs' lists is
+    the oracle's set on every frame, also after a re-balance."""
+    import torch
+    n, n_frames = 50000, 4
+    s = scenes.by_config(4, n)
+    frames = [s.frame(f) for f in range(n_frames)]
+    scene_file, out_file = tmp_path / "gscene.bin", tmp_path / "gout.bin"
+    with open(scene_file, "wb") as f:
+        f.write(struct.pack("<2I", n, n_frames))
+        for i in range(n):
+            f.write(struct.pack("<2I6f", int(s.entity[i]), int(s.kind[i]), *s.offset[i], *s.size[i]))
+        for pos, quat in frames:
+            f.write(np.concatenate([pos, quat, s.scale], axis=1).astype("<f4").tobytes())
+    devices = [str(i % torch.cuda.device_count()) for i in range(world)]
+    r = subprocess.run([_build(tmp_path, "group_runner"), str(scene_file), str(out_file)] + devices, capture_output=True, text=True)
+    assert r.returncode == 0 and "group_runner: ok" in r.stdout, r.stdout + r.stderr
+    raw = open(out_file, "rb").read()
+    at = 0
+    oracle = O.OracleSystem()
+    for fr in range(n_frames):
+        np_, ghosts = struct.unpack_from("<2Q", raw, at)
+        at += 16
+        got = np.frombuffer(raw, dtype="<u8", count=np_, offset=at)
+        at += 8 * np_
+        want = oracle.step(s, *frames[fr])
+        assert np.array_equal(got, want), f"frame {fr}"
+        assert 0 < ghosts < n
+    oracle.close()

@@ -161,3 +161,44 @@ def test_null_rotation_is_refused_after_the_collider_set_changed():
         ctx.step()
         assert np.array_equal(ctx.pairs_packed(sorted=True), oracle.step(sub))
     oracle.close()
+
+
+def test_reordered_colliders_give_the_same_pair_sets():
+    """gsc_reorder_colliders (temporal coherence): the dense arrays are permuted into the cell order of the
+    last step and the host hands over transforms in slot order; every collider keeps its global index, so the pair set
+    (orientation included) does not change."""
+    s = scenes.by_config(4, 60000)
+    rng = np.random.default_rng(5)
+    s.entity = (rng.permutation(s.n) + 11).astype(np.uint32)      # ids unrelated to the index order
+    oracle = O.OracleSystem()
+    with G.CollisionContext(s.n) as ctx:
+        ctx.upload_colliders(s.entity, s.kind, s.offset, s.size)
+        pos, quat = s.frame(0)
+        ctx.update_transforms(pos, quat, s.scale)
+        ctx.step()
+        assert np.array_equal(ctx.pairs_packed(sorted=True), oracle.step(s, pos, quat))
+        order = ctx.reorder_colliders()
+        assert np.array_equal(np.sort(order), np.arange(s.n, dtype=np.uint32))
+        assert np.array_equal(ctx.debug(N.GSC_DBG_ENTITY), s.entity[order])
+        with pytest.raises(G.GscError):
+            ctx.step()                                            # transforms must be handed over again, in slot order
+        with pytest.raises(G.GscError):
+            ctx.update_transforms(pos[order])                     # ... with rotation and scale
+        for f in (0, 1, 4):
+            pos, quat = s.frame(f)
+            ctx.update_transforms(pos[order], quat[order], s.scale[order])
+            out = ctx.step()
+            assert np.array_equal(ctx.pairs_packed(sorted=True), oracle.step(s, pos, quat)), f
+            # the colliders now arrive nearly cell-ordered: the sorted index stream is close to the identity
+            idx = ctx.debug(N.GSC_DBG_SORTED_IDX).astype(np.int64)
+            assert np.median(np.abs(idx - np.arange(s.n))) < s.n / 50
+        # a second reorder composes
+        order2 = ctx.reorder_colliders()
+        total = order[order2]
+        pos, quat = s.frame(5)
+        ctx.update_transforms(pos[total], quat[total], s.scale[total])
+        ctx.step()
+        assert np.array_equal(ctx.pairs_packed(sorted=True), oracle.step(s, pos, quat))
+        with pytest.raises(G.GscError):
+            ctx.append_colliders(s.entity[:1], s.kind[:1], s.offset[:1], s.size[:1])
+    oracle.close()
