@@ -186,10 +186,12 @@ def main():
     ap.add_argument("--frames", type=int, default=3, help="distinct jittered frames cycled through")
     ap.add_argument("--cpu-sample-n", type=int, default=0, help="collider count of the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--slot-order", action="store_true",
-                    help="temporal coherence: after one step, keep the colliders in that step's cell order (gsc_reorder_colliders) "
-                         "and hand over transforms in slot order")
+    ap.add_argument("--assign-order", action="store_true",
+                    help="keep the colliders in assign order for the whole run (round-1 behaviour).  Default: after a first "
+                         "measurement in assign order the colliders are kept in that frame's cell order "
+                         "(gsc_reorder_colliders, temporal coherence) and the transforms are handed over in slot order")
     args = ap.parse_args()
+    args.slot_order = not args.assign_order
     guard_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -259,10 +261,22 @@ def main():
         ctx.bind_device_transforms(d_pos[f].data_ptr(), d_quat[f].data_ptr(), d_scale.data_ptr())
         return ctx.step()
 
+    value_assign = None
+    base_frames = [(h_pos[f].numpy().copy(), h_quat[f].numpy().copy()) for f in range(min(2, nframes))] if not args.no_cpu_baseline else []
     if args.slot_order:
-        # one step in assign order, then the dense arrays follow that frame's cell order and the host
-        # marshals every later frame in slot order (bvh_update looks transforms up by entity anyway)
-        step_resident(0)
+        # SURVEY 8f N4 (temporal coherence).  First the same resident loop in ASSIGN order (the reference's dense order,
+        # what round 1 measured) as a reference point; then the dense arrays follow that frame's cell order
+        # (gsc_reorder_colliders) and every later frame is marshalled in slot order -- bvh_update looks transforms up by
+        # entity anyway (bounding_volume.rs:358-362).  Inputs, outputs and the pair set are the same.
+        ctx.set_flags(timing=False, graph=os.environ.get("GSC_BENCH_GRAPH", "1") == "1")
+        for i in range(args.warmup):
+            step_resident(i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            step_resident(args.warmup + i)
+        torch.cuda.synchronize()
+        value_assign = {"value": n * args.steps / (time.perf_counter() - t0), "ms_per_step": 1e3 * (time.perf_counter() - t0) / args.steps}
         order = torch.from_numpy(ctx.reorder_colliders().astype(np.int64))
         box = box[order.numpy()]
         for f in range(nframes):
@@ -276,6 +290,9 @@ def main():
         d_scale = h_scale.cuda()
 
     # ---- value: inputs resident in HBM ----
+    # timed region: stages 1-5 replayed from the captured CUDA graph (GSC_FLAG_GRAPH), no per-stage events
+    use_graph = os.environ.get("GSC_BENCH_GRAPH", "1") == "1"
+    ctx.set_flags(timing=False, graph=use_graph)
     for i in range(args.warmup):
         step_resident(i)
     sampler = ClockSampler(local_rank)
@@ -286,13 +303,21 @@ def main():
     for i in range(args.steps):
         out = step_resident(args.warmup + i)
         dev_ms.append(out.step_ms)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms_per_step = 1e3 * wall / args.steps
+    value = n * args.steps / wall
+    # the same K steps once more with a CUDA event between the stages (plain launches): the per-kernel durations the
+    # roofline figures are computed from
+    ctx.set_flags(timing=True, graph=False)
+    step_resident(0)
+    for i in range(args.steps):
+        out = step_resident(args.warmup + i)
         stage_ms += np.array(list(out.stage_ms))
         outs.append((out.n_pairs, out.n_sphere_obb, out.n_obb_obb, out.n_cells, out.sort_passes, out.n_sphere_sphere))
     torch.cuda.synchronize()
-    wall = time.perf_counter() - t0
     stage_ms /= args.steps
-    ms_per_step = 1e3 * wall / args.steps
-    value = n * args.steps / wall
+    ctx.set_flags(timing=False, graph=use_graph)
 
     # ---- e2e: host transforms in, contact pairs out, through the C ABI ----
     max_pairs = int(max(o[0] for o in outs))
@@ -410,6 +435,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.config, n), "frames_cycled": nframes, "slot_order": bool(args.slot_order),
+                   "graph_replay": use_graph, "assign_order": value_assign,
                    "l2": "inputs larger than L2 (no flush needed)" if n * 100 > 126e6 else "inputs fit in L2",
                    "box_fraction": round(f_box, 3), "contact_pairs_per_step": int(mean[0])},
         "p50_step_ms": float(np.median(dev_ms)), "device_ms_per_step": float(np.mean(dev_ms)),
@@ -422,7 +448,7 @@ def main():
                          "constant in this workload and sent once; sync_* is the same loop with the blocking gsc_step"),
                 "with_host_marshal": {"value": n * m_steps / wall_marshal, "ms_per_step": 1e3 * wall_marshal / m_steps, "steps": m_steps,
                                       "note": "numpy marshal (memcpy + gather, one host thread) of pageable arrays into the pinned bank inside the timed region"}},
-        "gpu_launches": 19 * args.steps,
+        "gpu_launches": 19 * args.steps,  # kernels per step (bvh_update + 18 in stages 1-5, replayed as one graph launch)
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic["bytes"] if traffic else None,
@@ -485,7 +511,7 @@ def main():
         sysm = O.OracleSystem(8, cores)
         ts = []
         for i in range(2):
-            pos, quat = (h_pos[i % nframes].numpy(), h_quat[i % nframes].numpy()) if (n_cpu == n and not args.slot_order) else cs.frame(i)
+            pos, quat = base_frames[i % len(base_frames)] if n_cpu == n else cs.frame(i)
             t0 = time.perf_counter()
             sysm.bvh_update(cs.entity, cs.kind, cs.offset, cs.size, pos, quat, cs.scale)
             sysm.grid_update()

@@ -72,8 +72,8 @@ EXPORTS = (
     "gsc_append_colliders", "gsc_remove_colliders", "gsc_collider_count", "gsc_hierarchy_upload", "gsc_hierarchy_update",
     "gsc_hierarchy_download", "gsc_open_peer_local", "gsc_slab_init", "gsc_slab_step", "gsc_slab_step_begin",
     "gsc_group_create", "gsc_group_destroy", "gsc_group_last_error", "gsc_group_upload_colliders",
-    "gsc_group_update_transforms", "gsc_group_step", "gsc_group_download_pairs", "gsc_group_rebalance", "gsc_group_member",
-    "gsc_map_transform_staging", "gsc_commit_transform_staging", "gsc_box_slots", "gsc_reorder_colliders",
+    "gsc_group_update_transforms", "gsc_group_step", "gsc_group_download_pairs", "gsc_group_rebalance", "gsc_group_reorder", "gsc_group_member",
+    "gsc_map_transform_staging", "gsc_commit_transform_staging", "gsc_box_slots", "gsc_reorder_colliders", "gsc_set_flags",
 )
 
 _lib = None
@@ -148,11 +148,13 @@ def load():
     L.gsc_group_step.argtypes = [vp, C.POINTER(GscStepOut)]
     L.gsc_group_download_pairs.argtypes = [vp, u32p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
     L.gsc_group_rebalance.argtypes = [vp]
+    L.gsc_group_reorder.argtypes = [vp]
     L.gsc_group_member.argtypes = [vp, C.c_uint32, C.POINTER(vp), C.POINTER(C.c_uint32), u32p]
     L.gsc_map_transform_staging.argtypes = [vp, C.c_uint32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.gsc_commit_transform_staging.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int]
     L.gsc_box_slots.argtypes = [vp, u32p, C.c_uint32, C.POINTER(C.c_uint32)]
     L.gsc_reorder_colliders.argtypes = [vp, u32p, C.c_uint32]
+    L.gsc_set_flags.argtypes = [vp, C.c_uint32]
     for name in EXPORTS:
         fn = getattr(L, name)  # raises AttributeError if the .so does not export it
         if name not in ("gsc_destroy", "gsc_last_error", "gsc_group_destroy", "gsc_group_last_error"):

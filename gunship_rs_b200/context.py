@@ -28,6 +28,7 @@ class CollisionContext:
                           (N.GSC_FLAG_TIMING if timing else 0) | (N.GSC_FLAG_CONTACTS if contacts else 0) |
                           (N.GSC_FLAG_GRAPH if graph else 0), 0)
         self.cap = max_colliders
+        self._flags = cfg.flags
         h = C.c_void_p()
         rc = self._lib.gsc_create(C.byref(cfg), C.byref(h))
         if rc != N.GSC_OK:
@@ -42,6 +43,12 @@ class CollisionContext:
         if getattr(self, "_h", None):
             self._lib.gsc_destroy(self._h)
             self._h = None
+
+    def set_flags(self, timing: bool = False, graph: bool = False):
+        """GSC_FLAG_TIMING / GSC_FLAG_GRAPH of the live context (per-stage times and graph replay exclude each other)"""
+        keep = self._flags & N.GSC_FLAG_CONTACTS
+        self._flags = keep | (N.GSC_FLAG_TIMING if timing else 0) | (N.GSC_FLAG_GRAPH if graph else 0)
+        self._check(self._lib.gsc_set_flags(self._h, self._flags))
 
     def __del__(self):
         try:
@@ -374,6 +381,10 @@ class CollisionGroup:
 
     def rebalance(self):
         self._check(self._lib.gsc_group_rebalance(self._h))
+
+    def reorder(self):
+        """every member keeps its colliders in the cell order of the last step (temporal coherence)"""
+        self._check(self._lib.gsc_group_reorder(self._h))
 
     def member_counts(self):
         out = []

@@ -66,7 +66,7 @@ struct gsc_ctx {
     // GSC_FLAG_GRAPH: stages 1-5 captured once per launch geometry
     cudaGraphExec_t graph_exec = nullptr;
     uint32_t graph_n = 0;
-    bool graph_window = false;
+    bool graph_window = false, graph_slab = false;
     int32_t graph_win[2] = { 0, 0 };
     // host -> device transform copies are cut into chunks; bvh_update starts on a chunk as soon as it has landed
     static constexpr int kChunks = 8;
@@ -440,6 +440,16 @@ int gsc_upload_colliders(gsc_ctx *c, uint32_t n, const uint32_t *entity, const u
     return GSC_OK;
 }
 
+int gsc_set_flags(gsc_ctx *c, uint32_t flags)
+{
+    if (int rc = check_ctx(c)) return rc;
+    NOT_IN_FLIGHT(c, "gsc_set_flags");
+    const uint32_t fixed = GSC_FLAG_CONTACTS;  // decides what was allocated
+    if ((flags & fixed) != (c->cfg.flags & fixed)) return fail(c, GSC_ERR_INVALID, "gsc_set_flags: GSC_FLAG_CONTACTS is fixed at gsc_create");
+    c->cfg.flags = flags;
+    return GSC_OK;
+}
+
 int gsc_collider_count(gsc_ctx *c, uint32_t *n_out)
 {
     if (int rc = check_ctx(c)) return rc;
@@ -699,13 +709,13 @@ static int stage_launches(gsc_ctx *c, bool slab, bool timing)
     FrameBlock *fb = c->d_fb;
     if (!slab) k_grid_setup<<<1, 32, 0, s>>>(fb, c->max_cells, n_total, c->have_window ? 1 : 0, c->win_lo, c->win_hi);
     if (n_total) {
-        k_cell_keys<<<tiles_for(n_total), kKeyThreads, 0, s>>>(n_total, c->d_rec, c->d_keys[0], c->d_wide, c->d_sort_scratch, fb);
+        k_cell_keys<<<tiles_for(n_total), kKeyThreads, 0, s>>>(n_total, n_dev, c->d_rec, c->d_keys[0], c->d_wide, c->d_sort_scratch, fb);
         if (timing) CU(c, cudaEventRecord(c->ev[2], s));
         launch_sort(s, n_total, c->d_keys, c->d_vals, true, kMaxPasses, &fb->sort, c->d_sort_scratch, true, n_dev);
         if (timing) CU(c, cudaEventRecord(c->ev[3], s));
         const uint32_t tb = (n_total + 1 + kTableThreads - 1) / kTableThreads;
         SortedVolumes sv{ c->d_rec_sorted, c->d_qrec_sorted, c->d_w3_sorted };
-        k_cell_table_permute<<<tb, kTableThreads, 0, s>>>(n_total, c->d_keys[0], c->d_vals[0], c->d_keys[1], c->d_vals[1],
+        k_cell_table_permute<<<tb, kTableThreads, 0, s>>>(n_total, n_dev, c->d_keys[0], c->d_vals[0], c->d_keys[1], c->d_vals[1],
                                                          c->d_rec, sv, c->d_cell_start, c->d_gaps, fb);
         k_fill_gaps<<<148 * 2, 256, 0, s>>>(c->d_cell_start, c->d_gaps, fb);
         if (timing) CU(c, cudaEventRecord(c->ev[4], s));
@@ -715,12 +725,12 @@ static int stage_launches(gsc_ctx *c, bool slab, bool timing)
             // (experimental, measured slower than k_pairs: DESIGN section 4) sphere-sphere pairs may be decided in its tail
             PairFuse pf{ c->d_pairs, c->max_pairs };
             const int fuse = (c->fuse_ss && !c->d_contacts) ? 1 : 0;
-            k_pairs_tiled<<<(n_launch + kTileA - 1) / kTileA, kTileA, sizeof(TileShared), s>>>(n_launch, c->d_keys[0], c->d_keys[1], sv,
+            k_pairs_tiled<<<(n_launch + kTileA - 1) / kTileA, kTileA, sizeof(TileShared), s>>>(n_launch, n_dev, c->d_keys[0], c->d_keys[1], sv,
                                                                                             c->d_cell_start, po, pf, fuse, c->d_overflow, fb);
             // tiles too dense for the staging buffers (normally none: the kernel exits at once)
-            k_pairs<true><<<148 * 16, kPairThreads, 0, s>>>(n_launch, c->d_keys[0], c->d_keys[1], sv, c->d_cell_start, po, c->d_overflow, fb);
+            k_pairs<true><<<148 * 16, kPairThreads, 0, s>>>(n_launch, n_dev, c->d_keys[0], c->d_keys[1], sv, c->d_cell_start, po, c->d_overflow, fb);
         } else {
-            k_pairs<false><<<(n_launch + kPairThreads - 1) / kPairThreads, kPairThreads, 0, s>>>(n_launch, c->d_keys[0], c->d_keys[1], sv,
+            k_pairs<false><<<(n_launch + kPairThreads - 1) / kPairThreads, kPairThreads, 0, s>>>(n_launch, n_dev, c->d_keys[0], c->d_keys[1], sv,
                                                                                               c->d_cell_start, po, nullptr, fb);
         }
         if (timing) CU(c, cudaEventRecord(c->ev[5], s));
@@ -747,16 +757,18 @@ static int stage_enqueue(gsc_ctx *c, bool slab = false)
     const bool timing = c->cfg.flags & GSC_FLAG_TIMING;
     // GSC_FLAG_GRAPH: the launch sequence has no host round trip and its geometry only depends on the collider count
     // (and the slab window), so it is captured once and replayed with ONE graph launch per step
-    if ((c->cfg.flags & GSC_FLAG_GRAPH) && !timing && !slab) {
-        const uint32_t n_total = c->n_local + c->n_ghost;
-        const bool same = c->graph_exec && c->graph_n == n_total && c->graph_window == c->have_window &&
-                          (!c->have_window || (c->graph_win[0] == c->win_lo && c->graph_win[1] == c->win_hi));
+    if ((c->cfg.flags & GSC_FLAG_GRAPH) && !timing) {
+        // (a slab step launches for the capacity and reads the real count from the device: its geometry never changes)
+        const uint32_t n_total = slab ? c->cap : c->n_local + c->n_ghost;
+        const bool window = !slab && c->have_window;
+        const bool same = c->graph_exec && c->graph_n == n_total && c->graph_slab == slab && c->graph_window == window &&
+                          (!window || (c->graph_win[0] == c->win_lo && c->graph_win[1] == c->win_hi));
         if (!same) {
             if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
             c->graph_exec = nullptr;
             cudaGraph_t graph = nullptr;
             CU(c, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            const int rc = stage_launches(c, false, false);
+            const int rc = stage_launches(c, slab, false);
             const cudaError_t e = cudaStreamEndCapture(s, &graph);
             if (rc != GSC_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
             if (e != cudaSuccess) return fail(c, GSC_ERR_CUDA, "graph capture: %s", cudaGetErrorString(e));
@@ -764,7 +776,8 @@ static int stage_enqueue(gsc_ctx *c, bool slab = false)
             cudaGraphDestroy(graph);
             if (e2 != cudaSuccess) { c->graph_exec = nullptr; return fail(c, GSC_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e2)); }
             c->graph_n = n_total;
-            c->graph_window = c->have_window;
+            c->graph_slab = slab;
+            c->graph_window = window;
             c->graph_win[0] = c->win_lo;
             c->graph_win[1] = c->win_hi;
         }
@@ -787,7 +800,7 @@ static int stage_collect(gsc_ctx *c, gsc_step_out *out)
     const FrameBlock &h = *c->h_fb;
     c->last_pairs = std::min<uint64_t>(h.n_pairs, c->max_pairs);
     if (c->slab_step) c->n_ghost = h.slab.n_ghost;
-    c->sorted_valid = h.status == 0 && h.grid.valid && !c->slab_step && c->n_ghost == 0;
+    c->sorted_valid = h.status == 0 && h.grid.valid;
     if (out) {
         memset(out, 0, sizeof *out);
         out->n_pairs = h.n_pairs;
@@ -1492,12 +1505,28 @@ int gsc_reorder_colliders(gsc_ctx *c, uint32_t *order, uint32_t cap)
 {
     if (int rc = check_ctx(c)) return rc;
     NOT_IN_FLIGHT(c, "gsc_reorder_colliders");
-    if (!c->sorted_valid) return fail(c, GSC_ERR_INVALID, "gsc_reorder_colliders: needs a completed single-context step on the current collider set");
+    if (!c->sorted_valid) return fail(c, GSC_ERR_INVALID, "gsc_reorder_colliders: needs a completed step on the current collider set");
     const uint32_t n = c->n_local;
     if (!order || cap < n) return fail(c, GSC_ERR_CAPACITY, "gsc_reorder_colliders: need room for %u entries", n);
     if (n == 0) return GSC_OK;
     cudaStream_t s = c->stream;
+    // the sorted index stream of the last step; after a slab step it also holds the ghosts (local index >= n_local),
+    // which are dropped here: the local colliders keep their relative cell order
+    const uint32_t n_sorted = c->slab_step ? c->h_fb->n_total : n + c->n_ghost;
     const uint32_t *vals = c->d_vals[c->h_fb->sort.num_passes & 1];
+    Scratch ord;
+    {
+        std::vector<uint32_t> all(n_sorted);
+        CU(c, cudaMemcpyAsync(all.data(), vals, (size_t)n_sorted * 4, cudaMemcpyDeviceToHost, s));
+        CU(c, cudaStreamSynchronize(s));
+        uint32_t k = 0;
+        for (uint32_t i = 0; i < n_sorted && k < n; ++i)
+            if (all[i] < n) order[k++] = all[i];
+        if (k != n) return fail(c, GSC_ERR_INVALID, "gsc_reorder_colliders: the last step's order covers %u of %u local colliders", k, n);
+        CU(c, cudaMalloc(&ord.p[0], (size_t)n * 4));
+        CU(c, cudaMemcpyAsync(ord.p[0], order, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        vals = (const uint32_t *)ord.p[0];
+    }
     Scratch tmp[2];
     uint8_t *kind_o = nullptr;
     float *off_o = nullptr, *size_o = nullptr;
@@ -1510,7 +1539,6 @@ int gsc_reorder_colliders(gsc_ctx *c, uint32_t *order, uint32_t cap)
     k_reorder_static<<<(n + 255) / 256, 256, 0, s>>>(n, vals, c->d_kind, c->d_offset, c->d_size, c->d_entity, c->have_gidx ? c->d_gidx : nullptr,
                                                    kind_o, off_o, size_o, ent_o, gidx_o);
     CU(c, cudaGetLastError());
-    CU(c, cudaMemcpyAsync(order, vals, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
     CU(c, cudaMemcpyAsync(c->d_kind, kind_o, n, cudaMemcpyDeviceToDevice, s));
     CU(c, cudaMemcpyAsync(c->d_offset, off_o, (size_t)n * 12, cudaMemcpyDeviceToDevice, s));
     CU(c, cudaMemcpyAsync(c->d_size, size_o, (size_t)n * 12, cudaMemcpyDeviceToDevice, s));

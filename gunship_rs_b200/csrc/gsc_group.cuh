@@ -23,7 +23,7 @@ struct gsc_group {
     std::vector<uint8_t> kind;
     std::vector<float> offset, size;
     std::vector<float> last_pos, last_quat, last_scale;  // the transforms of the last gsc_group_update_transforms
-    std::vector<std::vector<uint32_t>> owned;            // global indices per member, ascending (local order == global order)
+    std::vector<std::vector<uint32_t>> owned;            // global indices per member in the member's dense (slot) order
     std::vector<float> cuts;                             // x positions of the world-1 slab cuts
     std::vector<gsc_step_out> last;                      // per member, last step
     std::vector<uint8_t> rot_sent;                       // per member: rotation + scale are on the device for the current set
@@ -364,6 +364,27 @@ int gsc_group_rebalance(gsc_group *g)
     if (int rc = group_distribute(g, g->last_pos.data())) return rc;
     if (!g->last_quat.empty()) return group_scatter(g, g->last_pos.data(), g->last_quat.data(), g->last_scale.data());
     return GSC_OK;  // (no rotations were ever sent: the caller provides the next frame's transforms in full)
+}
+
+// Temporal coherence behind the group: every member's dense arrays go into the cell order of the step that just
+// completed (gsc_reorder_colliders) and the member's `owned` list is permuted the same way -- the group's scatter of the
+// engine's dense transform arrays is a gather anyway, so the engine-facing interface does not change at all.
+int gsc_group_reorder(gsc_group *g)
+{
+    if (!g) return GSC_ERR_INVALID;
+    if (!g->have_colliders) return gfail(g, GSC_ERR_INVALID, "gsc_group_reorder before gsc_group_upload_colliders");
+    const uint32_t world = (uint32_t)g->m.size();
+    for (uint32_t r = 0; r < world; ++r) {
+        std::vector<uint32_t> &own = g->owned[r];
+        std::vector<uint32_t> order(own.size() + 1), moved(own.size());
+        if (int rc = gsc_reorder_colliders(g->m[r], order.data(), (uint32_t)order.size())) return gmember_fail(g, r, rc);
+        for (size_t k = 0; k < own.size(); ++k) moved[k] = own[order[k]];
+        own.swap(moved);
+        g->rot_sent[r] = 0;
+    }
+    g->have_transforms = false;
+    if (!g->last_quat.empty()) return group_scatter(g, g->last_pos.data(), g->last_quat.data(), g->last_scale.data());
+    return GSC_OK;
 }
 
 int gsc_group_member(gsc_group *g, uint32_t i, gsc_ctx **ctx, uint32_t *n_local, uint32_t *owned)

@@ -399,15 +399,16 @@ constexpr int kKeyThreads = 256;
 // One CTA per sort tile (kSortTile volumes), so that the digit counts of the FIRST radix pass come for free:
 // tile_hist[d * num_tiles + tile] is what k_radix_upsweep would compute for pass 0.
 __global__ void __launch_bounds__(kKeyThreads)
-k_cell_keys(uint32_t n_cap, const float4 *__restrict__ rec, uint32_t *__restrict__ keys,
+k_cell_keys(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const float4 *__restrict__ rec, uint32_t *__restrict__ keys,
             uint32_t *__restrict__ wide_list, uint32_t *__restrict__ tile_hist, FrameBlock *__restrict__ fb)
 {
     constexpr int WARPS = kKeyThreads / 32;
     __shared__ __align__(16) uint16_t s_hist[WARPS][kRadix];
     const GridParams g = fb->grid;
     if (!g.valid) return;
-    // (the grid may be sized for a capacity: the step's volume count -- local + ghosts -- lives on the device)
-    const uint32_t n_total = min(fb->n_total, n_cap);
+    // (slab steps launch for a capacity: the step's volume count -- local + ghosts -- then lives on the device;
+    // otherwise the host knows it and no CTA waits for a load before it can start)
+    const uint32_t n_total = n_dev ? min(*n_dev, n_cap) : n_cap;
     const uint32_t num_tiles = (n_total + kSortTile - 1) / kSortTile;
     if (blockIdx.x >= num_tiles) return;
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -502,14 +503,14 @@ constexpr int kGapCap = 4096;
 constexpr int kWarpFillMax = 4096;  // cells a warp fills transposed; wider spans (rare) go gap by gap
 
 __global__ void __launch_bounds__(kTableThreads)
-k_cell_table_permute(uint32_t n_cap, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ vals_a,
+k_cell_table_permute(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ vals_a,
                      const uint32_t *__restrict__ keys_b, const uint32_t *__restrict__ vals_b,
                      const float4 *__restrict__ rec, SortedVolumes sv,
                      uint32_t *__restrict__ cell_start, uint4 *__restrict__ gaps, FrameBlock *__restrict__ fb)
 {
     const GridParams g = fb->grid;
     if (!g.valid) return;
-    const uint32_t n_total = min(fb->n_total, n_cap);
+    const uint32_t n_total = n_dev ? min(*n_dev, n_cap) : n_cap;
     if (blockIdx.x * (uint32_t)kTableThreads > n_total) return;  // (position n_total itself closes the table)
     const bool in_b = fb->sort.num_passes & 1;  // ping-pong parity of the sort
     const uint32_t *keys = in_b ? keys_b : keys_a;

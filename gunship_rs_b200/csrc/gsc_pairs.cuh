@@ -264,7 +264,7 @@ GSC_DEV void cp_async4(void *smem_dst, const void *gsrc)
 GSC_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __global__ void __launch_bounds__(kTileA, GSC_TILE_CTAS)
-k_pairs_tiled(uint32_t n_cap, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ keys_b,
+k_pairs_tiled(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ keys_b,
               SortedVolumes sv, const uint32_t *__restrict__ cell_start, PairOut out, PairFuse fuse, int fuse_ss,
               uint32_t *__restrict__ overflow_tiles, FrameBlock *__restrict__ fb)
 {
@@ -272,7 +272,7 @@ k_pairs_tiled(uint32_t n_cap, const uint32_t *__restrict__ keys_a, const uint32_
     TileShared &sh = *reinterpret_cast<TileShared *>(tile_smem);
     const GridParams g = fb->grid;
     if (!g.valid) return;
-    const uint32_t n_total = min(fb->n_total, n_cap);
+    const uint32_t n_total = n_dev ? min(*n_dev, n_cap) : n_cap;  // (device-side count: slab steps only)
     const uint32_t p0 = blockIdx.x * (uint32_t)kTileA;
     if (p0 >= n_total) return;
     const uint32_t *keys = (fb->sort.num_passes & 1) ? keys_b : keys_a;
@@ -536,13 +536,13 @@ __device__ __noinline__ void pair_drain_lane(PairShared &sh, uint32_t p, uint32_
 // QUEUE == true: persistent CTAs over the tiles queued in out.overflow_tiles by k_pairs_tiled
 template <bool QUEUE>
 __global__ void __launch_bounds__(kPairThreads, QUEUE ? 16 : GSC_PAIR_MIN_CTAS)
-k_pairs(uint32_t n_cap, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ keys_b, SortedVolumes sv,
+k_pairs(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ keys_b, SortedVolumes sv,
         const uint32_t *__restrict__ cell_start, PairOut out, const uint32_t *__restrict__ overflow_tiles, FrameBlock *__restrict__ fb)
 {
     __shared__ PairShared sh;
     const GridParams g = fb->grid;
     if (!g.valid) return;
-    const uint32_t n_total = min(fb->n_total, n_cap);
+    const uint32_t n_total = n_dev ? min(*n_dev, n_cap) : n_cap;  // (device-side count: slab steps only)
     const uint32_t *keys = (fb->sort.num_passes & 1) ? keys_b : keys_a;
     const int tid = threadIdx.x, lane = tid & 31;
     constexpr uint32_t kSlices = kTileA / kPairThreads;  // slices of kPairThreads volumes per tile

@@ -498,14 +498,38 @@ def bench_multi_gpu(args, n, rank, world, local_rank, metric, unit, workload_nam
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), outs
 
+    # timed region: no per-stage events, stages 1-5 replayed from one captured CUDA graph per step
+    use_graph = os.environ.get("GSC_BENCH_GRAPH", "1") == "1"
+    ctx.set_flags(timing=False, graph=use_graph)
+    slot_order = not getattr(args, "assign_order", False)
+    if slot_order:
+        # temporal coherence: after one step every rank keeps its colliders in that frame's cell order and
+        # marshals the later frames in slot order (gsc_reorder_colliders); the pair set does not change
+        step_resident(0)
+        order = ctx.reorder_colliders().astype(np.int64)
+        box = box[order]
+        for f in range(nframes):
+            h_pos[f].copy_(h_pos[f][torch.from_numpy(order)])
+            h_quat[f].copy_(h_quat[f][torch.from_numpy(order)])
+        h_scale = h_scale[torch.from_numpy(order)].contiguous().pin_memory()
+        h_bquat = [torch.from_numpy(np.ascontiguousarray(t.numpy()[box])).pin_memory() for t in h_quat]
+        h_bscale = torch.from_numpy(np.ascontiguousarray(h_scale.numpy()[box])).pin_memory()
+        d_pos = [t.to(dev) for t in h_pos]
+        d_quat = [t.to(dev) for t in h_quat]
+        d_scale = h_scale.to(dev)
     for i in range(args.warmup):
         step_resident(i)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    span, outs = timed(lambda i: step_resident(args.warmup + i), args.steps)
+    span, _ = timed(lambda i: step_resident(args.warmup + i), args.steps)
     clocks = sampler.stop() if rank == 0 else None
     value = n * args.steps / span
+    # the same steps with a CUDA event between the stages (plain launches) for the per-stage table
+    ctx.set_flags(timing=True, graph=False)
+    step_resident(0)
+    _, outs = timed(lambda i: step_resident(args.warmup + i), args.steps)
+    ctx.set_flags(timing=False, graph=use_graph)
 
     # e2e: host transforms in, pairs out to pinned host memory, every step
     max_pairs = int(max(o.n_pairs for o in outs))
@@ -583,7 +607,8 @@ def bench_multi_gpu(args, n, rank, world, local_rank, metric, unit, workload_nam
                                      if driver.push else "NCCL send/recv"),
                        "l2": "inputs larger than L2 (no flush needed)" if n_local * 100 > 126e6 else "per-rank inputs near L2 size",
                        "box_fraction": round(f_box, 3), "contact_pairs_per_step": int(sums[0]),
-                       "halo_colliders_per_step": int(sums[5]), "frame0_pair_set": fingerprint},
+                       "halo_colliders_per_step": int(sums[5]), "frame0_pair_set": fingerprint,
+                       "slot_order": slot_order, "graph_replay": use_graph},
             "e2e": {"value": n * args.steps / span_e2e, "unit": unit, "ms_per_step": 1e3 * span_e2e / args.steps,
                     "h2d_bytes_per_step": int(n * 12 + sums[8] * 16), "d2h_bytes_per_step": int(sums[7]),
                     "mode": "pipelined host loop: every rank hands frame f+1 over right after bvh_update of step f",

@@ -341,6 +341,8 @@ public:
     }
     // migrants: re-cut the slabs from the last frame's positions and the last step's work
     void rebalance() { check(gsc_group_rebalance(group_)); }
+    // temporal coherence: the slabs keep their colliders in the cell order of the last update
+    void reorder() { check(gsc_group_reorder(group_)); }
 
 private:
     void check(int rc) const

@@ -101,6 +101,8 @@ typedef struct gsc_step_out {
 /* ---- lifetime ---- */
 int  gsc_create(const gsc_config *cfg, gsc_ctx **out);
 void gsc_destroy(gsc_ctx *ctx);
+/* change GSC_FLAG_TIMING / GSC_FLAG_GRAPH of a live context (GSC_FLAG_CONTACTS is fixed at gsc_create) */
+int  gsc_set_flags(gsc_ctx *ctx, uint32_t flags);
 /* last error text of this context (never NULL); ctx == NULL gives the last gsc_create failure */
 const char *gsc_last_error(const gsc_ctx *ctx);
 int  gsc_abi_version(void);
@@ -374,6 +376,9 @@ int gsc_group_update_transforms(gsc_group *group, uint32_t n, const float *pos3,
 int gsc_group_step(gsc_group *group, gsc_step_out *total);
 int gsc_group_download_pairs(gsc_group *group, uint32_t *dst, uint64_t cap_pairs, int sorted, uint64_t *n_out);
 int gsc_group_rebalance(gsc_group *group);
+/* temporal coherence behind the group: every member keeps its colliders in the cell order of the step that just
+ * completed (gsc_reorder_colliders); the engine keeps handing over dense arrays in ITS order */
+int gsc_group_reorder(gsc_group *group);
 /* inspection: member i's context, its collider count and the global indices it owns (owned[n_local], may be NULL) */
 int gsc_group_member(gsc_group *group, uint32_t i, gsc_ctx **ctx, uint32_t *n_local, uint32_t *owned);
 

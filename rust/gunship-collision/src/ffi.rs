@@ -74,6 +74,7 @@ extern "C" {
     pub fn gsc_destroy(ctx: *mut gsc_ctx);
     pub fn gsc_last_error(ctx: *const gsc_ctx) -> *const c_char;
     pub fn gsc_abi_version() -> c_int;
+    pub fn gsc_set_flags(ctx: *mut gsc_ctx, flags: u32) -> c_int;
     pub fn gsc_upload_colliders(ctx: *mut gsc_ctx, n: u32, entity: *const u32, kind: *const u8, offset3: *const f32,
                                 size3: *const f32, global_index: *const u32) -> c_int;
     pub fn gsc_update_transforms(ctx: *mut gsc_ctx, n: u32, pos3: *const f32, quat4: *const f32, scale3: *const f32) -> c_int;
@@ -139,6 +140,7 @@ extern "C" {
     pub fn gsc_group_step(group: *mut gsc_group, total: *mut gsc_step_out) -> c_int;
     pub fn gsc_group_download_pairs(group: *mut gsc_group, dst: *mut u32, cap_pairs: u64, sorted: c_int, n_out: *mut u64) -> c_int;
     pub fn gsc_group_rebalance(group: *mut gsc_group) -> c_int;
+    pub fn gsc_group_reorder(group: *mut gsc_group) -> c_int;
     pub fn gsc_group_member(group: *mut gsc_group, i: u32, ctx: *mut *mut gsc_ctx, n_local: *mut u32, owned: *mut u32) -> c_int;
     // pinned transform staging
     pub fn gsc_map_transform_staging(ctx: *mut gsc_ctx, bank: u32, pos3: *mut *mut f32, box_quat4: *mut *mut f32,

@@ -40,6 +40,8 @@ def test_group_union_is_the_single_gpu_pair_set(cfg, n, world):
             assert out.n_wide == 0 and 0 < out.n_ghost < n
             # unsorted download: the same set
             assert np.array_equal(np.sort(grp.pairs_packed(sorted=False)), want)
+            if f == 1:
+                grp.reorder()       # members switch to the cell order of this frame; the dense interface does not change
     oracle.close()
 
 
