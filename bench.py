@@ -182,7 +182,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=4)
-    ap.add_argument("--n", type=int, default=0, help="override the collider count (parity/dev runs only)")
+    ap.add_argument("--n", "--colliders", dest="n", type=int, default=0,
+                    help="override the collider count (parity/dev runs only; under torchrun spell it --colliders)")
     ap.add_argument("--frames", type=int, default=3, help="distinct jittered frames cycled through")
     ap.add_argument("--cpu-sample-n", type=int, default=0, help="collider count of the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -399,8 +400,8 @@ def main():
 
     def marshal(i):
         b = i & 1
-        np.copyto(banks[b][0][:n], p_pos[b])
-        np.take(p_quat[b], box_idx, axis=0, out=banks[b][1][:n_box])
+        np.copyto(banks[b][0][:n], p_pos[b % len(p_pos)])
+        np.take(p_quat[b % len(p_quat)], box_idx, axis=0, out=banks[b][1][:n_box])
         ctx.commit_transform_staging(b, n_box, True, False)
 
     marshal(0)

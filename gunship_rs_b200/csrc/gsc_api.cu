@@ -65,7 +65,7 @@ struct gsc_ctx {
     float *h_stage[2][3] = { { nullptr, nullptr, nullptr }, { nullptr, nullptr, nullptr } };
     // GSC_FLAG_GRAPH: stages 1-5 captured once per launch geometry
     cudaGraphExec_t graph_exec = nullptr;
-    uint32_t graph_n = 0;
+    uint32_t graph_n = 0, graph_local = 0;
     bool graph_window = false, graph_slab = false;
     int32_t graph_win[2] = { 0, 0 };
     // host -> device transform copies are cut into chunks; bvh_update starts on a chunk as soon as it has landed
@@ -761,7 +761,8 @@ static int stage_enqueue(gsc_ctx *c, bool slab = false)
         // (a slab step launches for the capacity and reads the real count from the device: its geometry never changes)
         const uint32_t n_total = slab ? c->cap : c->n_local + c->n_ghost;
         const bool window = !slab && c->have_window;
-        const bool same = c->graph_exec && c->graph_n == n_total && c->graph_slab == slab && c->graph_window == window &&
+        const bool same = c->graph_exec && c->graph_n == n_total && c->graph_local == c->n_local && c->graph_slab == slab &&
+                          c->graph_window == window &&
                           (!window || (c->graph_win[0] == c->win_lo && c->graph_win[1] == c->win_hi));
         if (!same) {
             if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
@@ -776,6 +777,7 @@ static int stage_enqueue(gsc_ctx *c, bool slab = false)
             cudaGraphDestroy(graph);
             if (e2 != cudaSuccess) { c->graph_exec = nullptr; return fail(c, GSC_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e2)); }
             c->graph_n = n_total;
+            c->graph_local = c->n_local;  // (baked into k_wide_pairs' arguments)
             c->graph_slab = slab;
             c->graph_window = window;
             c->graph_win[0] = c->win_lo;

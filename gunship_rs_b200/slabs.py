@@ -444,41 +444,76 @@ def bench_multi_gpu(args, n, rank, world, local_rank, metric, unit, workload_nam
     balance = os.environ.get("GSC_SLAB_BALANCE", "work")
     weight = pair_work_estimate(scene.pos, scene.cell_hint) if balance == "work" and world > 1 else None
     owner = partition_x_slabs(scene.pos[:, 0], world, weight)
-    mine = np.nonzero(owner == rank)[0]
-    n_local = int(mine.shape[0])
     nframes = max(1, args.frames)
-    h_pos, h_quat = [], []
-    for f in range(nframes):
-        pos, quat = scene.frame(f)
-        hp = torch.empty((n_local, 3), dtype=torch.float32, pin_memory=True)
-        hq = torch.empty((n_local, 4), dtype=torch.float32, pin_memory=True)
-        hp.numpy()[:] = pos[mine]
-        hq.numpy()[:] = quat[mine]
-        h_pos.append(hp)
-        h_quat.append(hq)
-    h_scale = torch.from_numpy(np.ascontiguousarray(scene.scale[mine])).pin_memory()
-    # the host layer marshals rotation / scale for the boxes only (spheres ignore them, mod.rs:313-317)
-    box = scene.kind[mine] == 1
-    n_box = int(box.sum())
-    h_bquat = [torch.from_numpy(np.ascontiguousarray(t.numpy()[box])).pin_memory() for t in h_quat]
-    h_bscale = torch.from_numpy(np.ascontiguousarray(scene.scale[mine][box])).pin_memory()
-    d_pos = [t.to(dev) for t in h_pos]
-    d_quat = [t.to(dev) for t in h_quat]
-    d_scale = h_scale.to(dev)
-
-    cap = int(n_local * 1.25) + (1 << 16)  # room for ghosts
+    frames_full = [scene.frame(f) for f in range(nframes)]
+    f_box = float((scene.kind == 1).mean())
+    cap = int(n / world * 1.6) + (1 << 16)  # room for ghosts and for the re-cut slabs of the calibration below
     ctx = G.CollisionContext(cap, device=local_rank, timing=True)
-    ctx.upload_colliders(scene.entity[mine], scene.kind[mine], scene.offset[mine], scene.size[mine],
-                         global_index=mine.astype(np.uint32))
     driver = SlabDriver(GpuSlabBackend(ctx, local_rank))
     if os.environ.get("GSC_HALO", "push") == "push":
         driver.enable_peer_push()  # halo written straight into the neighbour's HBM over NVLink
-    f_box = float((scene.kind == 1).mean())
+    part = {}
+
+    def load_partition(owner):
+        """(re)build this rank's share: static collider data with global indices, pinned host frames, device frames"""
+        mine = np.nonzero(owner == rank)[0]
+        part["mine"] = mine
+        part["h_pos"], part["h_quat"] = [], []
+        for pos, quat in frames_full:
+            hp = torch.empty((mine.shape[0], 3), dtype=torch.float32, pin_memory=True)
+            hq = torch.empty((mine.shape[0], 4), dtype=torch.float32, pin_memory=True)
+            hp.numpy()[:] = pos[mine]
+            hq.numpy()[:] = quat[mine]
+            part["h_pos"].append(hp)
+            part["h_quat"].append(hq)
+        part["h_scale"] = torch.from_numpy(np.ascontiguousarray(scene.scale[mine])).pin_memory()
+        part["box"] = scene.kind[mine] == 1
+        ctx.upload_colliders(scene.entity[mine], scene.kind[mine], scene.offset[mine], scene.size[mine],
+                             global_index=mine.astype(np.uint32))
+        finish_frames()
+
+    def finish_frames():
+        # the host layer marshals rotation / scale for the boxes only (spheres ignore them, mod.rs:313-317)
+        box = part["box"]
+        part["n_box"] = int(box.sum())
+        part["h_bquat"] = [torch.from_numpy(np.ascontiguousarray(t.numpy()[box])).pin_memory() for t in part["h_quat"]]
+        part["h_bscale"] = torch.from_numpy(np.ascontiguousarray(part["h_scale"].numpy()[box])).pin_memory()
+        part["d_pos"] = [t.to(dev) for t in part["h_pos"]]
+        part["d_quat"] = [t.to(dev) for t in part["h_quat"]]
+        part["d_scale"] = part["h_scale"].to(dev)
 
     def step_resident(i):
         f = i % nframes
-        ctx.bind_device_transforms(d_pos[f].data_ptr(), d_quat[f].data_ptr(), d_scale.data_ptr())
+        ctx.bind_device_transforms(part["d_pos"][f].data_ptr(), part["d_quat"][f].data_ptr(), part["d_scale"].data_ptr())
         return driver.step()
+
+    load_partition(owner)
+
+    # Slab calibration: the a-priori weights give the SHAPE of the cost density, a few measured steps its SCALE per
+    # slab (device time of this rank's own stages, the exchange interval -- which holds the waits for the other ranks --
+    # left out); the slabs are re-cut by the corrected weights.  What an engine would do with gsc_group_rebalance.
+    calib = int(os.environ.get("GSC_SLAB_CALIBRATE", "2")) if (weight is not None and world > 1) else 0
+    calib_log = []
+    for _ in range(calib):
+        ctx.set_flags(timing=True, graph=False)
+        step_resident(0)
+        busy = np.zeros(1)
+        for i in range(3):
+            o = step_resident(i)
+            sm = list(o.stage_ms)
+            busy += sm[0] + sm[2] + sm[3] + sm[4] + sm[5]
+        mine = part["mine"]
+        t = torch.tensor([float(busy[0]) / 3.0, float(weight[mine].sum())], dtype=torch.float64, device=dev)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        allt = torch.stack(allt).cpu().numpy()
+        alpha = allt[:, 0] / np.maximum(allt[:, 1], 1e-9)
+        alpha /= alpha.mean()
+        calib_log.append([round(float(x), 4) for x in allt[:, 0]])
+        weight = weight * alpha[owner]
+        owner = partition_x_slabs(scene.pos[:, 0], world, weight)
+        load_partition(owner)
+    n_local = int(part["mine"].shape[0])
 
     def timed(fn, steps):
         """barrier + synchronize on both sides, CUDA events on the current stream, MAX over ranks"""
@@ -506,17 +541,14 @@ def bench_multi_gpu(args, n, rank, world, local_rank, metric, unit, workload_nam
         # temporal coherence: after one step every rank keeps its colliders in that frame's cell order and
         # marshals the later frames in slot order (gsc_reorder_colliders); the pair set does not change
         step_resident(0)
-        order = ctx.reorder_colliders().astype(np.int64)
-        box = box[order]
+        order = torch.from_numpy(ctx.reorder_colliders().astype(np.int64))
+        part["box"] = part["box"][order.numpy()]
         for f in range(nframes):
-            h_pos[f].copy_(h_pos[f][torch.from_numpy(order)])
-            h_quat[f].copy_(h_quat[f][torch.from_numpy(order)])
-        h_scale = h_scale[torch.from_numpy(order)].contiguous().pin_memory()
-        h_bquat = [torch.from_numpy(np.ascontiguousarray(t.numpy()[box])).pin_memory() for t in h_quat]
-        h_bscale = torch.from_numpy(np.ascontiguousarray(h_scale.numpy()[box])).pin_memory()
-        d_pos = [t.to(dev) for t in h_pos]
-        d_quat = [t.to(dev) for t in h_quat]
-        d_scale = h_scale.to(dev)
+            part["h_pos"][f].copy_(part["h_pos"][f][order])
+            part["h_quat"][f].copy_(part["h_quat"][f][order])
+        part["h_scale"] = part["h_scale"][order].contiguous().pin_memory()
+        finish_frames()
+    h_pos, h_quat, h_bquat, h_bscale, n_box = part["h_pos"], part["h_quat"], part["h_bquat"], part["h_bscale"], part["n_box"]
     for i in range(args.warmup):
         step_resident(i)
     sampler = ClockSampler(local_rank)
@@ -572,8 +604,14 @@ def bench_multi_gpu(args, n, rank, world, local_rank, metric, unit, workload_nam
 
     stage_ms = np.mean(np.array([list(o.stage_ms) for o in outs], dtype=np.float64), axis=0)
     st = torch.tensor(stage_ms, dtype=torch.float64, device=dev)
+    st_min = st.clone()
     dist.all_reduce(st, op=dist.ReduceOp.MAX)
+    dist.all_reduce(st_min, op=dist.ReduceOp.MIN)
     stage_ms = st.cpu().numpy()
+    stage_min = st_min.cpu().numpy()
+    cnt = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(cnt, torch.tensor([n_local], dtype=torch.int64, device=dev))
+    counts = [int(c.item()) for c in cnt]
     sums = total([np.mean([o.n_pairs for o in outs]), np.mean([o.n_sphere_obb for o in outs]),
                   np.mean([o.n_obb_obb for o in outs]), np.mean([o.n_sphere_sphere for o in outs]),
                   np.mean([o.n_cells for o in outs]), float(driver.last_halo_in), float(n_local),
@@ -608,7 +646,8 @@ def bench_multi_gpu(args, n, rank, world, local_rank, metric, unit, workload_nam
                        "l2": "inputs larger than L2 (no flush needed)" if n_local * 100 > 126e6 else "per-rank inputs near L2 size",
                        "box_fraction": round(f_box, 3), "contact_pairs_per_step": int(sums[0]),
                        "halo_colliders_per_step": int(sums[5]), "frame0_pair_set": fingerprint,
-                       "slot_order": slot_order, "graph_replay": use_graph},
+                       "slot_order": slot_order, "graph_replay": use_graph,
+                       "slab_calibration_busy_ms": calib_log, "colliders_per_rank": [int(x) for x in counts]},
             "e2e": {"value": n * args.steps / span_e2e, "unit": unit, "ms_per_step": 1e3 * span_e2e / args.steps,
                     "h2d_bytes_per_step": int(n * 12 + sums[8] * 16), "d2h_bytes_per_step": int(sums[7]),
                     "mode": "pipelined host loop: every rank hands frame f+1 over right after bvh_update of step f",
@@ -618,7 +657,9 @@ def bench_multi_gpu(args, n, rank, world, local_rank, metric, unit, workload_nam
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
                          "note": "per-rank launch: mean bytes per rank over the slowest rank's stage time"},
-            "stages": {N.STAGE_NAMES[i]: {"ms_max_over_ranks": round(float(stage_ms[i]), 4)} for i in range(6)},
+            "stages": {N.STAGE_NAMES[i]: {"ms_max_over_ranks": round(float(stage_ms[i]), 4),
+                                          "ms_min_over_ranks": round(float(stage_min[i]), 4)} for i in range(6)},
+            "stages_note": "the cell_keys interval holds the device-side exchange and, with it, the wait for the slowest rank",
         }
         emit(line)
     if driver.trace is not None and rank == 0:
