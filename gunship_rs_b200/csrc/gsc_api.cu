@@ -233,6 +233,9 @@ int status_to_error(gsc_ctx *c, const FrameBlock &fb)
     if (st & kStCellSize) return fail(c, GSC_ERR_RANGE, "cell size (longest AABB axis) is not positive: %g", (double)fb.grid.cell_size);
     if (st & kStRange) return fail(c, GSC_ERR_RANGE, "a grid coordinate leaves the i16 range of GridCoord (grid_collision.rs:535)");
     if (st & kStWindow) return fail(c, GSC_ERR_INVALID, "gsc_set_x_window does not cover the home cell of a local collider");
+    if (st & kStWideBorder)
+        return fail(c, GSC_ERR_RANGE, "a volume whose AABB spans 3 cells (rounding; gsc_step_out.n_wide) lies on a slab border: "
+                                      "multi-GPU steps match such volumes inside their own slab only");
     if (st & kStPeerTimeout)
         return fail(c, GSC_ERR_NCCL, "slab exchange: a peer GPU did not publish its bounds / finish its halo push within %llu ms "
                                      "(a rank failed, or the ranks are not stepping together)", c->peer_timeout_ns / 1000000ull);
@@ -857,7 +860,10 @@ int gsc_step_begin(gsc_ctx *c)
     NOT_IN_FLIGHT(c, "gsc_step_begin");
     c->slab_step = false;
     if (int rc = stage_bounds(c)) return rc;
-    if (int rc = stage_enqueue(c)) return rc;
+    if (int rc = stage_enqueue(c)) {
+        c->bounds_done = false;  // nothing of this step is usable: the next call starts over
+        return rc;
+    }
     c->in_flight = true;
     return GSC_OK;
 }
@@ -1237,17 +1243,17 @@ int sort_standalone(gsc_ctx *c, cudaStream_t s, uint32_t n, uint32_t *keys[2], u
     const int passes = radix_passes(key_bits);
     *which = passes & 1;
     if (n == 0 || passes == 0) { *which = 0; return GSC_OK; }
-    const uint32_t tiles = tiles_for(n);
+    Scratch hold;
     uint32_t *scratch = nullptr;  // [ctl 4 words][tile histogram + digit totals]
     const size_t words = 4 + sort_scratch_words(n);
     CU(c, cudaMalloc((void **)&scratch, words * 4));
+    hold.p[0] = scratch;  // freed on every return path
     SortControl *ctl = reinterpret_cast<SortControl *>(scratch);
     SortControl h{ passes, key_bits, radix_digit_bits(key_bits) };
     CU(c, cudaMemcpyAsync(ctl, &h, sizeof h, cudaMemcpyHostToDevice, s));
     launch_sort(s, n, keys, vals, identity, passes, ctl, scratch + 4);
     CU(c, cudaGetLastError());
     CU(c, cudaStreamSynchronize(s));
-    cudaFree(scratch);
     return GSC_OK;
 }
 }  // namespace
@@ -1264,9 +1270,12 @@ static int ensure_sorted_perm(gsc_ctx *c)
     // LSD over the 64-bit tuple with the 32-bit sort: second entity first, then (stable) the first
     const uint32_t m = (uint32_t)n;
     uint32_t *k[2] = { nullptr, nullptr }, *v[2] = { nullptr, nullptr };
+    Scratch hold;  // the four temporaries are freed on every return path
     for (int i = 0; i < 2; ++i) {
         CU(c, dmalloc(&k[i], m));
+        hold.p[i] = k[i];
         CU(c, dmalloc(&v[i], m));
+        hold.p[2 + i] = v[i];
     }
     if (!c->d_perm) CU(c, dmalloc(&c->d_perm, c->max_pairs));
     const uint32_t blocks = (m + 255) / 256;
@@ -1283,7 +1292,6 @@ static int ensure_sorted_perm(gsc_ctx *c)
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) rc = fail(c, GSC_ERR_CUDA, "sorted download: %s", cudaGetErrorString(e));
     }
-    for (int i = 0; i < 2; ++i) { cudaFree(k[i]); cudaFree(v[i]); }
     if (rc == GSC_OK) c->perm_valid = true;
     return rc;
 }

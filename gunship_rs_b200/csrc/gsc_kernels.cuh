@@ -36,6 +36,7 @@ enum : uint32_t {
     kStWindow = 1u << 7,
     kStPeerTimeout = 1u << 8,  // a peer GPU did not publish its bounds / finish its halo push in time
     kStGhostCap = 1u << 9,     // local + pushed ghost volumes exceed the context's capacity
+    kStWideBorder = 1u << 10,  // a 3-cell-wide volume touches a slab border: its cross-slab pairs would be lost
 };
 
 // ---- volume record: 32 B = 2 x float4, the unit the broadphase streams ----
@@ -77,6 +78,7 @@ struct GridParams {
     int32_t dims[3];
     uint32_t num_cells;  // dims product; also the key given to wide volumes
     int32_t valid;
+    int32_t windowed;  // the grid covers one x-slab of the world (multi-GPU step)
     float qorg[3], qscale[3], qmargin;  // conservative box quantisation of k_pairs: t = (v - qorg) * qscale, qscale = 128 / cell (x, y), 64 / cell (z)
 };
 
@@ -314,6 +316,7 @@ GSC_DEV void grid_setup(FrameBlock *fb, unsigned long long max_cells, uint32_t n
 {
     GridParams g;
     g.valid = 0;
+    g.windowed = has_window;
     g.num_cells = 0;
     g.cell_size = ord2f(fb->bounds[0]);
     for (int a = 0; a < 3; ++a) { g.origin[a] = 0; g.dims[a] = 0; g.qorg[a] = 0.0f; g.qscale[a] = 0.0f; }
@@ -433,6 +436,10 @@ k_cell_keys(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const float4 *__
             if (!(v.meta & kMetaGhost)) atomicOr(&fb->status, kStWindow);
         } else if (wide) {
             key = g.num_cells;
+            // Wide volumes are matched by k_wide_pairs against the LOCAL volumes only.  In a slab step that loses the
+            // pairs a wide volume has across a slab border: refuse instead of dropping them silently (it needs an
+            // AABB that spans three cells through rounding AND sits on a cut: never seen in practice).
+            if (g.windowed && ((v.meta & kMetaGhost) || c0[0] <= 2 || c0[0] >= g.dims[0] - 3)) atomicOr(&fb->status, kStWideBorder);
             if (!(v.meta & kMetaGhost)) wide_list[atomicAdd(&fb->n_wide, 1u)] = i;
         } else {
             key = ((uint32_t)c0[0] * (uint32_t)g.dims[1] + (uint32_t)c0[1]) * (uint32_t)g.dims[2] + (uint32_t)c0[2];
@@ -974,53 +981,62 @@ __global__ void k_slab_publish(const FrameBlock *__restrict__ fb, SlabPeers peer
 __global__ void k_slab_gather(FrameBlock *fb, const SlabMail *mail, uint32_t rank, uint32_t world, uint32_t seq,
                               unsigned long long max_cells, uint32_t n_hint, unsigned long long timeout_ns)
 {
-    const uint32_t s = threadIdx.x;
+    // one warp; lane r owns rank r's mailbox slot: the waits AND the reads of the slots run in parallel (a serial walk
+    // over 8 slots of system-scope loads costs ~60 us)
+    const uint32_t r = threadIdx.x;
+    const bool mine = r < world;
     bool ok = true;
-    if (s < world) ok = slab_wait_flag(&mail->from[s].seq, seq, timeout_ns);
-    const bool all_ok = __all_sync(0xffffffffu, ok);
-    if (threadIdx.x != 0) return;
-    if (!all_ok) {
-        atomicOr(&fb->status, kStPeerTimeout);
-        fb->grid.valid = 0;
+    if (mine) ok = slab_wait_flag(&mail->from[r].seq, seq, timeout_ns);
+    if (!__all_sync(0xffffffffu, ok)) {
+        if (r == 0) {
+            atomicOr(&fb->status, kStPeerTimeout);
+            fb->grid.valid = 0;
+        }
         return;
     }
     // global bounds: bounds[] are ordered-uint encodings, every one of them reduces with max
-    uint32_t gb[7] = { 0, 0, 0, 0, 0, 0, 0 }, st = 0;
-    for (uint32_t r = 0; r < world; ++r) {
-        const SlabMailSlot &m = mail->from[r];
-        (void)ld_acquire_sys(&m.seq);  // (the slot arrived: lane r saw it; this orders lane 0's reads behind it)
-        for (int i = 0; i < 7; ++i) gb[i] = max(gb[i], m.bounds[i]);
-        st |= m.status;
+    uint32_t b[8], st = 0, n_loc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = 0;
+    if (mine) {
+        const SlabMailSlot &m = mail->from[r];  // (lane r acquired this slot's sequence number above)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b[i] = m.bounds[i];
+        st = m.status;
+        n_loc = m.n_local;
     }
+    uint32_t gb[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) gb[i] = __reduce_max_sync(0xffffffffu, b[i]);
+    st = __reduce_or_sync(0xffffffffu, st);
+    const float cell = ord2f(gb[0]);
+    // home x-cell = floor(fl(aabb.min.x / cell)) (grid_collision.rs:329-335): range of rank r from its smallest / largest aabb.min.x
+    const bool has = mine && n_loc != 0 && b[0] != 0 && gb[0] != 0 && cell > 0.0f && b[1] != 0 && b[7] != 0;
+    float lo = 1.0f, hi = 0.0f;
+    if (has) {
+        lo = cell_coord_f(ord2f(~b[1]), cell);
+        hi = cell_coord_f(ord2f(b[7]), cell);
+        if (!(lo >= -32768.0f) || !(hi <= 32767.0f)) { lo = 1.0f; hi = 0.0f; }  // (grid_setup reports the range error)
+    }
+    const int32_t x_lo = (int32_t)lo, x_hi = (int32_t)hi;
+    const int32_t my_lo = __shfl_sync(0xffffffffu, x_lo, rank), my_hi = __shfl_sync(0xffffffffu, x_hi, rank);
+    SlabState &sl = fb->slab;
+    if (mine) {
+        sl.x_lo[r] = x_lo;
+        sl.x_hi[r] = x_hi;
+        sl.peer_n_local[r] = n_loc;
+        // rank r's takers look at home x-cells {x - 1, x}: it needs the foreign volumes in [x_lo_r - 1, x_hi_r]
+        int32_t plo = 1, phi = 0;
+        if (r != rank && my_lo <= my_hi && x_lo <= x_hi) {
+            plo = max(x_lo - 1, my_lo);
+            phi = min(x_hi, my_hi);
+        }
+        sl.push_lo[r] = plo;
+        sl.push_hi[r] = phi;
+    }
+    if (r != 0) return;
     for (int i = 0; i < 7; ++i) fb->bounds[i] = gb[i];
     if (st) atomicOr(&fb->status, st);
-    const float cell = ord2f(gb[0]);
-    SlabState &sl = fb->slab;
-    for (uint32_t r = 0; r < world; ++r) {
-        const SlabMailSlot &m = mail->from[r];
-        // home x-cell = floor(fl(aabb.min.x / cell)) (grid_collision.rs:329-335): range of rank r from its smallest / largest aabb.min.x
-        const bool has = m.n_local != 0 && m.bounds[0] != 0 && gb[0] != 0 && cell > 0.0f && m.bounds[1] != 0 && m.bounds[7] != 0;
-        float lo = 1.0f, hi = 0.0f;
-        if (has) {
-            lo = cell_coord_f(ord2f(~m.bounds[1]), cell);
-            hi = cell_coord_f(ord2f(m.bounds[7]), cell);
-            if (!(lo >= -32768.0f) || !(hi <= 32767.0f)) { lo = 1.0f; hi = 0.0f; }  // (grid_setup reports the range error)
-        }
-        sl.x_lo[r] = (int32_t)lo;
-        sl.x_hi[r] = (int32_t)hi;
-        sl.peer_n_local[r] = m.n_local;
-    }
-    const int32_t my_lo = sl.x_lo[rank], my_hi = sl.x_hi[rank];
-    for (uint32_t r = 0; r < world; ++r) {
-        // rank r's takers look at home x-cells {x - 1, x}: it needs the foreign volumes in [x_lo_r - 1, x_hi_r]
-        int32_t lo = 1, hi = 0;
-        if (r != rank && my_lo <= my_hi && sl.x_lo[r] <= sl.x_hi[r]) {
-            lo = max(sl.x_lo[r] - 1, my_lo);
-            hi = min(sl.x_hi[r], my_hi);
-        }
-        sl.push_lo[r] = lo;
-        sl.push_hi[r] = hi;
-    }
     // my grid covers my slab (+ the one column of ghosts below it), not the world
     grid_setup(fb, max_cells, n_hint, my_lo <= my_hi ? 1 : 0, my_lo - 1, my_hi);
     if (my_lo > my_hi) fb->grid.valid = 0;  // no local colliders: nothing to do on this rank (ghosts never take)

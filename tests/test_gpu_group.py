@@ -204,3 +204,25 @@ def test_reordered_colliders_give_the_same_pair_sets():
         with pytest.raises(G.GscError):
             ctx.append_colliders(s.entity[:1], s.kind[:1], s.offset[:1], s.size[:1])
     oracle.close()
+
+
+def test_wide_volume_on_a_slab_border_is_refused_not_dropped():
+    """Volumes that rounding makes span 3 cells are matched by k_wide_pairs against LOCAL volumes only; in a multi-GPU
+    step a wide volume on a slab border would silently lose its cross-slab pairs -- the step fails with
+    GSC_ERR_RANGE instead.  (Single context: the corner-cell rule is followed exactly, test_gpu_parity.)"""
+    rng = np.random.default_rng(0)
+    n = 6000
+    s = scenes.bench_scene(n)
+    k = rng.integers(-6, 6, size=(n, 3)).astype(np.float32)
+    pos = k + np.float32(0.5)
+    big = np.arange(n) % 2 == 0
+    for d in range(3):
+        pos[big, d] = np.nextafter(pos[big, d], np.float32(-100), dtype=np.float32)
+    s.pos = pos.astype(np.float32)
+    s.size[~big, 0] = 0.2
+    with G.CollisionGroup(_devices(2), n) as grp:
+        grp.upload_colliders(s.entity, s.kind, s.offset, s.size, s.pos)
+        grp.update_transforms(s.pos, s.quat, s.scale)
+        with pytest.raises(G.GscError) as ei:
+            grp.step()
+        assert ei.value.code == N.GSC_ERR_RANGE and "slab border" in str(ei.value)
