@@ -714,7 +714,12 @@ static int stage_launches(gsc_ctx *c, bool slab, bool timing)
     if (n_total) {
         k_cell_keys<<<tiles_for(n_total), kKeyThreads, 0, s>>>(n_total, n_dev, c->d_rec, c->d_keys[0], c->d_wide, c->d_sort_scratch, fb);
         if (timing) CU(c, cudaEventRecord(c->ev[2], s));
-        launch_sort(s, n_total, c->d_keys, c->d_vals, true, kMaxPasses, &fb->sort, c->d_sort_scratch, true, n_dev);
+        // the keys are cell ids <= max_cells: no more radix passes can ever be needed than that many bits take (passes
+        // beyond the step's real count exit at once on the device, but each of their launches still costs ~4 us)
+        int key_bits_max = 1;
+        while (key_bits_max < 32 && (1ull << key_bits_max) <= c->max_cells) ++key_bits_max;
+        launch_sort(s, n_total, c->d_keys, c->d_vals, true, std::min(kMaxPasses, radix_passes(key_bits_max)), &fb->sort,
+                    c->d_sort_scratch, true, n_dev);
         if (timing) CU(c, cudaEventRecord(c->ev[3], s));
         const uint32_t tb = (n_total + 1 + kTableThreads - 1) / kTableThreads;
         SortedVolumes sv{ c->d_rec_sorted, c->d_qrec_sorted, c->d_w3_sorted };
@@ -743,8 +748,8 @@ static int stage_launches(gsc_ctx *c, bool slab, bool timing)
         else
             k_narrow<false><<<148 * kNarrowCtasPerSm, kNarrowThreads, 0, s>>>(c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands, c->d_rec_sorted,
                                                              c->d_obb, c->d_pairs, nullptr, c->max_pairs, fb);
-        k_wide_pairs<<<kGridStrideBlocks, kNarrowThreads, 0, s>>>(c->n_local, c->d_wide, c->d_rec, c->d_obb, c->d_pairs,
-                                                                c->d_contacts, c->max_pairs, fb);
+        k_wide_pairs<<<148 * 2, kNarrowThreads, 0, s>>>(c->n_local, c->d_wide, c->d_rec, c->d_obb, c->d_pairs, c->d_contacts,
+                                                       c->max_pairs, fb);  // (normally no wide volumes: exits at once)
         if (timing) CU(c, cudaEventRecord(c->ev[6], s));
     } else if (timing) {
         for (int i = 2; i <= GSC_NUM_STAGES; ++i) CU(c, cudaEventRecord(c->ev[i], s));
