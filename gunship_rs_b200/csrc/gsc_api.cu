@@ -122,7 +122,7 @@ struct gsc_ctx {
     SlabMail *d_mail = nullptr;
     uint32_t slab_rank = 0, slab_world = 0, slab_seq = 0;
     bool slab_ready = false, slab_step = false;  // slab_step: the step in flight / last collected ran the device-driven exchange
-    unsigned long long peer_timeout_ns = 5000000000ull;
+    unsigned long long peer_timeout_ns = 20000000000ull;  // GSC_PEER_TIMEOUT_MS
     cudaEvent_t ev_slab[2] = { nullptr, nullptr };  // behind the publish / behind the done flags (in-process groups order on them)
 
     uint64_t max_pairs = 0, max_cands = 0, max_cells = 0;
@@ -233,6 +233,7 @@ int status_to_error(gsc_ctx *c, const FrameBlock &fb)
     if (st & kStCellSize) return fail(c, GSC_ERR_RANGE, "cell size (longest AABB axis) is not positive: %g", (double)fb.grid.cell_size);
     if (st & kStRange) return fail(c, GSC_ERR_RANGE, "a grid coordinate leaves the i16 range of GridCoord (grid_collision.rs:535)");
     if (st & kStWindow) return fail(c, GSC_ERR_INVALID, "gsc_set_x_window does not cover the home cell of a local collider");
+    if (st & kStCheck) return fail(c, GSC_ERR_CUDA, "internal bounds check failed (GSC_CHECKED build)");
     if (st & kStWideBorder)
         return fail(c, GSC_ERR_RANGE, "a volume whose AABB spans 3 cells (rounding; gsc_step_out.n_wide) lies on a slab border: "
                                       "multi-GPU steps match such volumes inside their own slab only");

@@ -37,7 +37,18 @@ enum : uint32_t {
     kStPeerTimeout = 1u << 8,  // a peer GPU did not publish its bounds / finish its halo push in time
     kStGhostCap = 1u << 9,     // local + pushed ghost volumes exceed the context's capacity
     kStWideBorder = 1u << 10,  // a 3-cell-wide volume touches a slab border: its cross-slab pairs would be lost
+    kStCheck = 1u << 11,       // -DGSC_CHECKED builds only: an internal bounds check failed (see GSC_CHECK)
 };
+
+// compute-sanitizer is closed on the pool this was developed on, so the kernels carry their own bounds checks for the
+// places that do raw address arithmetic (shared-memory slot addresses, staged indices, scatter destinations, peer
+// writes).  A -DGSC_CHECKED build (tools/checked_build.sh) evaluates them and reports a failure through the status word
+// -- the step then fails with GSC_ERR_CUDA -- instead of trapping; the production build compiles them away.
+#ifdef GSC_CHECKED
+#define GSC_CHECK(fb_, cond) do { if (!(cond)) atomicOr(&(fb_)->status, kStCheck); } while (0)
+#else
+#define GSC_CHECK(fb_, cond) do { } while (0)
+#endif
 
 // ---- volume record: 32 B = 2 x float4, the unit the broadphase streams ----
 //   sphere: r0 = (cx, cy, cz, radius)          r1 = (entity bits, 0, global index bits, meta)
@@ -565,6 +576,7 @@ k_cell_table_permute(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const u
                 const uint32_t k = __shfl_sync(0xffffffffu, kcur, j + step - 1);
                 if (k < c) j += step;
             }
+            GSC_CHECK(fb, c > last || (c <= C && p0 + j <= n_total));
             if (c <= last) cell_start[c] = p0 + j;
         }
         return;
@@ -873,7 +885,7 @@ GSC_DEV void halo_push_cta(uint32_t n_local, const float4 *__restrict__ rec, con
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(&s_count, (uint32_t)__popc(m));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (sel) s_list[base + __popc(m & ((1u << lane) - 1u))] = i;
+            if (sel) s_list[min(base + __popc(m & ((1u << lane) - 1u)), (uint32_t)kPushList - 1u)] = i;
         }
         __syncthreads();
         const uint32_t cnt = s_count;

@@ -386,6 +386,7 @@ k_pairs_tiled(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const uint32_t
         for (int r = 0; r <= kPairRows; ++r) {
             if (rl[r]) {
                 const int row = r < kPairRows ? r : kPairRows - 1;
+                GSC_CHECK(fb, ri < (uint32_t)kTileRuns && rb[r] >= seg_lo[row] && seg_off[row] + (rb[r] - seg_lo[row]) + rl[r] <= seg_off[row + 1]);
                 sh.run[ri] = make_uint4(P, seg_off[row] + (rb[r] - seg_lo[row]), rl[r], (uint32_t)tid | (r == kPairRows ? 0x80000000u : 0u));
                 ++ri;
                 P += rl[r];
@@ -430,12 +431,14 @@ k_pairs_tiled(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const uint32_t
                     }
                     // quantised AABB::test_aabb (bounding_volume.rs:338-343, 411-419; inclusive): three packed
                     // differences per subtraction, overlap on every axis iff no field went negative
+                    GSC_CHECK(fb, sidx < seg_off[kPairRows] && i < R && (tag & 0xffffu) < (uint32_t)kTileA);
                     const uint2 b = sh.cand[sidx];
                     const uint32_t t1 = aq.y - b.x;  // A.qmax - B.qmin per axis
                     const uint32_t t2 = b.y - aq.x;  // B.qmax - A.qmin per axis
                     bool pass = ((t1 | t2) & kQSign) == 0u;
                     if (tag >> 31) pass = pass && sh.cand_w3[sidx - own_off] < aw3;  // same cell: the later global index takes the pair
                     if (pass) {
+                        GSC_CHECK(fb, pa - pa0 < kTilePriv * kSlotStride && (!(tag >> 31) || sidx - own_off < own_len));
                         asm volatile("st.shared.u32 [%0], %1;" ::"r"(pa), "r"((tag << 16) | sidx) : "memory");
                         pa += kSlotStride;
                     }
@@ -588,6 +591,7 @@ k_pairs(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const uint32_t *__re
             const uint32_t t1 = a_maxg - b.x;  // A.qmax - B.qmin per axis
             const uint32_t t2 = b.y - a_min;   // B.qmax - A.qmin per axis
             if ((((t1 | t2) & kQSign) == 0u) && take) {
+                GSC_CHECK(fb, pa - pa0 < kPairPriv * kSlotStride && q < n_total);
                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(pa), "r"(q) : "memory");
                 pa += kSlotStride;
             }

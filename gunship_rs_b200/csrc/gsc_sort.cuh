@@ -292,6 +292,9 @@ k_radix_downsweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
         if (i < valid) {
             const uint32_t k = s_keys[i];
             const uint32_t dst = s_goff[(k >> shift) & mask] + i;
+#ifdef GSC_CHECKED
+            if (dst >= n) { asm volatile("trap;"); }  // (the sort has no status word: a checked build traps)
+#endif
             keys_out[dst] = k;
             vals_out[dst] = s_vals[i];
         }

@@ -471,6 +471,9 @@ def bench_multi_gpu(args, n, rank, world, local_rank, metric, unit, workload_nam
         ctx.upload_colliders(scene.entity[mine], scene.kind[mine], scene.offset[mine], scene.size[mine],
                              global_index=mine.astype(np.uint32))
         finish_frames()
+        # the ranks step together (the device-side waits carry a time limit): line them up after the host-side set-up,
+        # whose duration differs from rank to rank by seconds
+        dist.barrier()
 
     def finish_frames():
         # the host layer marshals rotation / scale for the boxes only (spheres ignore them, mod.rs:313-317)
@@ -548,6 +551,7 @@ def bench_multi_gpu(args, n, rank, world, local_rank, metric, unit, workload_nam
             part["h_quat"][f].copy_(part["h_quat"][f][order])
         part["h_scale"] = part["h_scale"][order].contiguous().pin_memory()
         finish_frames()
+        dist.barrier()
     h_pos, h_quat, h_bquat, h_bscale, n_box = part["h_pos"], part["h_quat"], part["h_bquat"], part["h_bscale"], part["n_box"]
     for i in range(args.warmup):
         step_resident(i)

@@ -37,7 +37,7 @@ enum {
     GSC_ERR_INVALID  = 1, /* bad argument / call order */
     GSC_ERR_CUDA     = 2, /* CUDA runtime failure (message in gsc_last_error) */
     GSC_ERR_NCCL     = 3, /* multi-GPU exchange failure: a peer GPU did not arrive within the time limit
-                             (gsc_slab_step / gsc_group_step; GSC_PEER_TIMEOUT_MS, default 5000) */
+                             (gsc_slab_step / gsc_group_step; GSC_PEER_TIMEOUT_MS, default 20000) */
     GSC_ERR_CAPACITY = 4, /* pair / candidate / cell-table capacity exceeded; needed sizes are in gsc_step_out */
     GSC_ERR_RANGE    = 5, /* a grid coordinate leaves i16 (grid_collision.rs:530-535), cell size is not
                              positive, or an input is NaN/Inf -- the reference's behaviour is undefined there */

@@ -77,6 +77,31 @@ def test_two_ranks_report_the_single_context_pair_set(tmp_path, cfg, n, ownershi
     oracle.close()
 
 
+@pytest.mark.parametrize("world,cfg,n", [(2, 4, 1 << 21), (4, 4, 1 << 21), (8, 3, 400000)])
+def test_one_rank_per_gpu_device_driven_exchange(tmp_path, world, cfg, n):
+    """`world` processes on `world` DIFFERENT GPUs (skipped on smaller boxes): the exchange runs on the device (k_slab_*,
+    CUDA IPC mailboxes, one host wait per step) and the union of the ranks' lists is the oracle's set -- at 2M colliders
+    for 2 and 4 ranks (the N-GPU union had only been checked at 2 ranks and 60k)."""
+    import torch
+    import torch.multiprocessing as mp
+    import oracle_lib as O
+    from gunship_rs_b200 import scenes
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    frames = (0, 1)
+    mp.spawn(_worker, args=(world, _free_port(), cfg, n, frames, str(tmp_path), "slabs", True), nprocs=world, join=True)
+    s = scenes.by_config(cfg, n)
+    oracle = O.OracleSystem()
+    for f in frames:
+        pos, quat = s.frame(f)
+        want = oracle.step(s, pos, quat)
+        parts = [np.load(tmp_path / f"pairs_slabs_{f}_{r}.npy") for r in range(world)]
+        got = np.sort(np.concatenate(parts))
+        assert len(got) == len(want) and np.array_equal(got, want)
+        assert all(len(p) > 0 for p in parts)
+    oracle.close()
+
+
 def test_phase_calls_single_rank_equal_gsc_step():
     """gsc_phase_bounds / gsc_set_global_bounds / gsc_local_x_range / gsc_set_x_window / gsc_phase_finish on ONE context
     reproduce gsc_step; a window that misses a local collider is rejected."""
