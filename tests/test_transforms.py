@@ -119,6 +119,12 @@ def test_cuda_hierarchy_is_bit_exact_and_feeds_the_step():
             assert pairs.shape[0] > 50
             assert out.n_pairs == pairs.shape[0] and np.array_equal(ctx.pairs_packed(), pairs)
         sysm.close()
+        # a NEW hierarchy (same size: the buffers are reused) must not inherit the previous one's local transforms:
+        # "NULL keeps the previous values" is refused until all three arrays were sent again
+        ctx.hierarchy_upload(rb, parent, node)
+        with pytest.raises(N.GscError):
+            ctx.hierarchy_update(lpos, None, None)
+        ctx.hierarchy_update(lpos, lquat, lscale)
         # error paths: a parent outside the previous row; an update after the collider set changed
         bad = parent.copy()
         bad[-1] = 0
