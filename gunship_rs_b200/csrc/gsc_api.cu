@@ -86,7 +86,6 @@ struct gsc_ctx {
     uint32_t *d_cell_start = nullptr, *d_wide = nullptr;
     uint32_t *d_overflow = nullptr;  // tiles of the pairs stage that did not fit its staging buffers
     bool pairs_tiled = false;        // GSC_PAIRS_TILED=1: the tile-staged, work-flattened pairs kernel (measured slower, see DESIGN)
-    bool fuse_ss = false;            // GSC_FUSE_SS=1 (with GSC_PAIRS_TILED=1): sphere-sphere pairs decided in the pairs tail (measured slower)
     uint4 *d_gaps = nullptr;
     bool have_window = false;
     int32_t win_lo = 0, win_hi = 0;
@@ -335,8 +334,6 @@ int gsc_create(const gsc_config *cfg, gsc_ctx **out)
     {
         const char *e = getenv("GSC_PAIRS_TILED");
         c->pairs_tiled = e && e[0] == '1';
-        e = getenv("GSC_FUSE_SS");
-        c->fuse_ss = c->pairs_tiled && e && e[0] == '1';
     }
     CR(dmalloc(&c->d_gaps, (size_t)kGapCap));
     CR(dmalloc(&c->d_pairs, c->max_pairs));
@@ -730,16 +727,16 @@ static int stage_launches(gsc_ctx *c, bool slab, bool timing)
         if (timing) CU(c, cudaEventRecord(c->ev[4], s));
         // sphere-sphere pairs are decided inside the pairs stage unless a contact has to be computed for them
         PairOut po{ c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands };
-        if (c->pairs_tiled) {
-            // (experimental, measured slower than k_pairs: DESIGN section 4) sphere-sphere pairs may be decided in its tail
-            PairFuse pf{ c->d_pairs, c->max_pairs };
-            const int fuse = (c->fuse_ss && !c->d_contacts) ? 1 : 0;
-            k_pairs_tiled<<<(n_launch + kTileA - 1) / kTileA, kTileA, sizeof(TileShared), s>>>(n_launch, n_dev, c->d_keys[0], c->d_keys[1], sv,
-                                                                                            c->d_cell_start, po, pf, fuse, c->d_overflow, fb);
+        if (c->pairs_tiled) {  // (experimental, measured slower than k_pairs: DESIGN section 4)
+            k_pairs_tiled<<<(n_launch + kTileA - 1) / kTileA, kTileA, sizeof(TileShared), s>>>(n_launch, n_dev, c->d_keys[0], c->d_keys[1],
+                                                                                            c->d_vals[0], c->d_vals[1], sv, c->d_cell_start,
+                                                                                            po, c->d_overflow, fb);
             // tiles too dense for the staging buffers (normally none: the kernel exits at once)
-            k_pairs<true><<<148 * 16, kPairThreads, 0, s>>>(n_launch, n_dev, c->d_keys[0], c->d_keys[1], sv, c->d_cell_start, po, c->d_overflow, fb);
+            k_pairs<true><<<148 * 16, kPairThreads, 0, s>>>(n_launch, n_dev, c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1], sv,
+                                                            c->d_cell_start, po, c->d_overflow, fb);
         } else {
-            k_pairs<false><<<(n_launch + kPairThreads - 1) / kPairThreads, kPairThreads, 0, s>>>(n_launch, n_dev, c->d_keys[0], c->d_keys[1], sv,
+            k_pairs<false><<<(n_launch + kPairThreads - 1) / kPairThreads, kPairThreads, 0, s>>>(n_launch, n_dev, c->d_keys[0], c->d_keys[1],
+                                                                                              c->d_vals[0], c->d_vals[1], sv,
                                                                                               c->d_cell_start, po, nullptr, fb);
         }
         if (timing) CU(c, cudaEventRecord(c->ev[5], s));
@@ -815,7 +812,7 @@ static int stage_collect(gsc_ctx *c, gsc_step_out *out)
     if (out) {
         memset(out, 0, sizeof *out);
         out->n_pairs = h.n_pairs;
-        out->n_sphere_sphere = (c->d_contacts || !c->fuse_ss) ? h.n_ss : h.n_ss_fused;  // (fuse_ss implies pairs_tiled)
+        out->n_sphere_sphere = h.n_ss;
         out->n_sphere_obb = h.n_so;
         out->n_obb_obb = h.n_oo;
         out->n_cells = h.grid.num_cells;

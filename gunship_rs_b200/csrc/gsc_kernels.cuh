@@ -140,7 +140,7 @@ struct FrameBlock {
     uint32_t n_total;     // local + ghost volumes of this step (k_grid_setup); kernels launched for a capacity clamp to it
     uint32_t n_overflow;  // tiles k_pairs_tiled could not stage (queued for k_pairs)
     uint32_t pad1;
-    unsigned long long n_ss_fused;  // AABB-overlapping sphere-sphere candidates decided inside the pairs stage
+    unsigned long long reserved0;
     GridParams grid;
     SortControl sort;
     SlabState slab;
@@ -672,7 +672,13 @@ k_narrow(const uint2 *__restrict__ cand_ss, const uint2 *__restrict__ cand_so, c
                     uint32_t ea, eb;
                     const Obb a = obb_load(obb + 4 * (size_t)c.x, &ea);
                     const Obb bb = obb_load(obb + 4 * (size_t)c.y, &eb);
-                    hit = test_obb_obb(a, bb);
+                    // BoundVolume::test runs AABB::test_aabb first (bounding_volume.rs:124-132).  The candidates only passed
+                    // the conservative quantised filter; the exact AABBs are re-derived here, bit for bit, with the function
+                    // bvh_update used on the very same OBB records (AABB::from_collider, bounding_volume.rs:161-327)
+                    float amn[3], amx[3], bmn[3], bmx[3];
+                    obb_aabb_fast(a, amn, amx);
+                    obb_aabb_fast(bb, bmn, bmx);
+                    hit = test_aabb(amn, amx, bmn, bmx) && test_obb_obb(a, bb);
                     item = make_uint2(ea, eb);
                     if (CONTACTS && hit) ct = contact_obb_obb(a, bb);
                 } else if (cls == 1) {  // Sphere::test_obb (mod.rs:391-394): either order calls sphere.test_obb(obb) (mod.rs:378,407)
@@ -683,13 +689,22 @@ k_narrow(const uint2 *__restrict__ cand_ss, const uint2 *__restrict__ cand_so, c
                     const float4 s0 = ldg_gather(srec + 2 * (size_t)si), s1 = ldg_gather(srec + 2 * (size_t)si + 1);
                     uint32_t oe;
                     const Obb o = obb_load(obb + 4 * (size_t)oi, &oe);
-                    hit = test_sphere_obb(s0.x, s0.y, s0.z, s0.w, o);
+                    float omn[3], omx[3];
+                    obb_aabb_fast(o, omn, omx);
+                    // a sphere's AABB: centre -+ (r, r, r) (bounding_volume.rs:150-159)
+                    const float smn[3] = { sub(s0.x, s0.w), sub(s0.y, s0.w), sub(s0.z, s0.w) };
+                    const float smx[3] = { add(s0.x, s0.w), add(s0.y, s0.w), add(s0.z, s0.w) };
+                    hit = test_aabb(smn, smx, omn, omx) && test_sphere_obb(s0.x, s0.y, s0.z, s0.w, o);
                     const uint32_t se = __float_as_uint(s1.x);
                     item = hi_is_sphere ? make_uint2(se, oe) : make_uint2(oe, se);
                     if (CONTACTS && hit) ct = contact_sphere_obb(s0.x, s0.y, s0.z, s0.w, o, hi_is_sphere);
                 } else {  // Sphere::test_sphere (mod.rs:383-389)
                     const float4 h0 = ldg_gather(srec + 2 * (size_t)c.x), l0 = ldg_gather(srec + 2 * (size_t)c.y);
-                    hit = test_sphere_sphere(h0.x, h0.y, h0.z, h0.w, l0.x, l0.y, l0.z, l0.w);
+                    const float hmn[3] = { sub(h0.x, h0.w), sub(h0.y, h0.w), sub(h0.z, h0.w) };
+                    const float hmx[3] = { add(h0.x, h0.w), add(h0.y, h0.w), add(h0.z, h0.w) };
+                    const float lmn[3] = { sub(l0.x, l0.w), sub(l0.y, l0.w), sub(l0.z, l0.w) };
+                    const float lmx[3] = { add(l0.x, l0.w), add(l0.y, l0.w), add(l0.z, l0.w) };
+                    hit = test_aabb(hmn, hmx, lmn, lmx) && test_sphere_sphere(h0.x, h0.y, h0.z, h0.w, l0.x, l0.y, l0.z, l0.w);
                     if (hit) {
                         const float4 h1 = ldg_gather(srec + 2 * (size_t)c.x + 1), l1 = ldg_gather(srec + 2 * (size_t)c.y + 1);
                         item = make_uint2(__float_as_uint(h1.x), __float_as_uint(l1.x));

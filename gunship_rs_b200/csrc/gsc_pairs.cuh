@@ -24,49 +24,44 @@
 //   k_pairs        the round-1 thread-per-volume walk through L1, kept for tiles whose segments do not fit the
 //                  staging buffers (hundreds of volumes per cell): k_pairs_tiled queues such tiles, k_pairs runs
 //                  persistently over the queue (normally empty: it exits at once).
-// Both end in the same tail: the survivors of the quantised filter take the exact inclusive AABB test on the
-// cell-ordered records, are classified by shape pair and oriented by global index; sphere-sphere pairs are decided
-// on the spot (Sphere::test_sphere, mod.rs:383-389 -- both records are in registers already), sphere-box and box-box
-// pairs are appended to the candidate lists of the SAT stage.
+// Both end in the same tail: the survivors of the quantised filter are classified by shape pair and oriented by global
+// index from their 4 B ordering words alone and appended to the three candidate lists of the SAT stage, which runs the
+// EXACT inclusive AABB test (on AABBs it re-derives bit for bit from the records it loads anyway) before the shape test.
+// (Round 2 measured two alternatives and dropped them: the exact test on the 32 B cell-ordered records in this tail --
+// 4 dependent 16 B gathers per survivor, 25% of the kernel's instructions, 31% of its stall samples -- and deciding
+// sphere-sphere pairs right here: +0.13 ms in this kernel for -0.01 ms in k_narrow.)
 #pragma once
 
 namespace gsc {
 
 struct PairOut {
-    uint2 *cand_ss;   // sphere-sphere candidates
+    uint2 *cand_ss;   // sphere-sphere candidates (pairs that passed the conservative quantised AABB filter)
     uint2 *cand_so;
     uint2 *cand_oo;
     unsigned long long cap_cands;
 };
-// k_pairs_tiled only: sphere-sphere pairs decided in the tail (GSC_FUSE_SS=1) are appended to the contact pairs directly
-struct PairFuse {
-    uint2 *pairs;
-    unsigned long long cap_pairs;
+// what the tail needs to classify a filtered pair WITHOUT touching the 32 B volume records: the 4 B ordering words
+// (gidx << 4 | flags: box bit, global index) and the sort's index stream (local index of a sorted position)
+struct PairRefs {
+    const uint32_t *w3;
+    const uint32_t *vals;
 };
 
-// AABB of a cell-ordered record.  sphere: centre -+ (r,r,r) exactly as AABB::from_collider computes it
-// (bounding_volume.rs:150-159); box: stored.
-GSC_DEV void rec_aabb(const float4 r0, const float4 r1, float mn[3], float mx[3])
+// Classify + orient a filtered (A at sorted position p, B at q) pair from the ordering words alone.  The EXACT
+// AABB::test_aabb (bounding_volume.rs:338-343) is not run here: the SAT stage re-derives both AABBs bit for bit from the
+// records it loads anyway (a sphere's from centre -+ radius, a box's with obb_aabb_fast from its OBB record -- the very
+// function and inputs bvh_update used) and tests them before the shape test.  Round 2: this took four dependent 16 B
+// gathers per survivor and their decode out of the pairs kernel (its tail was 25% of the instructions and 31% of the
+// stall samples).
+// A sphere is addressed by its cell-ordered POSITION (its record is read from the cell-ordered array, where both
+// members of a pair are at most a cell row apart), a box by its local index (its OBB record lives in collider order).
+// item = (later volume [| sphere flag], earlier volume); returns the class 0 sphere-sphere, 1 sphere-box, 2 box-box.
+GSC_DEV int pair_classify(uint32_t p, uint32_t q, PairRefs refs, uint2 *item)
 {
-    if (__float_as_uint(r1.w) & kMetaBox) {
-        mn[0] = r0.x; mn[1] = r0.y; mn[2] = r0.z;
-        mx[0] = r0.w; mx[1] = r1.x; mx[2] = r1.y;
-    } else {
-        mn[0] = sub(r0.x, r0.w); mn[1] = sub(r0.y, r0.w); mn[2] = sub(r0.z, r0.w);
-        mx[0] = add(r0.x, r0.w); mx[1] = add(r0.y, r0.w); mx[2] = add(r0.z, r0.w);
-    }
-}
-
-// orient a surviving (A, B) pair.  A sphere is addressed by its cell-ordered POSITION (its record is read from the
-// cell-ordered array, where both members of a pair are at most a cell row apart), a box by its local index (its OBB
-// record lives in collider order).  item = (later volume [| sphere flag], earlier volume); returns the class
-// 0 sphere-sphere, 1 sphere-box, 2 box-box.
-GSC_DEV int pair_classify(uint32_t a_pos, uint32_t a_gidx, uint32_t a_meta, uint32_t b_pos, uint32_t b_gidx, uint32_t b_meta,
-                          uint2 *item)
-{
-    const bool a_box = a_meta & kMetaBox, b_box = b_meta & kMetaBox;
-    const bool a_hi = a_gidx > b_gidx;  // tuple = (later index, earlier index), grid_collision.rs:440,497
-    const uint32_t a_ref = a_box ? a_meta >> 4 : a_pos, b_ref = b_box ? b_meta >> 4 : b_pos;
+    const uint32_t aw = __ldg(refs.w3 + p), bw = __ldg(refs.w3 + q);
+    const bool a_box = aw & kMetaBox, b_box = bw & kMetaBox;
+    const bool a_hi = (aw >> 4) > (bw >> 4);  // tuple = (later index, earlier index), grid_collision.rs:440,497
+    const uint32_t a_ref = a_box ? __ldg(refs.vals + p) : p, b_ref = b_box ? __ldg(refs.vals + q) : q;
     uint32_t hi = a_hi ? a_ref : b_ref;
     const uint32_t lo = a_hi ? b_ref : a_ref;
     const int cls = (int)a_box + (int)b_box;
@@ -75,106 +70,62 @@ GSC_DEV int pair_classify(uint32_t a_pos, uint32_t a_gidx, uint32_t a_meta, uint
     return cls;
 }
 
-// exact test + classification of one filtered (A at sorted position p, B at q) pair.
-//   returns 0 sphere-sphere HIT when fuse_ss (item = entities), else sphere-sphere candidate; 1; 2; 3 = nothing to emit.
-//   *was_ss: the pair was an AABB-overlapping sphere-sphere candidate (statistics)
-template <bool FUSE>
-GSC_DEV int pair_decide(uint32_t p, uint32_t q, const float4 *__restrict__ sv, uint2 *item, bool *was_ss)
-{
-    const float4 a0 = __ldg(sv + 2 * (size_t)p), a1 = __ldg(sv + 2 * (size_t)p + 1);
-    const float4 c0 = __ldg(sv + 2 * (size_t)q), c1 = __ldg(sv + 2 * (size_t)q + 1);
-    float amn[3], amx[3], cmn[3], cmx[3];
-    rec_aabb(a0, a1, amn, amx);
-    rec_aabb(c0, c1, cmn, cmx);
-    *was_ss = false;
-    // the exact AABB::test_aabb (bounding_volume.rs:338-343, 411-419), inclusive
-    if (amn[0] > cmx[0] || cmn[0] > amx[0] || amn[1] > cmx[1] || cmn[1] > amx[1] || amn[2] > cmx[2] || cmn[2] > amx[2]) return 3;
-    const uint32_t ag = __float_as_uint(a1.z), cg = __float_as_uint(c1.z);
-    const int cls = pair_classify(p, ag, __float_as_uint(a1.w), q, cg, __float_as_uint(c1.w), item);
-    if (cls == 0) {
-        *was_ss = true;
-        if (FUSE) {
-            const bool a_hi = ag > cg;
-            const float4 h = a_hi ? a0 : c0, l = a_hi ? c0 : a0;
-            if (!test_sphere_sphere(h.x, h.y, h.z, h.w, l.x, l.y, l.z, l.w)) return 3;
-            *item = a_hi ? make_uint2(__float_as_uint(a1.x), __float_as_uint(c1.x)) : make_uint2(__float_as_uint(c1.x), __float_as_uint(a1.x));
-        }
-    }
-    return cls;
-}
-
-// slow path of a full CTA list: decide and append one pair straight to the global lists
-template <bool FUSE>
-__device__ __noinline__ void pair_spill(uint32_t p, uint32_t q, const float4 *__restrict__ sv, PairOut out, PairFuse fuse, FrameBlock *fb)
+// slow path of a full CTA list: classify and append one pair straight to the global lists
+__device__ __noinline__ void pair_spill(uint32_t p, uint32_t q, PairRefs refs, PairOut out, FrameBlock *fb)
 {
     uint2 item;
-    bool was_ss;
-    const int cls = pair_decide<FUSE>(p, q, sv, &item, &was_ss);
-    if (FUSE && was_ss) atomicAdd(&fb->n_ss_fused, 1ull);
-    if (cls == 3) return;
-    if (FUSE && cls == 0) {
-        const unsigned long long at = atomicAdd(&fb->n_pairs, 1ull);
-        if (at < fuse.cap_pairs) fuse.pairs[at] = item;
-        return;
-    }
+    const int cls = pair_classify(p, q, refs, &item);
     unsigned long long *ctr = cls == 0 ? &fb->n_ss : (cls == 1 ? &fb->n_so : &fb->n_oo);
     uint2 *dst = cls == 0 ? out.cand_ss : (cls == 1 ? out.cand_so : out.cand_oo);
     const unsigned long long at = atomicAdd(ctr, 1ull);
     if (at < out.cap_cands) dst[at] = item;
 }
 
-// ---- the common tail: decide + append a CTA's filtered pairs ---------------------------------------------------
+// ---- the common tail: classify + append a CTA's filtered pairs -------------------------------------------------
 template <int WARPS>
 struct TailShared {
-    uint32_t warp_cls[WARPS][4];
+    uint32_t warp_cls[WARPS][3];
     unsigned long long base[3];
 };
 
 // `fetch(i)` yields the i-th listed pair as (p, q) sorted positions.  All threads of the CTA call.
-template <int THREADS, bool FUSE, class Fetch>
-GSC_DEV void pairs_tail(uint32_t have, Fetch fetch, const float4 *__restrict__ sv, const PairOut &out, const PairFuse &fuse,
-                        FrameBlock *__restrict__ fb, TailShared<THREADS / 32> &ts)
+template <int THREADS, class Fetch>
+GSC_DEV void pairs_tail(uint32_t have, Fetch fetch, PairRefs refs, const PairOut &out, FrameBlock *__restrict__ fb,
+                        TailShared<THREADS / 32> &ts)
 {
     constexpr int WARPS = THREADS / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (uint32_t base = 0; base < have; base += THREADS) {
         const uint32_t i = base + tid;
         int cls = 3;
-        bool was_ss = false;
         uint2 item = make_uint2(0, 0);
         if (i < have) {
             const uint2 e = fetch(i);
-            cls = pair_decide<FUSE>(e.x, e.y, sv, &item, &was_ss);
+            cls = pair_classify(e.x, e.y, refs, &item);
         }
-        uint32_t m[4], rank = 0;
+        uint32_t m[3], rank = 0;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             m[c] = __ballot_sync(0xffffffffu, cls == c);
             if (cls == c) rank = __popc(m[c] & ((1u << lane) - 1u));
         }
-        if (FUSE) m[3] = __ballot_sync(0xffffffffu, was_ss);
-        if (lane < (FUSE ? 4 : 3)) ts.warp_cls[warp][lane] = __popc(m[lane]);
+        if (lane < 3) ts.warp_cls[warp][lane] = __popc(m[lane]);
         __syncthreads();
-        if (tid < (FUSE ? 4 : 3)) {
+        if (tid < 3) {
             uint32_t tot = 0;
             for (int w = 0; w < WARPS; ++w) {
                 const uint32_t c = ts.warp_cls[w][tid];
                 ts.warp_cls[w][tid] = tot;
                 tot += c;
             }
-            if (tid == 3) {
-                if (tot) atomicAdd(&fb->n_ss_fused, (unsigned long long)tot);
-            } else {
-                unsigned long long *ctr = tid == 0 ? (FUSE ? &fb->n_pairs : &fb->n_ss) : (tid == 1 ? &fb->n_so : &fb->n_oo);
-                ts.base[tid] = tot ? atomicAdd(ctr, (unsigned long long)tot) : 0ull;
-            }
+            unsigned long long *ctr = tid == 0 ? &fb->n_ss : (tid == 1 ? &fb->n_so : &fb->n_oo);
+            ts.base[tid] = tot ? atomicAdd(ctr, (unsigned long long)tot) : 0ull;
         }
         __syncthreads();
         if (cls < 3) {
-            const bool to_pairs = cls == 0 && FUSE;
-            uint2 *dst = cls == 0 ? (FUSE ? fuse.pairs : out.cand_ss) : (cls == 1 ? out.cand_so : out.cand_oo);
+            uint2 *dst = cls == 0 ? out.cand_ss : (cls == 1 ? out.cand_so : out.cand_oo);
             const unsigned long long at = ts.base[cls] + ts.warp_cls[warp][cls] + rank;
-            if (at < (to_pairs ? fuse.cap_pairs : out.cap_cands)) dst[at] = item;
+            if (at < out.cap_cands) dst[at] = item;
         }
         __syncthreads();
     }
@@ -265,8 +216,9 @@ GSC_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory
 
 __global__ void __launch_bounds__(kTileA, GSC_TILE_CTAS)
 k_pairs_tiled(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ keys_b,
-              SortedVolumes sv, const uint32_t *__restrict__ cell_start, PairOut out, PairFuse fuse, int fuse_ss,
-              uint32_t *__restrict__ overflow_tiles, FrameBlock *__restrict__ fb)
+              const uint32_t *__restrict__ vals_a, const uint32_t *__restrict__ vals_b, SortedVolumes sv,
+              const uint32_t *__restrict__ cell_start, PairOut out, uint32_t *__restrict__ overflow_tiles,
+              FrameBlock *__restrict__ fb)
 {
     extern __shared__ __align__(16) unsigned char tile_smem[];
     TileShared &sh = *reinterpret_cast<TileShared *>(tile_smem);
@@ -276,6 +228,7 @@ k_pairs_tiled(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const uint32_t
     const uint32_t p0 = blockIdx.x * (uint32_t)kTileA;
     if (p0 >= n_total) return;
     const uint32_t *keys = (fb->sort.num_passes & 1) ? keys_b : keys_a;
+    const PairRefs refs{ sv.w3, (fb->sort.num_passes & 1) ? vals_b : vals_a };
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid < kPairRows) {
         sh.seg_lo[tid] = 0xffffffffu;
@@ -453,8 +406,7 @@ k_pairs_tiled(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const uint32_t
                 for (uint32_t j = 0; j < have; ++j) {
                     const uint32_t w = sh.priv[j * kTileA + tid];
                     if (at + j < (uint32_t)kTileList) sh.list[at + j] = w;
-                    else if (fuse_ss) pair_spill<true>(p0 + (w >> 16), global_pos(w & 0xffffu), sv.v, out, fuse, fb);
-                    else pair_spill<false>(p0 + (w >> 16), global_pos(w & 0xffffu), sv.v, out, fuse, fb);
+                    else pair_spill(p0 + (w >> 16), global_pos(w & 0xffffu), refs, out, fb);
                 }
                 pa = pa0;
             }
@@ -477,8 +429,7 @@ k_pairs_tiled(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const uint32_t
         for (uint32_t j = 0; j < have; ++j) {
             const uint32_t w = sh.priv[j * kTileA + tid];
             if (at + j < (uint32_t)kTileList) sh.list[at + j] = w;
-            else if (fuse_ss) pair_spill<true>(p0 + (w >> 16), global_pos(w & 0xffffu), sv.v, out, fuse, fb);
-            else pair_spill<false>(p0 + (w >> 16), global_pos(w & 0xffffu), sv.v, out, fuse, fb);
+            else pair_spill(p0 + (w >> 16), global_pos(w & 0xffffu), refs, out, fb);
         }
     }
     __syncthreads();
@@ -489,8 +440,7 @@ k_pairs_tiled(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const uint32_t
         const uint32_t w = sh.list[i];
         return make_uint2(p0 + (w >> 16), global_pos(w & 0xffffu));
     };
-    if (fuse_ss) pairs_tail<kTileA, true>(listed, fetch, sv.v, out, fuse, fb, sh.tail);
-    else pairs_tail<kTileA, false>(listed, fetch, sv.v, out, fuse, fb, sh.tail);
+    pairs_tail<kTileA>(listed, fetch, refs, out, fb, sh.tail);
 }
 
 // =================================================================================================================
@@ -524,14 +474,13 @@ struct PairShared {
 };
 
 // a lane whose private slots are (nearly) full moves them to the CTA list (rare: >= kPairPriv - 1 survivors)
-__device__ __noinline__ void pair_drain_lane(PairShared &sh, uint32_t p, uint32_t cnt, int tid, const float4 *__restrict__ sv,
-                                             PairOut out, FrameBlock *fb)
+__device__ __noinline__ void pair_drain_lane(PairShared &sh, uint32_t p, uint32_t cnt, int tid, PairRefs refs, PairOut out, FrameBlock *fb)
 {
     const uint32_t at = atomicAdd(&sh.count, cnt);
     for (uint32_t j = 0; j < cnt; ++j) {
         const uint32_t q = sh.priv[j * kPairThreads + tid];
         if (at + j < (uint32_t)kPairCap) sh.list[at + j] = make_uint2(p, q);
-        else pair_spill<false>(p, q, sv, out, PairFuse{ nullptr, 0 }, fb);
+        else pair_spill(p, q, refs, out, fb);
     }
 }
 
@@ -539,7 +488,8 @@ __device__ __noinline__ void pair_drain_lane(PairShared &sh, uint32_t p, uint32_
 // QUEUE == true: persistent CTAs over the tiles queued in out.overflow_tiles by k_pairs_tiled
 template <bool QUEUE>
 __global__ void __launch_bounds__(kPairThreads, QUEUE ? 16 : GSC_PAIR_MIN_CTAS)
-k_pairs(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ keys_b, SortedVolumes sv,
+k_pairs(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ keys_b,
+        const uint32_t *__restrict__ vals_a, const uint32_t *__restrict__ vals_b, SortedVolumes sv,
         const uint32_t *__restrict__ cell_start, PairOut out, const uint32_t *__restrict__ overflow_tiles, FrameBlock *__restrict__ fb)
 {
     __shared__ PairShared sh;
@@ -547,6 +497,7 @@ k_pairs(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const uint32_t *__re
     if (!g.valid) return;
     const uint32_t n_total = n_dev ? min(*n_dev, n_cap) : n_cap;  // (device-side count: slab steps only)
     const uint32_t *keys = (fb->sort.num_passes & 1) ? keys_b : keys_a;
+    const PairRefs refs{ sv.w3, (fb->sort.num_passes & 1) ? vals_b : vals_a };
     const int tid = threadIdx.x, lane = tid & 31;
     constexpr uint32_t kSlices = kTileA / kPairThreads;  // slices of kPairThreads volumes per tile
     const uint32_t n_slices = QUEUE ? fb->n_overflow * kSlices : gridDim.x;
@@ -598,7 +549,7 @@ k_pairs(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const uint32_t *__re
         };
         auto drain_if_full = [&]() {
             if (pa - pa0 > (kPairPriv - kPairTrip) * kSlotStride) {  // fewer than one trip of free slots left
-                pair_drain_lane(sh, p, (pa - pa0) / kSlotStride, tid, sv.v, out, fb);
+                pair_drain_lane(sh, p, (pa - pa0) / kSlotStride, tid, refs, out, fb);
                 pa = pa0;
             }
         };
@@ -645,14 +596,11 @@ k_pairs(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const uint32_t *__re
             for (uint32_t j = 0; j < cnt; ++j) {
                 const uint32_t q = sh.priv[j * kPairThreads + tid];
                 if (at + j < (uint32_t)kPairCap) sh.list[at + j] = make_uint2(p, q);
-                else pair_spill<false>(p, q, sv.v, out, PairFuse{ nullptr, 0 }, fb);
+                else pair_spill(p, q, refs, out, fb);
             }
         }
         __syncthreads();
-        // (sphere-sphere pairs stay with the SAT stage here: deciding them in this tail was measured 0.13 ms slower at 16M
-        // for 0.01 ms saved in k_narrow)
-        pairs_tail<kPairThreads, false>(min(sh.count, (uint32_t)kPairCap), [&](uint32_t i) { return sh.list[i]; }, sv.v, out,
-                                        PairFuse{ nullptr, 0 }, fb, sh.tail);
+        pairs_tail<kPairThreads>(min(sh.count, (uint32_t)kPairCap), [&](uint32_t i) { return sh.list[i]; }, refs, out, fb, sh.tail);
         if (!QUEUE) return;
         __syncthreads();
     }

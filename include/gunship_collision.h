@@ -61,8 +61,8 @@ enum {
     GSC_STAGE_CELL_KEYS  = 1, /* world_to_grid + cell keys + digit histograms */
     GSC_STAGE_SORT       = 2, /* radix sort of (cell, collider) */
     GSC_STAGE_CELL_TABLE = 3, /* cell start table + cell-order permutation of the volumes */
-    GSC_STAGE_PAIRS      = 4, /* neighbour-cell pair enumeration + AABB test -> candidate lists per shape pair */
-    GSC_STAGE_NARROW     = 5, /* sphere-sphere, sphere-OBB and OBB-OBB SAT over the candidates (+ wide volumes) */
+    GSC_STAGE_PAIRS      = 4, /* neighbour-cell pair enumeration + conservative AABB filter -> candidate lists per shape pair */
+    GSC_STAGE_NARROW     = 5, /* exact AABB test, then sphere-sphere, sphere-OBB and OBB-OBB SAT over the candidates (+ wide volumes) */
     GSC_NUM_STAGES       = 6
 };
 
@@ -80,9 +80,10 @@ typedef struct gsc_config {
 
 typedef struct gsc_step_out {
     uint64_t n_pairs;        /* contact pairs found (may exceed max_pairs on GSC_ERR_CAPACITY) */
-    uint64_t n_sphere_sphere;/* AABB-overlapping sphere/sphere candidates handed to the shape-test stage */
-    uint64_t n_sphere_obb;   /* AABB-overlapping sphere/box candidates handed to the SAT stage */
-    uint64_t n_obb_obb;      /* AABB-overlapping box/box candidates handed to the SAT stage */
+    uint64_t n_sphere_sphere;/* sphere/sphere candidates handed to the shape-test stage: pairs of neighbouring volumes that passed
+                                the conservative (quantised) AABB filter; that stage runs the exact AABB::test_aabb first */
+    uint64_t n_sphere_obb;   /* sphere/box candidates handed to the SAT stage (same definition) */
+    uint64_t n_obb_obb;      /* box/box candidates handed to the SAT stage (same definition) */
     uint64_t n_cells;        /* cells of the dense grid this frame */
     float    cell_size;      /* BoundingVolumeManager::longest_axis (bounding_volume.rs:365-381) */
     uint32_t n_wide;         /* volumes whose AABB spans > 2 cells on an axis (debug_assert grid_collision.rs:403-410) */
