@@ -126,10 +126,11 @@ def stage_bytes(n, f_box, n_cells, passes, n_pairs, n_so, n_oo, n_ss):
     b["cell_keys"] = n * 36
     # sort: pass 0 reads key 4 writes 8; later passes read 8 write 8
     b["sort"] = n * (12 + 16 * max(passes - 1, 0))
-    # cell table + permute: read key 4 + idx 4 + rec 32 (gather), write rec 32 + table 4 per cell
-    b["cell_table"] = n * 88 + n_cells * 4
-    # pairs: read sorted rec 32 + key 4 once (neighbour re-reads are served by L1/L2), write the candidate lists
-    b["pairs"] = n * 20 + (n_ss + n_so + n_oo) * 8
+    # cell table + permute: read key 4 + idx 4 + rec 32 (gather), write quantised box 8 + ordering word 4, table 4 per cell
+    b["cell_table"] = n * 52 + n_cells * 4
+    # pairs: read key 4 + quantised box 8 + ordering word 4 once (neighbour re-reads are served by L1/L2); per filtered
+    # pair the tail reads two ordering words and two indices (16) and writes the candidate (8)
+    b["pairs"] = n * 16 + (n_ss + n_so + n_oo) * 24
     # narrow: read candidates 8 + 2 x sphere rec 32 / sphere rec 32 + obb 64 / 2 x obb 64 per candidate, write hits
     b["narrow"] = n_ss * (8 + 64) + n_so * (8 + 96) + n_oo * (8 + 128) + n_pairs * 8
     return b

@@ -79,7 +79,7 @@ struct gsc_ctx {
     const float *b_pos = nullptr, *b_quat = nullptr, *b_scale = nullptr;    // in use (owned or bound)
 
     // per-step buffers
-    float4 *d_rec = nullptr, *d_rec_sorted = nullptr, *d_obb = nullptr;
+    float4 *d_rec = nullptr, *d_obb = nullptr;
     uint2 *d_qrec_sorted = nullptr;
     uint32_t *d_w3_sorted = nullptr;
     uint32_t *d_keys[2] = { nullptr, nullptr }, *d_vals[2] = { nullptr, nullptr };
@@ -319,7 +319,6 @@ int gsc_create(const gsc_config *cfg, gsc_ctx **out)
     CR(dmalloc(&c->d_quat, 4 * M));
     CR(dmalloc(&c->d_scale, 3 * M));
     CR(dmalloc(&c->d_rec, 2 * M));
-    CR(dmalloc(&c->d_rec_sorted, 2 * M));
     CR(dmalloc(&c->d_qrec_sorted, M + kPairTrip));  // k_pairs reads whole trips
     CR(dmalloc(&c->d_w3_sorted, M + kPairTrip));
     CR(dmalloc(&c->d_obb, 4 * M));
@@ -385,7 +384,7 @@ void gsc_destroy(gsc_ctx *c)
             cudaIpcCloseMemHandle(p.fb);
         }
     void *bufs[] = { c->d_entity, c->d_gidx, c->d_box_slot, c->d_kind, c->d_offset, c->d_size, c->d_pos, c->d_quat, c->d_scale, c->d_rec,
-                     c->d_rec_sorted, c->d_qrec_sorted, c->d_w3_sorted, c->d_obb, c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1], c->d_cell_start,
+                     c->d_qrec_sorted, c->d_w3_sorted, c->d_obb, c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1], c->d_cell_start,
                      c->d_wide, c->d_overflow, c->d_gaps, c->d_pairs, c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->d_pairs_sorted, c->d_contacts, c->d_contacts_sorted, c->d_perm, c->d_adj_entity, c->d_adj_offset, c->d_adj_other, c->d_fb, c->d_sort_scratch,
                      c->d_halo_rec, c->d_halo_obb, c->d_halo_count, c->d_hier_parent, c->d_hier_node, c->d_lpos, c->d_lquat,
                      c->d_lscale, c->d_dpos, c->d_dquat, c->d_dscale, c->d_dmat };
@@ -720,7 +719,7 @@ static int stage_launches(gsc_ctx *c, bool slab, bool timing)
                     c->d_sort_scratch, true, n_dev);
         if (timing) CU(c, cudaEventRecord(c->ev[3], s));
         const uint32_t tb = (n_total + 1 + kTableThreads - 1) / kTableThreads;
-        SortedVolumes sv{ c->d_rec_sorted, c->d_qrec_sorted, c->d_w3_sorted };
+        SortedVolumes sv{ c->d_qrec_sorted, c->d_w3_sorted };
         k_cell_table_permute<<<tb, kTableThreads, 0, s>>>(n_total, n_dev, c->d_keys[0], c->d_vals[0], c->d_keys[1], c->d_vals[1],
                                                          c->d_rec, sv, c->d_cell_start, c->d_gaps, fb);
         k_fill_gaps<<<148 * 2, 256, 0, s>>>(c->d_cell_start, c->d_gaps, fb);
@@ -741,10 +740,10 @@ static int stage_launches(gsc_ctx *c, bool slab, bool timing)
         }
         if (timing) CU(c, cudaEventRecord(c->ev[5], s));
         if (c->d_contacts)
-            k_narrow<true><<<148 * kNarrowCtasPerSm, kNarrowThreads, 0, s>>>(c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands, c->d_rec_sorted,
+            k_narrow<true><<<148 * kNarrowCtasPerSm, kNarrowThreads, 0, s>>>(c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands, c->d_rec,
                                                             c->d_obb, c->d_pairs, c->d_contacts, c->max_pairs, fb);
         else
-            k_narrow<false><<<148 * kNarrowCtasPerSm, kNarrowThreads, 0, s>>>(c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands, c->d_rec_sorted,
+            k_narrow<false><<<148 * kNarrowCtasPerSm, kNarrowThreads, 0, s>>>(c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->max_cands, c->d_rec,
                                                              c->d_obb, c->d_pairs, nullptr, c->max_pairs, fb);
         k_wide_pairs<<<148 * 2, kNarrowThreads, 0, s>>>(c->n_local, c->d_wide, c->d_rec, c->d_obb, c->d_pairs, c->d_contacts,
                                                        c->max_pairs, fb);  // (normally no wide volumes: exits at once)

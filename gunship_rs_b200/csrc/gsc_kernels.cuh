@@ -470,11 +470,11 @@ k_cell_keys(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const float4 *__
     tile_hist[(size_t)(2 * tid + 1) * num_tiles + tile] = c1;
 }
 
-// Cell-ordered volumes (one 32 B record = one DRAM sector per volume): the volume record in the form bvh_update
-// wrote it -- sphere (cx, cy, cz, r | entity, 0, gidx, meta), box (min.xyz, max.x | max.yz, gidx, meta) -- so the pairs
-// stage can run the exact AABB test AND Sphere::test_sphere on it, and the SAT stage reads its spheres from here.
-// meta of the sorted copy additionally carries kMetaReachY / kMetaReachZ: the AABB's max corner lies in
-// the next cell along y / z (cell(max) > cell(min)), which is what lets the pairs stage prune rows exactly.
+// What the pairs stage streams in CELL ORDER is 12 B per volume, not the 32 B record: the reach flags say whether the
+// AABB's max corner lies in the next cell along y / z (cell(max) > cell(min)), which is what lets the pairs stage prune
+// rows exactly.  (Rounds 1 and 2a also kept a 32 B cell-ordered copy of the record for the exact AABB test of the pairs
+// tail; the test now runs in the SAT stage on the records that stage loads anyway, so the copy -- 512 MB written per
+// 16M step -- is gone.)
 constexpr uint32_t kMetaReachY = 4u, kMetaReachZ = 8u;
 
 // and, for the filter loop of k_pairs, an 8 B conservatively quantised box per volume plus its ordering word:
@@ -494,7 +494,6 @@ constexpr uint32_t kQGuard = (1u << 10) | (1u << 21) | (1u << 31);
 constexpr uint32_t kQSign = (1u << 9) | (1u << 20) | (1u << 30);
 
 struct SortedVolumes {
-    float4 *v;
     uint2 *q;
     uint32_t *w3;
 };
@@ -541,15 +540,10 @@ k_cell_table_permute(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const u
     const uint32_t klo = p == 0 ? 0u : (p - 1 < n_total ? min(keys[p - 1], C) : C) + 1u;
     if (p < n_total) {
         const uint32_t i = vals[p];
-        const float4 r0 = ldg_gather(rec + 2 * (size_t)i);
-        float4 r1 = ldg_gather(rec + 2 * (size_t)i + 1);
-        const Volume v = volume_decode(r0, r1);
+        const Volume v = volume_decode(ldg_gather(rec + 2 * (size_t)i), ldg_gather(rec + 2 * (size_t)i + 1));
         uint32_t meta = v.meta;
         if (cell_coord_f(v.mx[1], g.cell_size) > cell_coord_f(v.mn[1], g.cell_size)) meta |= kMetaReachY;
         if (cell_coord_f(v.mx[2], g.cell_size) > cell_coord_f(v.mn[2], g.cell_size)) meta |= kMetaReachZ;
-        r1.w = __uint_as_float(meta);
-        sv.v[2 * (size_t)p] = r0;
-        sv.v[2 * (size_t)p + 1] = r1;
         const uint32_t wmin = quant_pack(quant_lo(v.mn[0], g.qorg[0], g.qscale[0], g.qmargin),
                                          quant_lo(v.mn[1], g.qorg[1], g.qscale[1], g.qmargin),
                                          quant_lo(v.mn[2], g.qorg[2], g.qscale[2], g.qmargin));
@@ -640,7 +634,7 @@ constexpr int kNarrowChunk = kNarrowThreads * 2;  // candidates per ticket
 template <bool CONTACTS>
 __global__ void __launch_bounds__(kNarrowThreads, kNarrowCtasPerSm)
 k_narrow(const uint2 *__restrict__ cand_ss, const uint2 *__restrict__ cand_so, const uint2 *__restrict__ cand_oo,
-         unsigned long long cap_cands, const float4 *__restrict__ srec, const float4 *__restrict__ obb,
+         unsigned long long cap_cands, const float4 *__restrict__ rec, const float4 *__restrict__ obb,
          uint2 *__restrict__ pairs, float4 *__restrict__ contacts, unsigned long long cap_pairs, FrameBlock *__restrict__ fb)
 {
     __shared__ EmitBuf<kNarrowWarps, kNarrowCap> s_out;
@@ -685,8 +679,7 @@ k_narrow(const uint2 *__restrict__ cand_ss, const uint2 *__restrict__ cand_so, c
                     const bool hi_is_sphere = c.x >> 31;
                     const uint32_t hi = c.x & 0x7fffffffu, lo = c.y;
                     const uint32_t si = hi_is_sphere ? hi : lo, oi = hi_is_sphere ? lo : hi;
-                    // (the sphere is addressed by its cell-ordered position, pair_classify)
-                    const float4 s0 = ldg_gather(srec + 2 * (size_t)si), s1 = ldg_gather(srec + 2 * (size_t)si + 1);
+                    const float4 s0 = ldg_gather(rec + 2 * (size_t)si), s1 = ldg_gather(rec + 2 * (size_t)si + 1);
                     uint32_t oe;
                     const Obb o = obb_load(obb + 4 * (size_t)oi, &oe);
                     float omn[3], omx[3];
@@ -699,14 +692,14 @@ k_narrow(const uint2 *__restrict__ cand_ss, const uint2 *__restrict__ cand_so, c
                     item = hi_is_sphere ? make_uint2(se, oe) : make_uint2(oe, se);
                     if (CONTACTS && hit) ct = contact_sphere_obb(s0.x, s0.y, s0.z, s0.w, o, hi_is_sphere);
                 } else {  // Sphere::test_sphere (mod.rs:383-389)
-                    const float4 h0 = ldg_gather(srec + 2 * (size_t)c.x), l0 = ldg_gather(srec + 2 * (size_t)c.y);
+                    const float4 h0 = ldg_gather(rec + 2 * (size_t)c.x), l0 = ldg_gather(rec + 2 * (size_t)c.y);
                     const float hmn[3] = { sub(h0.x, h0.w), sub(h0.y, h0.w), sub(h0.z, h0.w) };
                     const float hmx[3] = { add(h0.x, h0.w), add(h0.y, h0.w), add(h0.z, h0.w) };
                     const float lmn[3] = { sub(l0.x, l0.w), sub(l0.y, l0.w), sub(l0.z, l0.w) };
                     const float lmx[3] = { add(l0.x, l0.w), add(l0.y, l0.w), add(l0.z, l0.w) };
                     hit = test_aabb(hmn, hmx, lmn, lmx) && test_sphere_sphere(h0.x, h0.y, h0.z, h0.w, l0.x, l0.y, l0.z, l0.w);
                     if (hit) {
-                        const float4 h1 = ldg_gather(srec + 2 * (size_t)c.x + 1), l1 = ldg_gather(srec + 2 * (size_t)c.y + 1);
+                        const float4 h1 = ldg_gather(rec + 2 * (size_t)c.x + 1), l1 = ldg_gather(rec + 2 * (size_t)c.y + 1);
                         item = make_uint2(__float_as_uint(h1.x), __float_as_uint(l1.x));
                         if (CONTACTS) ct = contact_sphere_sphere(h0.x, h0.y, h0.z, h0.w, l0.x, l0.y, l0.z, l0.w);
                     }

@@ -53,15 +53,15 @@ struct PairRefs {
 // function and inputs bvh_update used) and tests them before the shape test.  Round 2: this took four dependent 16 B
 // gathers per survivor and their decode out of the pairs kernel (its tail was 25% of the instructions and 31% of the
 // stall samples).
-// A sphere is addressed by its cell-ordered POSITION (its record is read from the cell-ordered array, where both
-// members of a pair are at most a cell row apart), a box by its local index (its OBB record lives in collider order).
+// Both members are addressed by their LOCAL index (where the 32 B volume record and the 64 B OBB record live); once the
+// colliders are kept in a previous frame's cell order (gsc_reorder_colliders) those are neighbours in memory too.
 // item = (later volume [| sphere flag], earlier volume); returns the class 0 sphere-sphere, 1 sphere-box, 2 box-box.
 GSC_DEV int pair_classify(uint32_t p, uint32_t q, PairRefs refs, uint2 *item)
 {
     const uint32_t aw = __ldg(refs.w3 + p), bw = __ldg(refs.w3 + q);
     const bool a_box = aw & kMetaBox, b_box = bw & kMetaBox;
     const bool a_hi = (aw >> 4) > (bw >> 4);  // tuple = (later index, earlier index), grid_collision.rs:440,497
-    const uint32_t a_ref = a_box ? __ldg(refs.vals + p) : p, b_ref = b_box ? __ldg(refs.vals + q) : q;
+    const uint32_t a_ref = __ldg(refs.vals + p), b_ref = __ldg(refs.vals + q);
     uint32_t hi = a_hi ? a_ref : b_ref;
     const uint32_t lo = a_hi ? b_ref : a_ref;
     const int cls = (int)a_box + (int)b_box;
