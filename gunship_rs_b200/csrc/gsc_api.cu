@@ -80,8 +80,8 @@ struct gsc_ctx {
 
     // per-step buffers
     float4 *d_rec = nullptr, *d_obb = nullptr;
-    uint2 *d_qrec_sorted = nullptr, *d_qrec = nullptr;   // quantised boxes in cell order / in index order
-    uint32_t *d_w3_sorted = nullptr, *d_w3 = nullptr;     // ordering words, likewise
+    uint2 *d_qrec_sorted = nullptr;
+    uint32_t *d_w3_sorted = nullptr;
     uint32_t *d_keys[2] = { nullptr, nullptr }, *d_vals[2] = { nullptr, nullptr };
     uint32_t *d_cell_start = nullptr, *d_wide = nullptr;
     uint32_t *d_overflow = nullptr;  // tiles of the pairs stage that did not fit its staging buffers
@@ -199,7 +199,7 @@ inline uint32_t tiles_for(uint32_t n) { return (n + kSortTile - 1) / kSortTile; 
 // `n_dev`: optional device-side element count (<= n); the launches are then sized for n and clamp to *n_dev
 void launch_sort(cudaStream_t s, uint32_t n, uint32_t *keys[2], uint32_t *vals[2], bool first_vals_identity,
                  int max_passes, const SortControl *ctl, uint32_t *scratch, bool have_pass0_hist = false,
-                 const uint32_t *n_dev = nullptr, SortPayload payload = SortPayload{ nullptr, nullptr, nullptr, nullptr })
+                 const uint32_t *n_dev = nullptr)
 {
     const uint32_t tiles = tiles_for(n);
     if (tiles == 0) return;
@@ -210,7 +210,7 @@ void launch_sort(cudaStream_t s, uint32_t n, uint32_t *keys[2], uint32_t *vals[2
         if (pass > 0 || !have_pass0_hist) k_radix_upsweep<<<tiles, kSortThreads, 0, s>>>(keys[in], n, pass, ctl, tile_hist, tiles, n_dev);
         k_radix_scan<<<kRadix, 256, 0, s>>>(tile_hist, tiles, pass, ctl, digit_total, n_dev);
         k_radix_downsweep<<<tiles, kSortThreads, 0, s>>>(keys[in], vin, keys[out], vals[out], n, pass, ctl, tile_hist,
-                                                        digit_total, tiles, n_dev, payload);
+                                                        digit_total, tiles, n_dev);
     }
 }
 
@@ -321,8 +321,6 @@ int gsc_create(const gsc_config *cfg, gsc_ctx **out)
     CR(dmalloc(&c->d_rec, 2 * M));
     CR(dmalloc(&c->d_qrec_sorted, M + kPairTrip));  // k_pairs reads whole trips
     CR(dmalloc(&c->d_w3_sorted, M + kPairTrip));
-    CR(dmalloc(&c->d_qrec, M));
-    CR(dmalloc(&c->d_w3, M));
     CR(dmalloc(&c->d_obb, 4 * M));
     for (int i = 0; i < 2; ++i) {
         CR(dmalloc(&c->d_keys[i], M));
@@ -386,7 +384,7 @@ void gsc_destroy(gsc_ctx *c)
             cudaIpcCloseMemHandle(p.fb);
         }
     void *bufs[] = { c->d_entity, c->d_gidx, c->d_box_slot, c->d_kind, c->d_offset, c->d_size, c->d_pos, c->d_quat, c->d_scale, c->d_rec,
-                     c->d_qrec_sorted, c->d_w3_sorted, c->d_qrec, c->d_w3, c->d_obb, c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1], c->d_cell_start,
+                     c->d_qrec_sorted, c->d_w3_sorted, c->d_obb, c->d_keys[0], c->d_keys[1], c->d_vals[0], c->d_vals[1], c->d_cell_start,
                      c->d_wide, c->d_overflow, c->d_gaps, c->d_pairs, c->d_cand_ss, c->d_cand_so, c->d_cand_oo, c->d_pairs_sorted, c->d_contacts, c->d_contacts_sorted, c->d_perm, c->d_adj_entity, c->d_adj_offset, c->d_adj_other, c->d_fb, c->d_sort_scratch,
                      c->d_halo_rec, c->d_halo_obb, c->d_halo_count, c->d_hier_parent, c->d_hier_node, c->d_lpos, c->d_lquat,
                      c->d_lscale, c->d_dpos, c->d_dquat, c->d_dscale, c->d_dmat };
@@ -711,20 +709,19 @@ static int stage_launches(gsc_ctx *c, bool slab, bool timing)
     FrameBlock *fb = c->d_fb;
     if (!slab) k_grid_setup<<<1, 32, 0, s>>>(fb, c->max_cells, n_total, c->have_window ? 1 : 0, c->win_lo, c->win_hi);
     if (n_total) {
-        SortedVolumes sv{ c->d_qrec_sorted, c->d_w3_sorted };
-        k_cell_keys<<<tiles_for(n_total), kKeyThreads, 0, s>>>(n_total, n_dev, c->d_rec, c->d_keys[0], SortedVolumes{ c->d_qrec, c->d_w3 },
-                                                              c->d_wide, c->d_sort_scratch, fb);
+        k_cell_keys<<<tiles_for(n_total), kKeyThreads, 0, s>>>(n_total, n_dev, c->d_rec, c->d_keys[0], c->d_wide, c->d_sort_scratch, fb);
         if (timing) CU(c, cudaEventRecord(c->ev[2], s));
         // the keys are cell ids <= max_cells: no more radix passes can ever be needed than that many bits take (passes
         // beyond the step's real count exit at once on the device, but each of their launches still costs ~4 us)
         int key_bits_max = 1;
         while (key_bits_max < 32 && (1ull << key_bits_max) <= c->max_cells) ++key_bits_max;
-        // the last pass carries the 12 B pair records (index order -> cell order) along with the indices
         launch_sort(s, n_total, c->d_keys, c->d_vals, true, std::min(kMaxPasses, radix_passes(key_bits_max)), &fb->sort,
-                    c->d_sort_scratch, true, n_dev, SortPayload{ c->d_qrec, c->d_w3, c->d_qrec_sorted, c->d_w3_sorted });
+                    c->d_sort_scratch, true, n_dev);
         if (timing) CU(c, cudaEventRecord(c->ev[3], s));
         const uint32_t tb = (n_total + 1 + kTableThreads - 1) / kTableThreads;
-        k_cell_table<<<tb, kTableThreads, 0, s>>>(n_total, n_dev, c->d_keys[0], c->d_keys[1], c->d_cell_start, c->d_gaps, fb);
+        SortedVolumes sv{ c->d_qrec_sorted, c->d_w3_sorted };
+        k_cell_table_permute<<<tb, kTableThreads, 0, s>>>(n_total, n_dev, c->d_keys[0], c->d_vals[0], c->d_keys[1], c->d_vals[1],
+                                                         c->d_rec, sv, c->d_cell_start, c->d_gaps, fb);
         k_fill_gaps<<<148 * 2, 256, 0, s>>>(c->d_cell_start, c->d_gaps, fb);
         if (timing) CU(c, cudaEventRecord(c->ev[4], s));
         // sphere-sphere pairs are decided inside the pairs stage unless a contact has to be computed for them

@@ -405,47 +405,6 @@ GSC_DEV bool home_cell(const Volume &v, const GridParams &g, int c_mn[3], int c_
     return wide;
 }
 
-// What the pairs stage streams in CELL ORDER is 12 B per volume, not the 32 B record: the reach flags say whether the
-// AABB's max corner lies in the next cell along y / z (cell(max) > cell(min)), which is what lets the pairs stage prune
-// rows exactly.  (Rounds 1 and 2a also kept a 32 B cell-ordered copy of the record for the exact AABB test of the pairs
-// tail; the test now runs in the SAT stage on the records that stage loads anyway, so the copy -- 512 MB written per
-// 16M step -- is gone.)
-constexpr uint32_t kMetaReachY = 4u, kMetaReachZ = 8u;
-
-// and, for the filter loop of k_pairs, an 8 B conservatively quantised box per volume plus its ordering word:
-//   q[p]  = (Wmin, Wmax | G)      w3[p] = gidx << 4 | meta flags
-// Each W packs the three axes of the quantised min (max) corner into one word -- x: bits 0-9, y: bits 11-20, z: bits
-// 22-30 -- with a guard bit G above every field (bits 10, 21, 31).  The quantum is cell/128 on x, y and cell/64 on z,
-// qmin = floor(t) - margin, qmax = ceil(t) + margin with t = (v - world_min) * quanta_per_cell / cell, and only the
-// LOW bits of the integer are kept: coordinates are compared modulo 8 cells.  That is enough because k_pairs only
-// ever compares volumes whose home cells differ by at most one per axis: A.max - B.min and B.max - A.min then lie
-// in (-2, 3) cells = (-256, 384) quanta (x, y) resp. (-128, 192) (z), inside the signed range of the field.  So
-//   t1 = (A.Wmax | G) - B.Wmin,   t2 = (B.Wmax | G) - A.Wmin      (the guard bits absorb the borrows)
-// hold the three differences each, and the boxes overlap on every axis  <=>  no field of t1 or t2 is negative
-//   <=>  ((t1 | t2) & kQSign) == 0:
-// two subtractions and one logic op per candidate instead of six compares.  Exact overlap always implies quantised
-// overlap (never a false negative; the f32 error of t is below the margin); the exact test runs on the survivors only.
-constexpr uint32_t kQGuard = (1u << 10) | (1u << 21) | (1u << 31);
-constexpr uint32_t kQSign = (1u << 9) | (1u << 20) | (1u << 30);
-
-struct SortedVolumes {
-    uint2 *q;
-    uint32_t *w3;
-};
-
-GSC_DEV uint32_t quant_lo(float v, float org, float scale, float margin)
-{
-    return (uint32_t)fmaxf(floorf((v - org) * scale) - margin, 0.0f);
-}
-GSC_DEV uint32_t quant_hi(float v, float org, float scale, float margin)
-{
-    return (uint32_t)(ceilf((v - org) * scale) + margin);
-}
-GSC_DEV uint32_t quant_pack(uint32_t x, uint32_t y, uint32_t z)
-{
-    return (x & 1023u) | ((y & 1023u) << 11) | ((z & 511u) << 22);
-}
-
 // ---- stage 1: cell keys -----------------------------------------------------------------------------
 // key = (x * dims.y + y) * dims.z + z of the home cell: x is the major axis, so x-slabs of the
 // multi-GPU partition are contiguous key ranges and cells of one (x,y) row are contiguous in z.
@@ -455,7 +414,7 @@ constexpr int kKeyThreads = 256;
 // tile_hist[d * num_tiles + tile] is what k_radix_upsweep would compute for pass 0.
 __global__ void __launch_bounds__(kKeyThreads)
 k_cell_keys(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const float4 *__restrict__ rec, uint32_t *__restrict__ keys,
-            SortedVolumes by_index, uint32_t *__restrict__ wide_list, uint32_t *__restrict__ tile_hist, FrameBlock *__restrict__ fb)
+            uint32_t *__restrict__ wide_list, uint32_t *__restrict__ tile_hist, FrameBlock *__restrict__ fb)
 {
     constexpr int WARPS = kKeyThreads / 32;
     __shared__ __align__(16) uint16_t s_hist[WARPS][kRadix];
@@ -498,21 +457,6 @@ k_cell_keys(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const float4 *__
         }
         keys[i] = key;
         hist_add(s_hist[warp], key & mask);
-        // The 12 B the pairs stage streams per volume -- conservatively quantised box + ordering word -- are produced HERE,
-        // in index order, while the record is in registers anyway (this kernel is HBM bound, its issue slots are idle); the
-        // LAST radix pass carries them to their cell-ordered positions together with the index it scatters (round 2:
-        // k_cell_table_permute used to gather the 32 B record again through the sorted index, 0.2 ms at 16M).
-        uint32_t meta = v.meta;
-        if (c1[1] > c0[1]) meta |= kMetaReachY;
-        if (c1[2] > c0[2]) meta |= kMetaReachZ;
-        const uint32_t wmin = quant_pack(quant_lo(v.mn[0], g.qorg[0], g.qscale[0], g.qmargin),
-                                         quant_lo(v.mn[1], g.qorg[1], g.qscale[1], g.qmargin),
-                                         quant_lo(v.mn[2], g.qorg[2], g.qscale[2], g.qmargin));
-        const uint32_t wmax = quant_pack(quant_hi(v.mx[0], g.qorg[0], g.qscale[0], g.qmargin),
-                                         quant_hi(v.mx[1], g.qorg[1], g.qscale[1], g.qmargin),
-                                         quant_hi(v.mx[2], g.qorg[2], g.qscale[2], g.qmargin));
-        by_index.q[i] = make_uint2(wmin, wmax | kQGuard);
-        by_index.w3[i] = (v.gidx << 4) | (meta & 15u);
     }
     __syncthreads();
     uint32_t c0 = 0, c1 = 0;
@@ -526,7 +470,48 @@ k_cell_keys(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const float4 *__
     tile_hist[(size_t)(2 * tid + 1) * num_tiles + tile] = c1;
 }
 
-// ---- stage 3: cell start table (the cell-order permutation of the 12 B pair records rides on the last radix pass) ----
+// What the pairs stage streams in CELL ORDER is 12 B per volume, not the 32 B record: the reach flags say whether the
+// AABB's max corner lies in the next cell along y / z (cell(max) > cell(min)), which is what lets the pairs stage prune
+// rows exactly.  (Rounds 1 and 2a also kept a 32 B cell-ordered copy of the record for the exact AABB test of the pairs
+// tail; the test now runs in the SAT stage on the records that stage loads anyway, so the copy -- 512 MB written per
+// 16M step -- is gone.)
+constexpr uint32_t kMetaReachY = 4u, kMetaReachZ = 8u;
+
+// and, for the filter loop of k_pairs, an 8 B conservatively quantised box per volume plus its ordering word:
+//   q[p]  = (Wmin, Wmax | G)      w3[p] = gidx << 4 | meta flags
+// Each W packs the three axes of the quantised min (max) corner into one word -- x: bits 0-9, y: bits 11-20, z: bits
+// 22-30 -- with a guard bit G above every field (bits 10, 21, 31).  The quantum is cell/128 on x, y and cell/64 on z,
+// qmin = floor(t) - margin, qmax = ceil(t) + margin with t = (v - world_min) * quanta_per_cell / cell, and only the
+// LOW bits of the integer are kept: coordinates are compared modulo 8 cells.  That is enough because k_pairs only
+// ever compares volumes whose home cells differ by at most one per axis: A.max - B.min and B.max - A.min then lie
+// in (-2, 3) cells = (-256, 384) quanta (x, y) resp. (-128, 192) (z), inside the signed range of the field.  So
+//   t1 = (A.Wmax | G) - B.Wmin,   t2 = (B.Wmax | G) - A.Wmin      (the guard bits absorb the borrows)
+// hold the three differences each, and the boxes overlap on every axis  <=>  no field of t1 or t2 is negative
+//   <=>  ((t1 | t2) & kQSign) == 0:
+// two subtractions and one logic op per candidate instead of six compares.  Exact overlap always implies quantised
+// overlap (never a false negative; the f32 error of t is below the margin); the exact test runs on the survivors only.
+constexpr uint32_t kQGuard = (1u << 10) | (1u << 21) | (1u << 31);
+constexpr uint32_t kQSign = (1u << 9) | (1u << 20) | (1u << 30);
+
+struct SortedVolumes {
+    uint2 *q;
+    uint32_t *w3;
+};
+
+GSC_DEV uint32_t quant_lo(float v, float org, float scale, float margin)
+{
+    return (uint32_t)fmaxf(floorf((v - org) * scale) - margin, 0.0f);
+}
+GSC_DEV uint32_t quant_hi(float v, float org, float scale, float margin)
+{
+    return (uint32_t)(ceilf((v - org) * scale) + margin);
+}
+GSC_DEV uint32_t quant_pack(uint32_t x, uint32_t y, uint32_t z)
+{
+    return (x & 1023u) | ((y & 1023u) << 11) | ((z & 511u) << 22);
+}
+
+// ---- stage 3: cell start table + cell-order permutation of the volume records ---------------------
 // start[c] = first sorted position whose key >= c, for c in [0, num_cells]; thread p fills the gap
 // (key[p-1], key[p]].  Long gaps (empty space) are filled by the whole warp.
 constexpr int kTableThreads = 256;
@@ -535,20 +520,39 @@ constexpr int kGapCap = 4096;
 constexpr int kWarpFillMax = 4096;  // cells a warp fills transposed; wider spans (rare) go gap by gap
 
 __global__ void __launch_bounds__(kTableThreads)
-k_cell_table(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ keys_b,
-             uint32_t *__restrict__ cell_start, uint4 *__restrict__ gaps, FrameBlock *__restrict__ fb)
+k_cell_table_permute(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ vals_a,
+                     const uint32_t *__restrict__ keys_b, const uint32_t *__restrict__ vals_b,
+                     const float4 *__restrict__ rec, SortedVolumes sv,
+                     uint32_t *__restrict__ cell_start, uint4 *__restrict__ gaps, FrameBlock *__restrict__ fb)
 {
     const GridParams g = fb->grid;
     if (!g.valid) return;
     const uint32_t n_total = n_dev ? min(*n_dev, n_cap) : n_cap;
     if (blockIdx.x * (uint32_t)kTableThreads > n_total) return;  // (position n_total itself closes the table)
-    const uint32_t *keys = (fb->sort.num_passes & 1) ? keys_b : keys_a;  // ping-pong parity of the sort
+    const bool in_b = fb->sort.num_passes & 1;  // ping-pong parity of the sort
+    const uint32_t *keys = in_b ? keys_b : keys_a;
+    const uint32_t *vals = in_b ? vals_b : vals_a;
     const uint32_t p = blockIdx.x * kTableThreads + threadIdx.x;  // p in [0, n_total]
     const uint32_t C = g.num_cells;
     // thread p fills start[] for the cells of the key gap (key[p-1], key[p]] (keys clamped to C; positions behind
     // n_total count as key C, so their gaps are empty and the kernel needs no tail special case)
     const uint32_t kcur = p < n_total ? min(keys[p], C) : C;
     const uint32_t klo = p == 0 ? 0u : (p - 1 < n_total ? min(keys[p - 1], C) : C) + 1u;
+    if (p < n_total) {
+        const uint32_t i = vals[p];
+        const Volume v = volume_decode(ldg_gather(rec + 2 * (size_t)i), ldg_gather(rec + 2 * (size_t)i + 1));
+        uint32_t meta = v.meta;
+        if (cell_coord_f(v.mx[1], g.cell_size) > cell_coord_f(v.mn[1], g.cell_size)) meta |= kMetaReachY;
+        if (cell_coord_f(v.mx[2], g.cell_size) > cell_coord_f(v.mn[2], g.cell_size)) meta |= kMetaReachZ;
+        const uint32_t wmin = quant_pack(quant_lo(v.mn[0], g.qorg[0], g.qscale[0], g.qmargin),
+                                         quant_lo(v.mn[1], g.qorg[1], g.qscale[1], g.qmargin),
+                                         quant_lo(v.mn[2], g.qorg[2], g.qscale[2], g.qmargin));
+        const uint32_t wmax = quant_pack(quant_hi(v.mx[0], g.qorg[0], g.qscale[0], g.qmargin),
+                                         quant_hi(v.mx[1], g.qorg[1], g.qscale[1], g.qmargin),
+                                         quant_hi(v.mx[2], g.qorg[2], g.qscale[2], g.qmargin));
+        sv.q[p] = make_uint2(wmin, wmax | kQGuard);
+        sv.w3[p] = (v.gidx << 4) | (meta & 15u);
+    }
     // The warp's 32 positions own the contiguous cells [first, last].  Normally the warp fills them TRANSPOSED: lane l
     // takes cells first + l, first + 32 + l, ... and finds each cell's start -- position of the first key >= the
     // cell -- by a 5-step binary search over the warp's sorted keys (shuffles).  32 cells per trip whatever the gap

@@ -162,16 +162,6 @@ k_radix_scan(uint32_t *__restrict__ tile_hist, uint32_t num_tiles, int pass, con
     if (tid == 0) digit_total[blockIdx.x] = carry;
 }
 
-// Payload that rides on the LAST pass of a sort: 8 B + 4 B records stored in VALUE order (src_*) are carried to the
-// sorted positions of their values (dst_*) while the pass scatters the values anyway.  The collision step uses it for
-// the quantised boxes and ordering words of the pairs stage (gsc_kernels.cuh, k_cell_keys); null = plain sort.
-struct SortPayload {
-    const uint2 *src_q;
-    const uint32_t *src_w;
-    uint2 *dst_q;
-    uint32_t *dst_w;
-};
-
 // grid = num_tiles CTAs of kSortThreads threads, 64 registers (4 CTAs = 32 warps per SM).
 //   keys_in/vals_in -> keys_out/vals_out; vals_in == nullptr means "value = position" (first pass).
 // ncu (round 1): this kernel is bound by the shared-memory / MIO pipe (mio_throttle + short_scoreboard), not by
@@ -180,8 +170,7 @@ __global__ void __launch_bounds__(kSortThreads, 4)
 k_radix_downsweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                   uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n, int pass,
                   const SortControl *__restrict__ ctl, const uint32_t *__restrict__ tile_hist,
-                  const uint32_t *__restrict__ digit_total, uint32_t num_tiles, const uint32_t *__restrict__ n_dev,
-                  SortPayload payload)
+                  const uint32_t *__restrict__ digit_total, uint32_t num_tiles, const uint32_t *__restrict__ n_dev)
 {
     constexpr int WARPS = kSortThreads / 32;
     constexpr int WTILE = 32 * kSortIpt;
@@ -297,32 +286,17 @@ k_radix_downsweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
     // ---- write digit runs contiguously ----
     const uint32_t remaining = n - tile_base;
     const uint32_t valid = remaining < (uint32_t)kSortTile ? remaining : (uint32_t)kSortTile;
-    const bool carry = payload.src_q != nullptr && pass + 1 == ctl->num_passes;  // (uniform)
 #pragma unroll
     for (int j = 0; j < kSortIpt; ++j) {
         const uint32_t i = tid + j * kSortThreads;
         if (i < valid) {
             const uint32_t k = s_keys[i];
             const uint32_t dst = s_goff[(k >> shift) & mask] + i;
-
 #ifdef GSC_CHECKED
             if (dst >= n) { asm volatile("trap;"); }  // (the sort has no status word: a checked build traps)
 #endif
             keys_out[dst] = k;
             vals_out[dst] = s_vals[i];
-        }
-    }
-    if (carry) {  // the final position of every value is known here: its payload goes along (a loop of its own: the
-                  // scatter above runs at the register limit of 4 resident CTAs)
-#pragma unroll 4
-        for (int j = 0; j < kSortIpt; ++j) {
-            const uint32_t i = tid + j * kSortThreads;
-            if (i < valid) {
-                const uint32_t dst = s_goff[(s_keys[i] >> shift) & mask] + i;
-                const uint32_t v = s_vals[i];
-                payload.dst_q[dst] = __ldg(payload.src_q + v);
-                payload.dst_w[dst] = __ldg(payload.src_w + v);
-            }
         }
     }
 }
