@@ -14,16 +14,21 @@
 // cell(B.min) > cell(A.max) there, hence B.min > A.max by monotonicity of floor(fl(p / c)).
 //
 // Two kernels:
-//   k_pairs_tiled  the production path.  One CTA = a TILE of kTileA consecutive cell-sorted volumes.  Their runs are
-//                  monotone in the sorted position, so per row the union of the tile's runs is ONE contiguous
-//                  segment of the sorted array: the five segments are staged in shared memory once, coalesced
-//                  (cp.async), every candidate byte is read from L2/HBM once per tile.  The (A, run) work is then
-//                  FLATTENED: the tile's non-empty runs are listed with their prefix sums and every lane takes an
-//                  equal, contiguous share of the tile's tests -- no lane waits for the longest run of its warp
-//                  (the round-1 kernel ran at 17/32 active lanes in its filter loop).
-//   k_pairs        the round-1 thread-per-volume walk through L1, kept for tiles whose segments do not fit the
-//                  staging buffers (hundreds of volumes per cell): k_pairs_tiled queues such tiles, k_pairs runs
-//                  persistently over the queue (normally empty: it exits at once).
+//   k_pairs        the production path: one thread per cell-sorted volume A walks A's five runs through L1 (lanes of one
+//                  cell walk the same run together, so their candidate loads coalesce), four candidates per trip, doing
+//                  only the quantised overlap test; survivors go into private shared-memory slots with a predicated
+//                  store.  k_pairs<false>: one CTA per kPairThreads volumes of the whole sorted array.
+//   k_pairs_tiled  the `north_star` form, built and measured in round 2 (opt-in: GSC_PAIRS_TILED=1).  One CTA = a TILE
+//                  of kTileA consecutive cell-sorted volumes.  Their runs are monotone in the sorted position, so per
+//                  row the union of the tile's runs is ONE contiguous segment of the sorted array: the five segments
+//                  are staged in shared memory once, coalesced (cp.async), every candidate byte is read from L2/HBM
+//                  once per tile.  The (A, run) work is then FLATTENED: the tile's non-empty runs are listed with their
+//                  prefix sums and every lane takes an equal, contiguous share of the tile's tests.  Bit-exact, and
+//                  1.7-2x SLOWER than k_pairs at 16M (profiles/r02_pairs_tiled_v1_ncu.md: 690 instructions of tile
+//                  set-up per 32 volumes against 120, and a divergent run switch in every iteration of the flattened
+//                  loop because runs are only 5.6 candidates long).  Tiles whose segments do not fit the staging
+//                  buffers (hundreds of volumes per cell) are queued and walked by k_pairs<true>, persistent over the
+//                  queue (normally empty: it exits at once).
 // Both end in the same tail: the survivors of the quantised filter are classified by shape pair and oriented by global
 // index from their 4 B ordering words alone and appended to the three candidate lists of the SAT stage, which runs the
 // EXACT inclusive AABB test (on AABBs it re-derives bit for bit from the records it loads anyway) before the shape test.
