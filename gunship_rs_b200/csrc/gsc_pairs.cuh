@@ -459,7 +459,7 @@ k_pairs_tiled(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const uint32_t
 #define GSC_PAIR_THREADS 64
 #endif
 #ifndef GSC_PAIR_MIN_CTAS
-#define GSC_PAIR_MIN_CTAS 20
+#define GSC_PAIR_MIN_CTAS 24  // 16 / 20 / 24 resident CTAs measured with the round-2 tail: 0.926 / 0.852 / 0.842 ms at 16M
 #endif
 #ifndef GSC_PAIR_PRIV
 #define GSC_PAIR_PRIV 12  // 8 / 12 / 16 / 24 measured: 0.942 / 0.903 / 0.913 / 0.936 ms at 16M
