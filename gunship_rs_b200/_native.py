@@ -147,7 +147,7 @@ def load():
     L.gsc_group_update_transforms.argtypes = [vp, C.c_uint32, f32p, f32p, f32p]
     L.gsc_group_step.argtypes = [vp, C.POINTER(GscStepOut)]
     L.gsc_group_download_pairs.argtypes = [vp, u32p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
-    L.gsc_group_rebalance.argtypes = [vp]
+    L.gsc_group_rebalance.argtypes = [vp, C.c_uint32, f32p]
     L.gsc_group_reorder.argtypes = [vp]
     L.gsc_group_member.argtypes = [vp, C.c_uint32, C.POINTER(vp), C.POINTER(C.c_uint32), u32p]
     L.gsc_map_transform_staging.argtypes = [vp, C.c_uint32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]

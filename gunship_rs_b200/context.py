@@ -379,11 +379,15 @@ class CollisionGroup:
         p = self.pairs(sorted).astype(np.uint64)
         return (p[:, 0] << np.uint64(32)) | p[:, 1]
 
-    def rebalance(self):
-        self._check(self._lib.gsc_group_rebalance(self._h))
+    def rebalance(self, pos):
+        """re-cut the slabs from the current positions (dense order) and the last step's work; the next
+        update_transforms must carry rotation and scale again"""
+        p = _c(pos, np.float32)
+        self._check(self._lib.gsc_group_rebalance(self._h, int(p.shape[0]), _ptr(p)))
 
     def reorder(self):
-        """every member keeps its colliders in the cell order of the last step (temporal coherence)"""
+        """every member keeps its colliders in the cell order of the last step (temporal coherence); the next
+        update_transforms must carry rotation and scale again"""
         self._check(self._lib.gsc_group_reorder(self._h))
 
     def member_counts(self):

@@ -22,7 +22,6 @@ struct gsc_group {
     std::vector<uint32_t> entity;
     std::vector<uint8_t> kind;
     std::vector<float> offset, size;
-    std::vector<float> last_pos, last_quat, last_scale;  // the transforms of the last gsc_group_update_transforms
     std::vector<std::vector<uint32_t>> owned;            // global indices per member in the member's dense (slot) order
     std::vector<float> cuts;                             // x positions of the world-1 slab cuts
     std::vector<gsc_step_out> last;                      // per member, last step
@@ -192,9 +191,6 @@ int gsc_group_upload_colliders(gsc_group *g, uint32_t n, const uint32_t *entity,
     g->kind.assign(kind, kind + n);
     g->offset.assign(offset3, offset3 + 3 * (size_t)n);
     g->size.assign(size3, size3 + 3 * (size_t)n);
-    g->last_pos.assign(pos3, pos3 + 3 * (size_t)n);
-    g->last_quat.clear();
-    g->last_scale.clear();
     // count-balanced x-slabs: the cuts are the world-quantiles of x (gsc_group_rebalance refines them by measured work)
     std::vector<float> xs(n);
     for (uint32_t i = 0; i < n; ++i) xs[i] = pos3[3 * (size_t)i];
@@ -219,11 +215,6 @@ int gsc_group_update_transforms(gsc_group *g, uint32_t n, const float *pos3, con
     if (!g->have_colliders || n != g->n) return gfail(g, GSC_ERR_INVALID, "gsc_group_update_transforms: n=%u does not match the %u uploaded colliders", n, g->n);
     if (n && !pos3) return gfail(g, GSC_ERR_INVALID, "gsc_group_update_transforms: null positions");
     if ((quat4 == nullptr) != (scale3 == nullptr)) return gfail(g, GSC_ERR_INVALID, "gsc_group_update_transforms: pass rotation and scale together");
-    g->last_pos.assign(pos3, pos3 + 3 * (size_t)n);
-    if (quat4) {
-        g->last_quat.assign(quat4, quat4 + 4 * (size_t)n);
-        g->last_scale.assign(scale3, scale3 + 3 * (size_t)n);
-    }
     return group_scatter(g, pos3, quat4, scale3);
 }
 
@@ -316,20 +307,22 @@ int gsc_group_download_pairs(gsc_group *g, uint32_t *dst, uint64_t cap_pairs, in
 }
 
 // Re-cut the slabs so that every member gets the same share of the work of the LAST step, then move the colliders
-// whose owner changed (they "migrate": the static arrays of every member are rebuilt from the engine's dense arrays,
-// the last frame's transforms are handed over again).  Work model of a slab: colliders + 0.7 x AABB-overlapping
-// candidate pairs (the per-collider stages cost about as much as 26 quantised tests, a candidate stands for ~18),
-// spread evenly over the slab's x-extent: the cumulative work is piecewise linear in x and the new cuts are its
-// world-quantiles.
-int gsc_group_rebalance(gsc_group *g)
+// whose owner changed (they "migrate": the static arrays of every member are rebuilt from the engine's dense arrays).
+// `pos3` = the current positions (dense order), which decide the new owners.  Work model of a slab: colliders + 0.7 x
+// candidate pairs (the per-collider stages cost about as much as 26 quantised tests, a candidate stands for ~18), spread
+// evenly over the slab's x-extent: the cumulative work is piecewise linear in x and the new cuts are its world-quantiles.
+// Afterwards the next gsc_group_update_transforms must carry rotation and scale again (the group keeps no copy of the
+// engine's transform arrays).
+int gsc_group_rebalance(gsc_group *g, uint32_t n_pos, const float *pos3)
 {
     if (!g) return GSC_ERR_INVALID;
     if (!g->have_colliders) return gfail(g, GSC_ERR_INVALID, "gsc_group_rebalance before gsc_group_upload_colliders");
+    if (n_pos != g->n || (n_pos && !pos3)) return gfail(g, GSC_ERR_INVALID, "gsc_group_rebalance: positions of all %u colliders are needed", g->n);
     const uint32_t world = (uint32_t)g->m.size(), n = g->n;
     if (world < 2 || n == 0) return GSC_OK;
     float xmin = INFINITY, xmax = -INFINITY;
     for (uint32_t i = 0; i < n; ++i) {
-        const float x = g->last_pos[3 * (size_t)i];
+        const float x = pos3[3 * (size_t)i];
         xmin = std::min(xmin, x);
         xmax = std::max(xmax, x);
     }
@@ -340,7 +333,7 @@ int gsc_group_rebalance(gsc_group *g)
     edge[world] = xmax;
     for (uint32_t r = 1; r < world; ++r) edge[r] = std::min<double>(std::max<double>(g->cuts[r - 1], xmin), xmax);
     std::vector<uint64_t> count(world, 0);
-    for (uint32_t i = 0; i < n; ++i) ++count[owner_of(g->cuts, g->last_pos[3 * (size_t)i])];
+    for (uint32_t i = 0; i < n; ++i) ++count[owner_of(g->cuts, pos3[3 * (size_t)i])];
     for (uint32_t r = 0; r < world; ++r) {
         const gsc_step_out &o = g->last[r];
         const double cands = (double)(o.n_sphere_sphere + o.n_sphere_obb + o.n_obb_obb);
@@ -361,9 +354,7 @@ int gsc_group_rebalance(gsc_group *g)
     }
     std::sort(cuts.begin(), cuts.end());
     g->cuts = cuts;
-    if (int rc = group_distribute(g, g->last_pos.data())) return rc;
-    if (!g->last_quat.empty()) return group_scatter(g, g->last_pos.data(), g->last_quat.data(), g->last_scale.data());
-    return GSC_OK;  // (no rotations were ever sent: the caller provides the next frame's transforms in full)
+    return group_distribute(g, pos3);
 }
 
 // Temporal coherence behind the group: every member's dense arrays go into the cell order of the step that just
@@ -382,8 +373,7 @@ int gsc_group_reorder(gsc_group *g)
         own.swap(moved);
         g->rot_sent[r] = 0;
     }
-    g->have_transforms = false;
-    if (!g->last_quat.empty()) return group_scatter(g, g->last_pos.data(), g->last_quat.data(), g->last_scale.data());
+    g->have_transforms = false;  // the next gsc_group_update_transforms carries rotation and scale again
     return GSC_OK;
 }
 

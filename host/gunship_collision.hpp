@@ -339,8 +339,8 @@ public:
         collisions.clear();
         for (size_t i = 0; i < (size_t)n; ++i) collisions.insert({ pairs_[2 * i], pairs_[2 * i + 1] });
     }
-    // migrants: re-cut the slabs from the last frame's positions and the last step's work
-    void rebalance() { check(gsc_group_rebalance(group_)); }
+    // migrants: re-cut the slabs from the current positions (dense order) and the last step's work
+    void rebalance(const std::vector<float> &pos3) { check(gsc_group_rebalance(group_, n_, pos3.data())); }
     // temporal coherence: the slabs keep their colliders in the cell order of the last update
     void reorder() { check(gsc_group_reorder(group_)); }
 

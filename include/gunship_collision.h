@@ -364,7 +364,8 @@ int gsc_slab_step_begin(gsc_ctx *ctx);
  * order; the group scatters them to the slabs (pinned staging per member), steps all members with the device-driven
  * exchange above (ordered by stream events, so members may even share a GPU) and returns the union of the members'
  * pair lists, which IS the single-GPU pair set (no cross-rank dedupe).  gsc_group_rebalance re-cuts the slabs from
- * the last frame's positions and the per-slab work of the last step (colliders + candidate pairs; migrants change owner; SURVEY 8e collectives 2 and 3). */
+ * the current positions and the per-slab work of the last step (colliders + candidate pairs; migrants change owner;
+ * SURVEY 8e collectives 2 and 3). */
 typedef struct gsc_group gsc_group;
 int  gsc_group_create(uint32_t n_devices, const int32_t *devices, const gsc_config *cfg, gsc_group **out);
 void gsc_group_destroy(gsc_group *group);
@@ -376,7 +377,10 @@ int gsc_group_update_transforms(gsc_group *group, uint32_t n, const float *pos3,
 /* total: sums over the members (stage_ms / step_ms: max over members; d_pairs / d_contacts NULL) */
 int gsc_group_step(gsc_group *group, gsc_step_out *total);
 int gsc_group_download_pairs(gsc_group *group, uint32_t *dst, uint64_t cap_pairs, int sorted, uint64_t *n_out);
-int gsc_group_rebalance(gsc_group *group);
+/* re-cut the slabs by the work of the last step; pos3 = the CURRENT positions of all n colliders (dense order), which
+ * decide the new owners.  After gsc_group_rebalance and after gsc_group_reorder the next gsc_group_update_transforms must
+ * carry rotation and scale again (the group keeps no copy of the engine's transform arrays). */
+int gsc_group_rebalance(gsc_group *group, uint32_t n, const float *pos3);
 /* temporal coherence behind the group: every member keeps its colliders in the cell order of the step that just
  * completed (gsc_reorder_colliders); the engine keeps handing over dense arrays in ITS order */
 int gsc_group_reorder(gsc_group *group);

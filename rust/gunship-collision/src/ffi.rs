@@ -139,7 +139,7 @@ extern "C" {
                                        scale3: *const f32) -> c_int;
     pub fn gsc_group_step(group: *mut gsc_group, total: *mut gsc_step_out) -> c_int;
     pub fn gsc_group_download_pairs(group: *mut gsc_group, dst: *mut u32, cap_pairs: u64, sorted: c_int, n_out: *mut u64) -> c_int;
-    pub fn gsc_group_rebalance(group: *mut gsc_group) -> c_int;
+    pub fn gsc_group_rebalance(group: *mut gsc_group, n: u32, pos3: *const f32) -> c_int;
     pub fn gsc_group_reorder(group: *mut gsc_group) -> c_int;
     pub fn gsc_group_member(group: *mut gsc_group, i: u32, ctx: *mut *mut gsc_ctx, n_local: *mut u32, owned: *mut u32) -> c_int;
     // pinned transform staging

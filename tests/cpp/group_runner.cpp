@@ -62,7 +62,7 @@ int main(int argc, char **argv)
             std::fwrite(&np, 8, 1, o);
             std::fwrite(&gh, 8, 1, o);
             std::fwrite(packed.data(), 8, packed.size(), o);
-            if (fr == n_frames / 2) system.rebalance();
+            if (fr == n_frames / 2) system.rebalance(pos[fr]);
         }
         std::fclose(o);
         std::printf("group_runner: ok, %zu devices, cell %.7f\n", devices.size(), system.cell_size);

@@ -42,6 +42,8 @@ def test_group_union_is_the_single_gpu_pair_set(cfg, n, world):
             assert np.array_equal(np.sort(grp.pairs_packed(sorted=False)), want)
             if f == 1:
                 grp.reorder()       # members switch to the cell order of this frame; the dense interface does not change
+                with pytest.raises(G.GscError):
+                    grp.step()      # (transforms have to be handed over again, in full)
     oracle.close()
 
 
@@ -81,9 +83,12 @@ def test_migrants_and_rebalance_over_fifty_frames():
                 assert out.n_pairs == len(want) and np.array_equal(grp.pairs_packed(sorted=True), want), f
             if f % 10 == 9:
                 ghosts_before = out.n_ghost
-                grp.rebalance()
+                grp.rebalance(pos)
                 counts = grp.member_counts()
                 assert sum(counts) == n
+                with pytest.raises(G.GscError):
+                    grp.update_transforms(pos)                               # the new owners need rotation and scale again
+                grp.update_transforms(pos, quat, s.scale)
                 out2 = grp.step()                                            # same frame, new ownership: same set
                 want = oracle.step(s, pos, quat)
                 assert np.array_equal(grp.pairs_packed(sorted=True), want), f

@@ -25,6 +25,7 @@ with G.CollisionGroup([0, 0], 30000) as grp:
     out = grp.step()
     assert np.array_equal(grp.pairs_packed(sorted=True), want)
     grp.reorder()
+    grp.update_transforms(s.pos, s.quat, s.scale)
     grp.step()
     assert np.array_equal(grp.pairs_packed(sorted=True), want)
     print("group of 2: ok,", out.n_ghost, "ghosts")
