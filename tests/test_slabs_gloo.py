@@ -91,3 +91,26 @@ def test_partition_x_slabs_is_balanced_and_ordered():
         for r in range(world - 1):
             assert x[owner == r].max() <= x[owner == r + 1].min()
     assert slabs.needed_range(5, 9) == (4, 9)
+
+
+def test_weighted_slab_partition_balances_the_estimated_work():
+    """partition_x_slabs(x, world, weight): cuts at equal cumulative weight along x; pair_work_estimate: 26 + 9 x cell
+    occupancy (what bench.py starts its slab calibration from)"""
+    import numpy as np
+    from gunship_rs_b200 import scenes, slabs
+    s = scenes.by_config(4, 60000)
+    w = slabs.pair_work_estimate(s.pos, s.cell_hint)
+    assert w.shape == (s.n,) and w.min() >= 35.0          # a collider always shares its own cell with itself
+    # occupancy really is the number of colliders with the same home cell
+    cell = np.floor(s.pos.astype(np.float64) / s.cell_hint).astype(np.int64)
+    i = int(np.argmax(w))
+    same = int(np.all(cell == cell[i], axis=1).sum())
+    assert w[i] == 26.0 + 9.0 * same and same > 1
+    for world in (2, 4, 8):
+        owner = slabs.partition_x_slabs(s.pos[:, 0], world, w)
+        share = np.array([w[owner == r].sum() for r in range(world)]) / w.sum()
+        assert np.all(np.abs(share - 1.0 / world) < 0.01)     # equal work ...
+        xs = [s.pos[owner == r, 0] for r in range(world)]
+        assert all(xs[r].max() <= xs[r + 1].min() for r in range(world - 1))   # ... in x-slabs
+        count = slabs.partition_x_slabs(s.pos[:, 0], world)
+        assert np.bincount(count, minlength=world).max() - np.bincount(count, minlength=world).min() <= 1
