@@ -489,7 +489,8 @@ constexpr uint32_t kMetaReachY = 4u, kMetaReachZ = 8u;
 // hold the three differences each, and the boxes overlap on every axis  <=>  no field of t1 or t2 is negative
 //   <=>  ((t1 | t2) & kQSign) == 0:
 // two subtractions and one logic op per candidate instead of six compares.  Exact overlap always implies quantised
-// overlap (never a false negative; the f32 error of t is below the margin); the exact test runs on the survivors only.
+// overlap (never a false negative; the f32 error of t is below the margin); the exact test runs on the survivors only
+// (in the SAT stage, k_narrow).
 constexpr uint32_t kQGuard = (1u << 10) | (1u << 21) | (1u << 31);
 constexpr uint32_t kQSign = (1u << 9) | (1u << 20) | (1u << 30);
 
@@ -511,7 +512,7 @@ GSC_DEV uint32_t quant_pack(uint32_t x, uint32_t y, uint32_t z)
     return (x & 1023u) | ((y & 1023u) << 11) | ((z & 511u) << 22);
 }
 
-// ---- stage 3: cell start table + cell-order permutation of the volume records ---------------------
+// ---- stage 3: cell start table + the cell-ordered 12 B pair records (quantised box, ordering word) ----
 // start[c] = first sorted position whose key >= c, for c in [0, num_cells]; thread p fills the gap
 // (key[p-1], key[p]].  Long gaps (empty space) are filled by the whole warp.
 constexpr int kTableThreads = 256;
