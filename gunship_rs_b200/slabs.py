@@ -99,6 +99,13 @@ class ShmControl:
 
     TIMEOUT_S = float(os.environ.get("GSC_CONTROL_TIMEOUT_S", "60"))
 
+    @staticmethod
+    def usable():
+        """The publish below is 'payload, then sequence number' through plain numpy stores: correct on hosts that keep
+        store order (x86).  Anywhere else (aarch64: Grace) the driver falls back to torch.distributed collectives."""
+        import platform
+        return platform.machine().lower() in ("x86_64", "amd64", "i686", "i386")
+
     def all_gather(self, values):
         """(x86 only: the sequence number is published after the payload and relies on the store order of the
         platform; the default exchange -- GSC_EXCHANGE=device -- does not use this class at all)"""
@@ -180,7 +187,7 @@ class SlabDriver:
         if os.environ.get("GSC_EXCHANGE", "device") == "device" and hasattr(be, "slab_init") and distinct:
             be.slab_init(self.rank, self.world)
             self.device_exchange = True
-        elif os.environ.get("GSC_CONTROL", "shm") == "shm":
+        elif os.environ.get("GSC_CONTROL", "shm") == "shm" and ShmControl.usable():
             self.shm = ShmControl(dist, self.group, self.rank, self.world)  # same box: host control plane
 
     def _t(self, name, t0):

@@ -27,7 +27,7 @@ fn main() {
     println!("cargo:rustc-link-search=native=/usr/local/cuda/lib64");
     println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rustc-link-lib=dylib=stdc++");
-    for f in &["gsc_api.cu", "gsc_kernels.cuh", "gsc_pairs.cuh", "gsc_sort.cuh", "gsc_math.cuh", "gsc_hierarchy.cuh"] {
+    for f in &["gsc_api.cu", "gsc_kernels.cuh", "gsc_pairs.cuh", "gsc_sort.cuh", "gsc_math.cuh", "gsc_hierarchy.cuh", "gsc_group.cuh"] {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
     println!("cargo:rerun-if-changed={}", root.join("include/gunship_collision.h").display());
