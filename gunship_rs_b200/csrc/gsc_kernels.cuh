@@ -250,8 +250,8 @@ k_bvh_update(uint32_t first, uint32_t n, const uint8_t *__restrict__ kind, const
             const float r = size3[3 * i];  // mod.rs:316 radius is not scaled
             mn[0] = sub(cx, r); mn[1] = sub(cy, r); mn[2] = sub(cz, r);
             mx[0] = add(cx, r); mx[1] = add(cy, r); mx[2] = add(cz, r);
-            rec[2 * (size_t)i] = make_float4(cx, cy, cz, r);
-            rec[2 * (size_t)i + 1] = make_float4(__uint_as_float(e), 0.0f, __uint_as_float(g), __uint_as_float(i << 4));
+            st256(rec + 2 * (size_t)i, make_float4(cx, cy, cz, r),
+                  make_float4(__uint_as_float(e), 0.0f, __uint_as_float(g), __uint_as_float(i << 4)));
         } else if (k == 1) {
             Obb o;
             // mod.rs:320  half_widths = widths * scale * 0.5
@@ -264,13 +264,13 @@ k_bvh_update(uint32_t first, uint32_t n, const uint8_t *__restrict__ kind, const
             quat_to_mat3(q.x, q.y, q.z, q.w, o.m);  // mod.rs:322
             obb_aabb_fast(o, mn, mx);  // == the 8-vertex walk of bounding_volume.rs:161-327, bit for bit
             obb_store(obb + 4 * (size_t)i, o, e);
-            rec[2 * (size_t)i] = make_float4(mn[0], mn[1], mn[2], mx[0]);
-            rec[2 * (size_t)i + 1] = make_float4(mx[1], mx[2], __uint_as_float(g), __uint_as_float((i << 4) | kMetaBox));
+            st256(rec + 2 * (size_t)i, make_float4(mn[0], mn[1], mn[2], mx[0]),
+                  make_float4(mx[1], mx[2], __uint_as_float(g), __uint_as_float((i << 4) | kMetaBox)));
         } else {
             st |= kStMesh;  // mod.rs:331 unimplemented!()
             // keep the record decodable: a zero-size sphere far away is never produced; mark and bail
-            rec[2 * (size_t)i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            rec[2 * (size_t)i + 1] = make_float4(__uint_as_float(e), 0.0f, __uint_as_float(g), __uint_as_float(i << 4));
+            st256(rec + 2 * (size_t)i, make_float4(0.f, 0.f, 0.f, 0.f),
+                  make_float4(__uint_as_float(e), 0.0f, __uint_as_float(g), __uint_as_float(i << 4)));
             mn[0] = mn[1] = mn[2] = mx[0] = mx[1] = mx[2] = 0.0f;
         }
         // bounding_volume.rs:365-381: longest_axis = max(0, every diff), strict > from 0.0
@@ -436,7 +436,8 @@ k_cell_keys(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const float4 *__
     for (int j = 0; j < kSortTile / kKeyThreads; ++j) {
         const uint32_t i = tile_base + j * kKeyThreads + tid;
         if (i >= n_total) break;
-        const Volume v = volume_decode(__ldg(rec + 2 * (size_t)i), __ldg(rec + 2 * (size_t)i + 1));
+        const F8 rv = ld256(rec + 2 * (size_t)i);
+        const Volume v = volume_decode(rv.lo, rv.hi);
         int c0[3], c1[3];
         const bool wide = home_cell(v, g, c0, c1);
         uint32_t key;
@@ -541,7 +542,8 @@ k_cell_table_permute(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const u
     const uint32_t klo = p == 0 ? 0u : (p - 1 < n_total ? min(keys[p - 1], C) : C) + 1u;
     if (p < n_total) {
         const uint32_t i = vals[p];
-        const Volume v = volume_decode(ldg_gather(rec + 2 * (size_t)i), ldg_gather(rec + 2 * (size_t)i + 1));
+        const F8 rv = ld256_gather(rec + 2 * (size_t)i);
+        const Volume v = volume_decode(rv.lo, rv.hi);
         uint32_t meta = v.meta;
         if (cell_coord_f(v.mx[1], g.cell_size) > cell_coord_f(v.mn[1], g.cell_size)) meta |= kMetaReachY;
         if (cell_coord_f(v.mx[2], g.cell_size) > cell_coord_f(v.mn[2], g.cell_size)) meta |= kMetaReachZ;
@@ -680,7 +682,8 @@ k_narrow(const uint2 *__restrict__ cand_ss, const uint2 *__restrict__ cand_so, c
                     const bool hi_is_sphere = c.x >> 31;
                     const uint32_t hi = c.x & 0x7fffffffu, lo = c.y;
                     const uint32_t si = hi_is_sphere ? hi : lo, oi = hi_is_sphere ? lo : hi;
-                    const float4 s0 = ldg_gather(rec + 2 * (size_t)si), s1 = ldg_gather(rec + 2 * (size_t)si + 1);
+                    const F8 sr = ld256_gather(rec + 2 * (size_t)si);
+                    const float4 s0 = sr.lo, s1 = sr.hi;
                     uint32_t oe;
                     const Obb o = obb_load(obb + 4 * (size_t)oi, &oe);
                     float omn[3], omx[3];
@@ -693,14 +696,23 @@ k_narrow(const uint2 *__restrict__ cand_ss, const uint2 *__restrict__ cand_so, c
                     item = hi_is_sphere ? make_uint2(se, oe) : make_uint2(oe, se);
                     if (CONTACTS && hit) ct = contact_sphere_obb(s0.x, s0.y, s0.z, s0.w, o, hi_is_sphere);
                 } else {  // Sphere::test_sphere (mod.rs:383-389)
+#ifndef GSC_NO_LDST256
+                    const F8 hr = ld256_gather(rec + 2 * (size_t)c.x), lr = ld256_gather(rec + 2 * (size_t)c.y);
+                    const float4 h0 = hr.lo, l0 = lr.lo;
+#else
                     const float4 h0 = ldg_gather(rec + 2 * (size_t)c.x), l0 = ldg_gather(rec + 2 * (size_t)c.y);
+#endif
                     const float hmn[3] = { sub(h0.x, h0.w), sub(h0.y, h0.w), sub(h0.z, h0.w) };
                     const float hmx[3] = { add(h0.x, h0.w), add(h0.y, h0.w), add(h0.z, h0.w) };
                     const float lmn[3] = { sub(l0.x, l0.w), sub(l0.y, l0.w), sub(l0.z, l0.w) };
                     const float lmx[3] = { add(l0.x, l0.w), add(l0.y, l0.w), add(l0.z, l0.w) };
                     hit = test_aabb(hmn, hmx, lmn, lmx) && test_sphere_sphere(h0.x, h0.y, h0.z, h0.w, l0.x, l0.y, l0.z, l0.w);
                     if (hit) {
+#ifndef GSC_NO_LDST256
+                        const float4 h1 = hr.hi, l1 = lr.hi;  // (the entity ids came with the same 32 B access)
+#else
                         const float4 h1 = ldg_gather(rec + 2 * (size_t)c.x + 1), l1 = ldg_gather(rec + 2 * (size_t)c.y + 1);
+#endif
                         item = make_uint2(__float_as_uint(h1.x), __float_as_uint(l1.x));
                         if (CONTACTS) ct = contact_sphere_sphere(h0.x, h0.y, h0.z, h0.w, l0.x, l0.y, l0.z, l0.w);
                     }
