@@ -162,6 +162,39 @@ k_radix_scan(uint32_t *__restrict__ tile_hist, uint32_t num_tiles, int pass, con
     if (tid == 0) digit_total[blockIdx.x] = carry;
 }
 
+// Stable ranking of a warp's kSortIpt x 32 keys by their digit: order is (j, lane) == original order.  Peers = the
+// lanes holding the same digit, from one ballot per digit bit (MATCH.ANY serialises over the distinct values of the
+// warp and was measured ~50 cycles per instruction and SM).  A digit narrower than BITS only adds ballots of zeros.
+template <int BITS>
+__device__ __forceinline__ void radix_rank(const uint32_t (&key)[kSortIpt], int shift, uint32_t mask, uint32_t *hist /* this warp's */,
+                                           int lane, uint16_t (&rank)[kSortIpt])
+{
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int j = 0; j < kSortIpt; ++j) {
+        const uint32_t d = (key[j] >> shift) & mask;
+        uint32_t peers = 0xffffffffu;
+#pragma unroll
+        for (int b = 0; b < BITS; ++b) {
+            // peers &= (my bit b is set) ? ballot : ~ballot -- as four instructions (LOP3 to a predicate, VOTE, SEL, LOP3);
+            // written in C++ the compiler derives the ballot predicate and the select mask separately (six)
+            asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t, bal, m;\n\t"
+                "and.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\t"
+                "vote.sync.ballot.b32 bal, p, 0xffffffff;\n\t"
+                "selp.b32 m, 0, 0xffffffff, p;\n\t"
+                "lop3.b32 %0, %0, bal, m, 0x60;\n\t}"
+                : "+r"(peers)
+                : "r"(d), "r"(1u << b));
+        }
+        const uint32_t before = hist[d];
+        const uint32_t r = __popc(peers & lt_mask);
+        __syncwarp();
+        if (r == 0) hist[d] = before + __popc(peers);
+        __syncwarp();
+        rank[j] = (uint16_t)(before + r);
+    }
+}
+
 // grid = num_tiles CTAs of kSortThreads threads, 64 registers (4 CTAs = 32 warps per SM).
 //   keys_in/vals_in -> keys_out/vals_out; vals_in == nullptr means "value = position" (first pass).
 // ncu (round 1): this kernel is bound by the shared-memory / MIO pipe (mio_throttle + short_scoreboard), not by
@@ -218,8 +251,19 @@ k_radix_downsweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
     // peers = lanes holding the same digit, from one ballot per significant digit bit (MATCH.ANY serialises over
     // the distinct values of the warp and was measured ~50 cycles per instruction and SM)
     const int digit_bits = min(ctl->digit_bits, ctl->key_bits - shift);
-    const uint32_t lt_mask = (1u << lane) - 1u;
     uint16_t rank[kSortIpt];
+#ifndef GSC_SORT_RANK_GENERIC
+    // the ballot loop is unrolled for the digit width at hand (grid-uniform): nine run-time "is this bit in use"
+    // predicates kept the predicate file full and made the compiler re-create every ballot predicate from a register
+#ifdef GSC_SORT_RANK9_ONLY
+    radix_rank<9>(key, shift, mask, s_hist[warp], lane, rank);
+#else
+    if (digit_bits == 9) radix_rank<9>(key, shift, mask, s_hist[warp], lane, rank);
+    else if (digit_bits == 8) radix_rank<8>(key, shift, mask, s_hist[warp], lane, rank);
+    else radix_rank<7>(key, shift, mask, s_hist[warp], lane, rank);  // (<= 7 bits: the extra ballots see zeros)
+#endif
+#else
+    const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
     for (int j = 0; j < kSortIpt; ++j) {
         const uint32_t d = (key[j] >> shift) & mask;
@@ -239,6 +283,7 @@ k_radix_downsweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
         __syncwarp();
         rank[j] = (uint16_t)(before + r);
     }
+#endif
     __syncthreads();
 
     // ---- per digit pair (thread t owns digits 2t, 2t+1): warp counts -> offsets within the digit, tile counts ----
