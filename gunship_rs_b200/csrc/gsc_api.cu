@@ -718,7 +718,7 @@ static int stage_launches(gsc_ctx *c, bool slab, bool timing)
         launch_sort(s, n_total, c->d_keys, c->d_vals, true, std::min(kMaxPasses, radix_passes(key_bits_max)), &fb->sort,
                     c->d_sort_scratch, true, n_dev);
         if (timing) CU(c, cudaEventRecord(c->ev[3], s));
-        const uint32_t tb = (n_total + 1 + kTableThreads - 1) / kTableThreads;
+        const uint32_t tb = (n_total + 1 + kTableSpan - 1) / kTableSpan;
         SortedVolumes sv{ c->d_qrec_sorted, c->d_w3_sorted };
         k_cell_table_permute<<<tb, kTableThreads, 0, s>>>(n_total, n_dev, c->d_keys[0], c->d_vals[0], c->d_keys[1], c->d_vals[1],
                                                          c->d_rec, sv, c->d_cell_start, c->d_gaps, fb);

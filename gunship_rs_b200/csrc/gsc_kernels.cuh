@@ -517,50 +517,26 @@ GSC_DEV uint32_t quant_pack(uint32_t x, uint32_t y, uint32_t z)
 // start[c] = first sorted position whose key >= c, for c in [0, num_cells]; thread p fills the gap
 // (key[p-1], key[p]].  Long gaps (empty space) are filled by the whole warp.
 constexpr int kTableThreads = 256;
+#ifndef GSC_TABLE_IPT
+#define GSC_TABLE_IPT 2
+#endif
+#ifndef GSC_TABLE_MIN_CTAS
+#define GSC_TABLE_MIN_CTAS 6  // measured at 16M (slot order): 1 position per thread 0.290 ms; 2 positions 0.284 (48 registers,
+#endif                        // 5 CTAs), 0.249 with 6 resident CTAs (40 registers); 4 positions 0.275 (72 registers)
+constexpr int kTableIpt = GSC_TABLE_IPT;  // sorted positions per thread: their record gathers are in flight together
+constexpr int kTableSpan = kTableThreads * kTableIpt;  // positions per CTA
 constexpr int kGapLong = 1 << 14;  // empty-cell runs longer than this are filled by the whole grid
 constexpr int kGapCap = 4096;
 constexpr int kWarpFillMax = 4096;  // cells a warp fills transposed; wider spans (rare) go gap by gap
 
-__global__ void __launch_bounds__(kTableThreads)
-k_cell_table_permute(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ vals_a,
-                     const uint32_t *__restrict__ keys_b, const uint32_t *__restrict__ vals_b,
-                     const float4 *__restrict__ rec, SortedVolumes sv,
-                     uint32_t *__restrict__ cell_start, uint4 *__restrict__ gaps, FrameBlock *__restrict__ fb)
+// start[] for the cells the warp's 32 consecutive positions own: lane's position p owns the key gap (klo, kcur]
+GSC_DEV void table_fill_warp(uint32_t p, uint32_t klo, uint32_t kcur, int lane, uint32_t C, uint32_t n_total,
+                             uint32_t *__restrict__ cell_start, uint4 *__restrict__ gaps, FrameBlock *__restrict__ fb)
 {
-    const GridParams g = fb->grid;
-    if (!g.valid) return;
-    const uint32_t n_total = n_dev ? min(*n_dev, n_cap) : n_cap;
-    if (blockIdx.x * (uint32_t)kTableThreads > n_total) return;  // (position n_total itself closes the table)
-    const bool in_b = fb->sort.num_passes & 1;  // ping-pong parity of the sort
-    const uint32_t *keys = in_b ? keys_b : keys_a;
-    const uint32_t *vals = in_b ? vals_b : vals_a;
-    const uint32_t p = blockIdx.x * kTableThreads + threadIdx.x;  // p in [0, n_total]
-    const uint32_t C = g.num_cells;
-    // thread p fills start[] for the cells of the key gap (key[p-1], key[p]] (keys clamped to C; positions behind
-    // n_total count as key C, so their gaps are empty and the kernel needs no tail special case)
-    const uint32_t kcur = p < n_total ? min(keys[p], C) : C;
-    const uint32_t klo = p == 0 ? 0u : (p - 1 < n_total ? min(keys[p - 1], C) : C) + 1u;
-    if (p < n_total) {
-        const uint32_t i = vals[p];
-        const F8 rv = ld256_gather(rec + 2 * (size_t)i);
-        const Volume v = volume_decode(rv.lo, rv.hi);
-        uint32_t meta = v.meta;
-        if (cell_coord_f(v.mx[1], g.cell_size) > cell_coord_f(v.mn[1], g.cell_size)) meta |= kMetaReachY;
-        if (cell_coord_f(v.mx[2], g.cell_size) > cell_coord_f(v.mn[2], g.cell_size)) meta |= kMetaReachZ;
-        const uint32_t wmin = quant_pack(quant_lo(v.mn[0], g.qorg[0], g.qscale[0], g.qmargin),
-                                         quant_lo(v.mn[1], g.qorg[1], g.qscale[1], g.qmargin),
-                                         quant_lo(v.mn[2], g.qorg[2], g.qscale[2], g.qmargin));
-        const uint32_t wmax = quant_pack(quant_hi(v.mx[0], g.qorg[0], g.qscale[0], g.qmargin),
-                                         quant_hi(v.mx[1], g.qorg[1], g.qscale[1], g.qmargin),
-                                         quant_hi(v.mx[2], g.qorg[2], g.qscale[2], g.qmargin));
-        sv.q[p] = make_uint2(wmin, wmax | kQGuard);
-        sv.w3[p] = (v.gidx << 4) | (meta & 15u);
-    }
     // The warp's 32 positions own the contiguous cells [first, last].  Normally the warp fills them TRANSPOSED: lane l
     // takes cells first + l, first + 32 + l, ... and finds each cell's start -- position of the first key >= the
     // cell -- by a 5-step binary search over the warp's sorted keys (shuffles).  32 cells per trip whatever the gap
     // sizes, instead of every lane walking its own gap (sparse space: 20-cell gaps in every lane, 32 serial loops).
-    const int lane = threadIdx.x & 31;
     const uint32_t first = __shfl_sync(0xffffffffu, klo, 0), last = __shfl_sync(0xffffffffu, kcur, 31);
     const uint32_t span = last + 1u - first;  // >= 0: klo of lane 0 <= its key + 1 <= last + 1
     if (span <= (uint32_t)kWarpFillMax) {
@@ -600,6 +576,55 @@ k_cell_table_permute(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const u
         const uint32_t sp = __shfl_sync(0xffffffffu, p, src);
         for (int64_t c = slo + lane; c <= shi; c += 32) cell_start[c] = sp;
     }
+}
+
+__global__ void __launch_bounds__(kTableThreads, GSC_TABLE_MIN_CTAS)
+k_cell_table_permute(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const uint32_t *__restrict__ keys_a, const uint32_t *__restrict__ vals_a,
+                     const uint32_t *__restrict__ keys_b, const uint32_t *__restrict__ vals_b,
+                     const float4 *__restrict__ rec, SortedVolumes sv,
+                     uint32_t *__restrict__ cell_start, uint4 *__restrict__ gaps, FrameBlock *__restrict__ fb)
+{
+    const GridParams g = fb->grid;
+    if (!g.valid) return;
+    const uint32_t n_total = n_dev ? min(*n_dev, n_cap) : n_cap;
+    if (blockIdx.x * (uint32_t)kTableSpan > n_total) return;  // (position n_total itself closes the table)
+    const bool in_b = fb->sort.num_passes & 1;  // ping-pong parity of the sort
+    const uint32_t *keys = in_b ? keys_b : keys_a;
+    const uint32_t *vals = in_b ? vals_b : vals_a;
+    const uint32_t C = g.num_cells;
+    // thread positions p in [0, n_total]; position p fills start[] for the cells of the key gap (key[p-1], key[p]]
+    // (keys clamped to C; positions behind n_total count as key C, so their gaps are empty and the kernel needs no
+    // tail special case).  A thread takes kTableIpt positions kTableThreads apart and has their record gathers -- the
+    // one latency-bound access of the kernel -- in flight together.
+    uint32_t p[kTableIpt], kcur[kTableIpt], klo[kTableIpt];
+    F8 rv[kTableIpt];
+#pragma unroll
+    for (int u = 0; u < kTableIpt; ++u) {
+        p[u] = blockIdx.x * (uint32_t)kTableSpan + u * kTableThreads + threadIdx.x;
+        kcur[u] = p[u] < n_total ? min(keys[p[u]], C) : C;
+        klo[u] = p[u] == 0 ? 0u : (p[u] - 1 < n_total ? min(keys[p[u] - 1], C) : C) + 1u;
+        if (p[u] < n_total) rv[u] = ld256_gather(rec + 2 * (size_t)vals[p[u]]);
+    }
+#pragma unroll
+    for (int u = 0; u < kTableIpt; ++u) {
+        if (p[u] < n_total) {
+            const Volume v = volume_decode(rv[u].lo, rv[u].hi);
+            uint32_t meta = v.meta;
+            if (cell_coord_f(v.mx[1], g.cell_size) > cell_coord_f(v.mn[1], g.cell_size)) meta |= kMetaReachY;
+            if (cell_coord_f(v.mx[2], g.cell_size) > cell_coord_f(v.mn[2], g.cell_size)) meta |= kMetaReachZ;
+            const uint32_t wmin = quant_pack(quant_lo(v.mn[0], g.qorg[0], g.qscale[0], g.qmargin),
+                                             quant_lo(v.mn[1], g.qorg[1], g.qscale[1], g.qmargin),
+                                             quant_lo(v.mn[2], g.qorg[2], g.qscale[2], g.qmargin));
+            const uint32_t wmax = quant_pack(quant_hi(v.mx[0], g.qorg[0], g.qscale[0], g.qmargin),
+                                             quant_hi(v.mx[1], g.qorg[1], g.qscale[1], g.qmargin),
+                                             quant_hi(v.mx[2], g.qorg[2], g.qscale[2], g.qmargin));
+            sv.q[p[u]] = make_uint2(wmin, wmax | kQGuard);
+            sv.w3[p[u]] = (v.gidx << 4) | (meta & 15u);
+        }
+    }
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int u = 0; u < kTableIpt; ++u) table_fill_warp(p[u], klo[u], kcur[u], lane, C, n_total, cell_start, gaps, fb);
 }
 
 __global__ void __launch_bounds__(256)
