@@ -456,7 +456,7 @@ def main():
                      "frac": achieved / peak, "traffic": traffic["bytes"] if traffic else None,
                      "traffic_source": traffic["source"] if traffic else None, "peak_kind": peak_kind,
                      "alg_bytes_per_launch": sb[dom_name] / launches_in_stage, "launches_per_step": launches_in_stage,
-                     "note": ("k_pairs is not HBM bound (ncu r02b: L1 data pipe 78%, issue 59%, 17/32 lanes in its loop); the HBM "
+                     "note": ("k_pairs is not HBM bound (ncu r02e: L1 data pipe 85%, issue 67%, 20/32 lanes active); the HBM "
                               "fraction is reported because the contract asks for it" if dom_name == "pairs" else ""),
                      "step_alg_bytes": int(total_bytes), "step_frac": total_bytes / (np.mean(dev_ms) * 1e-3) / 1e9 / peak},
         "stages": stages,
