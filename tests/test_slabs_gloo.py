@@ -114,3 +114,52 @@ def test_weighted_slab_partition_balances_the_estimated_work():
         assert all(xs[r].max() <= xs[r + 1].min() for r in range(world - 1))   # ... in x-slabs
         count = slabs.partition_x_slabs(s.pos[:, 0], world)
         assert np.bincount(count, minlength=world).max() - np.bincount(count, minlength=world).min() <= 1
+
+
+def _control_worker(rank, world, port, mode, out_dir):
+    """rank 1 leaves the protocol (abort flag, or simply never arrives); rank 0 must not spin forever"""
+    sys.path.insert(0, ROOT)
+    import time
+    import torch.distributed as dist
+    from gunship_rs_b200 import slabs
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    if mode == "timeout":
+        slabs.ShmControl.TIMEOUT_S = 1.0
+    ctl = slabs.ShmControl(dist, None, rank, world)
+    first = ctl.all_gather([float(rank + 1), 10.0 * (rank + 1)])       # a healthy round first
+    assert first.shape == (world, 2) and first[:, 0].tolist() == [1.0, 2.0]
+    ctl.barrier()
+    t0 = time.monotonic()
+    outcome = "returned"
+    if rank == 0:
+        try:
+            ctl.all_gather([1.0])
+        except RuntimeError as e:          # the peer aborted its step
+            outcome = "aborted: " + str(e)
+        except TimeoutError as e:          # the peer never arrived
+            outcome = "timeout: " + str(e)
+    elif mode == "abort":
+        time.sleep(0.3)                    # rank 0 is spinning by now
+        ctl.abort()
+    else:
+        time.sleep(2.5)                    # never joins the second round
+    with open(os.path.join(out_dir, f"o_{rank}.txt"), "w") as f:
+        f.write(f"{outcome}\n{time.monotonic() - t0:.3f}\n")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["abort", "timeout"])
+def test_control_plane_fails_together_instead_of_spinning(tmp_path, mode):
+    """a rank that leaves its step with an error (or dies) must take the others with it -- the spin on the
+    shared-memory control block has an abort flag and a deadline."""
+    import torch.multiprocessing as mp
+    from gunship_rs_b200 import slabs
+    if not slabs.ShmControl.usable():
+        pytest.skip("shared-memory control plane is x86 only")
+    mp.spawn(_control_worker, args=(2, _free_port(), mode, str(tmp_path)), nprocs=2, join=True)
+    outcome, dt = (tmp_path / "o_0.txt").read_text().splitlines()
+    if mode == "abort":
+        assert outcome.startswith("aborted: ") and float(dt) < 2.0
+    else:
+        assert outcome.startswith("timeout: ") and 0.9 <= float(dt) < 2.4
