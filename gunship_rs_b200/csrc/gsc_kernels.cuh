@@ -224,7 +224,10 @@ GSC_DEV void emit_finish(EmitBuf<WARPS, CAP> &b, uint2 *__restrict__ out, float4
 // bounds (needed to place the dense grid), reduced warp -> CTA -> one atomic per CTA.
 constexpr int kBvhThreads = 256;
 
-__global__ void __launch_bounds__(kBvhThreads, 6)
+#ifndef GSC_BVH_MIN_CTAS
+#define GSC_BVH_MIN_CTAS 8  // 6 (40 registers) / 8 (32 registers, 56 B of spills): 0.398 / 0.394 ms at 16M
+#endif
+__global__ void __launch_bounds__(kBvhThreads, GSC_BVH_MIN_CTAS)
 k_bvh_update(uint32_t first, uint32_t n, const uint8_t *__restrict__ kind, const float *__restrict__ offset3,
              const float *__restrict__ size3, const float *__restrict__ pos3, const float *__restrict__ quat4,
              const float *__restrict__ scale3, const uint32_t *__restrict__ entity,
@@ -412,7 +415,10 @@ constexpr int kKeyThreads = 256;
 
 // One CTA per sort tile (kSortTile volumes), so that the digit counts of the FIRST radix pass come for free:
 // tile_hist[d * num_tiles + tile] is what k_radix_upsweep would compute for pass 0.
-__global__ void __launch_bounds__(kKeyThreads)
+#ifndef GSC_KEYS_MIN_CTAS
+#define GSC_KEYS_MIN_CTAS 8  // 34 registers without a bound (7 CTAs) / 32 with (8 CTAs): 0.126 / 0.122 ms at 16M
+#endif
+__global__ void __launch_bounds__(kKeyThreads, GSC_KEYS_MIN_CTAS)
 k_cell_keys(uint32_t n_cap, const uint32_t *__restrict__ n_dev, const float4 *__restrict__ rec, uint32_t *__restrict__ keys,
             uint32_t *__restrict__ wide_list, uint32_t *__restrict__ tile_hist, FrameBlock *__restrict__ fb)
 {
@@ -521,8 +527,9 @@ constexpr int kTableThreads = 256;
 #define GSC_TABLE_IPT 2
 #endif
 #ifndef GSC_TABLE_MIN_CTAS
-#define GSC_TABLE_MIN_CTAS 6  // measured at 16M (slot order): 1 position per thread 0.290 ms; 2 positions 0.284 (48 registers,
-#endif                        // 5 CTAs), 0.249 with 6 resident CTAs (40 registers); 4 positions 0.275 (72 registers)
+#define GSC_TABLE_MIN_CTAS 7  // measured at 16M (slot order): 1 position per thread 0.290 ms; 2 positions 0.284 (48 registers,
+#endif                        // 5 CTAs), 0.249 with a bound of 6 CTAs (40 registers), 0.233 with 7 (32 registers: 8 CTAs
+                              // resident); 4 positions 0.275 (72 registers)
 constexpr int kTableIpt = GSC_TABLE_IPT;  // sorted positions per thread: their record gathers are in flight together
 constexpr int kTableSpan = kTableThreads * kTableIpt;  // positions per CTA
 constexpr int kGapLong = 1 << 14;  // empty-cell runs longer than this are filled by the whole grid
